@@ -1,0 +1,173 @@
+"""Generate the committed golden fixtures under tests/golden/ from the UNMODIFIED reference.
+
+Run in the build container (where /root/reference exists):   python -m oracle.make_golden
+TEST INFRASTRUCTURE -- not imported by the product path.  The reference ships no tests, checkpoints or golden
+vectors, so the pins are outputs of the live reference on seeded weights
+(`jen1_b200.weights.random_state_dict`, loaded with the reference's own `load_state_dict`) and seeded inputs.
+Weights are NOT stored (1.2 GB): fixtures hold seeds, inputs and reference outputs only.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import warnings
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+warnings.filterwarnings("ignore")
+
+from jen1_b200.config import UNetDesc, tiny_desc  # noqa: E402
+from jen1_b200.weights import random_state_dict  # noqa: E402
+from oracle import ref_import  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def desc_overrides(desc: UNetDesc) -> dict:
+    return dict(in_channels=desc.in_channels, channels=desc.channels, multipliers=list(desc.multipliers),
+                factors=list(desc.factors), num_blocks=list(desc.num_blocks), attentions=list(desc.attentions),
+                out_channels=desc.out_channels, context_channels=list(desc.context_channels),
+                context_embedding_features=desc.context_embedding_features,
+                context_embedding_max_length=desc.context_embedding_max_length,
+                attention_heads=desc.attention_heads, attention_multiplier=desc.attention_multiplier,
+                resnet_groups=desc.resnet_groups)
+
+
+def make_inputs(desc: UNetDesc, B: int, T: int, seed: int, masked_tail: int = 0):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, desc.in_channels, T, generator=g)
+    t = torch.randint(0, 1000, (B,), generator=g)
+    emb = torch.randn(B, desc.context_embedding_max_length, desc.context_embedding_features, generator=g)
+    mask = torch.ones(B, desc.context_embedding_max_length, dtype=torch.bool)
+    if masked_tail:
+        mask[:, -masked_tail:] = False
+        emb = emb * mask.unsqueeze(-1)  # T5Conditioner zeroes padded rows (conditioners.py:109)
+    cc = torch.randn(B, desc.context_channels[0], T, generator=g)
+    return x, t, emb, mask, cc
+
+
+VARIANTS = {
+    "plain": dict(embedding_scale=1.0),
+    "cfg": dict(embedding_scale=0.8, batch_cfg=True, scale_cfg=True, embedding_mask_proba=0.0),
+    "cfg_causal": dict(embedding_scale=0.8, batch_cfg=True, scale_cfg=True, embedding_mask_proba=0.0, causal=True),
+    "cfg_noscale": dict(embedding_scale=0.8, batch_cfg=True, scale_cfg=False, embedding_mask_proba=0.0),
+}
+
+
+def run_unet_cases(desc, model, cases):
+    out = {}
+    with torch.no_grad():
+        for name, (B, T, seed, masked_tail, variants) in cases.items():
+            x, t, emb, mask, cc = make_inputs(desc, B, T, seed, masked_tail)
+            rec = dict(B=B, T=T, seed=seed, masked_tail=masked_tail, outputs={})
+            for v in variants:
+                kw = dict(VARIANTS[v])
+                y = model(x, t, embedding=emb, embedding_mask=mask, features=None, channels_list=[cc], **kw)
+                rec["outputs"][v] = y.clone()
+            # one stochastic cond-dropout case: the reference draws bernoulli from the global RNG (model.py:325)
+            torch.manual_seed(1234 + seed)
+            y = model(x, t, embedding=emb, embedding_mask=mask, features=None, channels_list=[cc],
+                      embedding_scale=0.8, batch_cfg=True, scale_cfg=True, embedding_mask_proba=0.5)
+            rec["outputs"]["cfg_dropout_p0.5_seed%d" % (1234 + seed)] = y.clone()
+            out[name] = rec
+    return out
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    ref_import.install_shims()
+
+    # ---- 1. state_dict inventory of the reference (names, shapes, order) -------------------------------
+    spec = {}
+    for tag, desc in (("full", UNetDesc()), ("tiny", tiny_desc())):
+        model = ref_import.build_reference_unet(**desc_overrides(desc))
+        spec[tag] = [[k, list(v.shape)] for k, v in model.state_dict().items()]
+        assert [(n, list(s)) for n, s, _ in desc.tensor_spec()] == [(k, s) for k, s in spec[tag]], tag
+    with open(os.path.join(GOLD, "state_dict_spec.json"), "w") as f:
+        json.dump(spec, f)
+
+    # ---- 2. tiny UNet: several shapes / variants + per-stage taps --------------------------------------
+    desc = tiny_desc()
+    sd = random_state_dict(desc, seed=7)
+    model = ref_import.build_reference_unet(**desc_overrides(desc))
+    model.load_state_dict(sd, strict=True)
+    cases = {
+        "T50_B2": (2, 50, 11, 0, ["plain", "cfg", "cfg_causal", "cfg_noscale"]),
+        "T33_B1_masked": (1, 33, 12, 5, ["plain", "cfg"]),
+        "T8_B3": (3, 8, 13, 0, ["cfg", "cfg_causal"]),
+        "T1_B1": (1, 1, 14, 3, ["cfg"]),
+    }
+    tiny = run_unet_cases(desc, model, cases)
+    torch.save(dict(weights_seed=7, cases=tiny), os.path.join(GOLD, "unet_tiny.pt"))
+
+    # ---- 3. diffusion process on the tiny model --------------------------------------------------------
+    diff = ref_import.build_reference_diffusion(sampling_steps=100)
+    tables = {k: getattr(diff, k).clone() for k in (
+        "betas", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod",
+        "log_one_minus_alphas_cumprod", "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod",
+        "posterior_variance", "posterior_log_variance_clipped", "posterior_mean_coef1", "posterior_mean_coef2")}
+    pairs = {}
+    for S in (100, 50, 25, 250, 999):
+        times = torch.linspace(-1, 999, steps=S + 1)
+        times = list(reversed(times.int().tolist()))
+        pairs[str(S)] = list(zip(times[:-1], times[1:]))
+    gdm = dict(tables=tables, pairs=pairs)
+    from jen1.diffusion.gdm.noise_schedule import get_beta_schedule
+    gdm["betas_cosine"] = get_beta_schedule("cosine", 1000)[0].to(torch.float32)
+
+    # DDIM trajectories with the reference loop driving the reference tiny model
+    traj = {}
+    for tag, (B, T, S, seed, causal, use_init) in {
+        "S25_B2_T50": (2, 50, 25, 21, False, False),
+        "S25_B1_T33_causal_init": (1, 33, 25, 22, True, True),
+    }.items():
+        d = ref_import.build_reference_diffusion(sampling_steps=S)
+        x, t, emb, mask, cc = make_inputs(desc, B, T, seed, 4)
+        cond = dict(cross_attn_cond=emb, cross_attn_masks=mask, global_cond=None, input_concat_cond=cc)
+        init = 0.5 * x if use_init else None
+        torch.manual_seed(seed)
+        y = d.sample(model, (B, desc.in_channels, T), cond, return_all_timesteps=True, causal=causal, init_data=init)
+        traj[tag] = dict(B=B, T=T, S=S, seed=seed, causal=causal, use_init=use_init, all_steps=y.clone())
+    gdm["traj"] = traj
+
+    # q_sample / training loss
+    d = ref_import.build_reference_diffusion(sampling_steps=100)
+    x, t, emb, mask, cc = make_inputs(desc, 3, 50, 31, 0)
+    cond = dict(cross_attn_cond=emb, cross_attn_masks=mask, global_cond=None, input_concat_cond=cc)
+    noise = torch.randn_like(x)
+    gdm["q_sample"] = dict(seed=31, x_t=d.q_sample(x, t, noise).clone(), noise=noise)
+    torch.manual_seed(77)
+    with torch.no_grad():
+        gdm["train_loss"] = dict(seed=31, rng_seed=77, loss=float(d.training_loosses(model, x, t, cond, causal=False)))
+    for obj in ("x0", "v"):
+        d2 = ref_import.build_reference_diffusion(sampling_steps=25, objective=obj)
+        xx, tt, emb, mask, cc = make_inputs(desc, 1, 20, 41, 0)
+        cond = dict(cross_attn_cond=emb, cross_attn_masks=mask, global_cond=None, input_concat_cond=cc)
+        torch.manual_seed(5)
+        gdm["traj_" + obj] = d2.sample(model, (1, desc.in_channels, 20), cond).clone()
+    torch.save(gdm, os.path.join(GOLD, "gdm.pt"))
+
+    # ---- 4. full-size UNet at config 1 (T=150) ---------------------------------------------------------
+    desc = UNetDesc()
+    sd = random_state_dict(desc, seed=0)
+    model = ref_import.build_reference_unet()
+    model.load_state_dict(sd, strict=True)
+    cases = {
+        "T150_B1": (1, 150, 101, 0, ["plain", "cfg", "cfg_causal"]),
+        "T150_B1_masked": (1, 150, 102, 100, ["cfg"]),
+        "T47_B2": (2, 47, 103, 0, ["cfg"]),
+    }
+    full = run_unet_cases(desc, model, cases)
+    for rec in full.values():  # keep the fixture small: fp32 [B,128,T]
+        pass
+    torch.save(dict(weights_seed=0, cases=full), os.path.join(GOLD, "unet_full.pt"))
+    print("golden fixtures written to", GOLD)
+    for fn in sorted(os.listdir(GOLD)):
+        print("  %-28s %8.1f KB" % (fn, os.path.getsize(os.path.join(GOLD, fn)) / 1024))
+
+
+if __name__ == "__main__":
+    main()
