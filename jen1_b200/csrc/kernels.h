@@ -1,0 +1,82 @@
+// Launch interfaces of the hand-written kernels (all asynchronous on the given stream).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cuda_bf16.h>
+
+#include "conv_params.h"
+
+namespace jen1 {
+
+typedef __nv_bfloat16 bf16;
+
+// ---- fused tap-GEMM (conv / linear) ------------------------------------------------------------------
+// TA: activation (and residual) storage type, TW: weight storage type, TO: output storage type.
+template <typename TA, typename TW, typename TO>
+cudaError_t launch_conv_generic(const ConvParams& p, cudaStream_t stream);
+int conv_generic_row_tile();
+int conv_generic_col_tile();
+
+// tcgen05 / TMEM / TMA implementation for bf16 storage; returns false if the shape is not supported.
+bool conv_umma_supported(const ConvParams& p);
+cudaError_t launch_conv_umma(const ConvParams& p, const void* packed_w, cudaStream_t stream);
+
+// ---- boundary: [Bx][C][L] fp32 (reference layout) -> channels-last T [Bx][L][C] + GroupNorm partials (FG = 1)
+template <typename T>
+cudaError_t launch_pack_ncl(const float* x, T* out, float* stats, int Bx, int C, int L, cudaStream_t stream);
+int pack_rows_per_entry();
+
+// ---- per-row (sum, sumsq) of a [R][C] matrix -> rowpart [R][1][2]
+template <typename T>
+cudaError_t launch_rowstats(const T* x, float* rowpart, int R, int C, cudaStream_t stream);
+
+// ---- learned Fourier time features (reference utils/module.py:66-72): out fp32 [n][2*half+1]
+cudaError_t launch_time_features(const int64_t* t, const float* weights, float* out, int n, int half,
+                                 cudaStream_t stream);
+
+// ---- attention core: softmax(q k^T * scale) v with zero-logit key masking (reference blocks.py:355-380, 431-434)
+struct AttnParams {
+  const void* q;   // T, element (r, i, h, e) at q[((r*N + i) * q_ld) + q_off + h*d + e]
+  int q_ld, q_off;
+  int B2, Bc, N, M, H, d, C;
+  float scale;
+  int causal;
+  int cross;
+  // self-attention keys/values: rows (r*N + j) of `kv`, K at k_off, V at v_off
+  const void* kv;
+  int kv_ld, k_off, v_off;
+  // cross-attention K/V cache (row stride kvc_ld, this layer's K at kvc_off, V at kvc_off + C)
+  const void* kv_cond;   // [Bc][M-1] rows
+  const void* kv_fixed;  // [M] rows
+  const void* kv_time;   // [n_rows] rows (the time-token key/value per conditioning row)
+  int kvc_ld, kvc_off;
+  const uint8_t* drop;   // [Bc] cond-dropout flags or nullptr
+  const float* mask;     // [Bc][M-1] or nullptr
+  const int* cond_row;   // [B2]
+  void* out;             // T [B2][N][C]
+};
+template <typename T>
+cudaError_t launch_attention(const AttnParams& p, cudaStream_t stream);
+
+// ---- classifier-free-guidance combine + std rescale (reference model.py:362-369) fused with the x0/eps
+//      conversion, clamp and DDIM update (reference gdm.py:128-141, 212-222)
+struct SamplerParams {
+  const float* y;  // fp32 [B2][L][C] UNet output, rows [0,B) conditional, [B,2B) unconditional when cfg
+  int B, C, L;
+  int cfg;        // 1: two halves are combined; 0: y is the prediction
+  float emb_scale;
+  int scale_cfg;
+  float phi, one_minus_phi;
+  int mode;       // 0: write the combined prediction to pred_out; 1: DDIM step
+  float* pred_out;      // fp32 [B][C][L]
+  const float* x;       // fp32 [B][C][L] current state
+  const float* noise;   // fp32 [B][C][L] (unused on the last step)
+  float* x_out;         // next state (may alias x)
+  const float* coef;    // [S][8]: sqrt_recip_ac, sqrt_recipm1_ac, sqrt_ac, sqrt_1m_ac, sqrt_alpha_next, c, sigma, last
+  const int* step;      // device scalar: row of `coef`
+  int objective;        // 0 noise, 1 x0, 2 v
+};
+cudaError_t launch_sampler(const SamplerParams& p, cudaStream_t stream);
+
+}  // namespace jen1

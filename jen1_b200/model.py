@@ -1,0 +1,105 @@
+"""`UNetCFG1d` -- drop-in callable for the reference denoiser, executed by the B200 engine.
+
+Mirrors the call surface of reference jen1/model/model.py:268-376 (`UNetCFG1d.__init__/forward`) and the
+`state_dict` layout of SURVEY.md section 8b: construct it from the same keyword arguments as the reference's
+`ModelConfig`, `load_state_dict()` a reference checkpoint dict, then call it exactly as
+`GaussianDiffusion.model_predictions` does (reference jen1/diffusion/gdm/gdm.py:118-125).  The reference's own
+sampling loop can drive this object unchanged; `jen1_b200.diffusion.GaussianDiffusion` additionally recognises
+it and runs the fused, CUDA-graph-captured loop.
+
+Semantics kept from the reference:
+  * the bernoulli cond-dropout draw is made here with torch's RNG, in the same place and with the same shapes
+    as reference utils/module.py:36-42, so seeded runs consume the same random stream;
+  * `AssertionError` on missing / mis-shaped input-concat context (reference model.py:189-199).
+Deviations (documented in DESIGN.md): `batch_cfg=False` evaluates the two guidance branches in one batched pass
+(same arithmetic per sample); `features` (global conditioning) is rejected because the reference config sets
+`context_features=None`.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Sequence
+
+import torch
+
+from .config import UNetDesc
+from .engine import Engine
+from .weights import check_state_dict
+
+
+class UNetCFG1d:
+    def __init__(self, desc: Optional[UNetDesc] = None, *, device="cuda:0", dtype: str = "bf16", **model_kwargs):
+        if desc is None:
+            model_kwargs.pop("use_snake", None)
+            model_kwargs.pop("use_stft", None)
+            model_kwargs.pop("use_stft_context", None)
+            model_kwargs.pop("context_features", None)
+            desc = UNetDesc(**model_kwargs)
+        self.desc = desc
+        self.device = torch.device(device)
+        self.dtype = dtype
+        self.engine: Optional[Engine] = None
+        self._ctx_key = None
+        self.training = False
+
+    # ---- nn.Module-like surface used by the reference glue (generation.py:62-72) ------------------------
+    def load_state_dict(self, state_dict: Dict[str, torch.Tensor], strict: bool = True):
+        sd = {k[len("_orig_mod."):] if k.startswith("_orig_mod.") else k: v for k, v in state_dict.items()}
+        check_state_dict(self.desc, sd)
+        if strict:
+            extra = set(sd) - {n for n, _, _ in self.desc.tensor_spec()}
+            if extra:
+                raise KeyError("unexpected keys in state_dict: %s" % sorted(extra)[:3])
+        if self.engine is not None:
+            self.engine.close()
+        self.engine = Engine(self.desc, sd, device=self.device, dtype=self.dtype)
+        self._ctx_key = None
+        return self
+
+    def eval(self):
+        return self
+
+    def to(self, device):
+        if self.engine is not None and torch.device(device) != self.engine.device:
+            raise RuntimeError("the engine is bound to %s; construct a new UNetCFG1d for another device" % self.engine.device)
+        self.device = torch.device(device)
+        return self
+
+    # ---- conditioning caches -----------------------------------------------------------------------------
+    def set_context(self, embedding: torch.Tensor, embedding_mask: Optional[torch.Tensor]):
+        key = (embedding.data_ptr(), embedding._version, tuple(embedding.shape),
+               None if embedding_mask is None else (embedding_mask.data_ptr(), embedding_mask._version))
+        if key != self._ctx_key:
+            self.engine.set_context(embedding, embedding_mask)
+            self._ctx_key = key
+            self._ctx_hold = (embedding, embedding_mask)  # keep the keyed storage alive
+
+    # ---- forward -----------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def __call__(self, x: torch.Tensor, time: torch.Tensor, *, embedding: torch.Tensor,
+                 embedding_mask: Optional[torch.Tensor] = None, embedding_scale: float = 1.0,
+                 embedding_mask_proba: float = 0.0, batch_cfg: bool = False, scale_cfg: bool = False,
+                 scale_phi: float = 0.7, features=None, channels_list: Optional[Sequence[torch.Tensor]] = None,
+                 causal: bool = False) -> torch.Tensor:
+        if self.engine is None:
+            raise RuntimeError("UNetCFG1d: load_state_dict() must be called before the model is used")
+        assert features is None, "global conditioning features are not supported (reference context_features=None)"
+        assert channels_list is not None, "Missing context"
+        channels = channels_list[0]
+        assert channels is not None, "Missing context for layer 0 at index 0"
+        assert channels.shape[1] == self.desc.context_channels[0], \
+            "Expected context with %d channels at idx 0" % self.desc.context_channels[0]
+        b = embedding.shape[0]
+        dev = self.engine.device
+        drop = None
+        if embedding_mask_proba > 0.0:  # reference model.py:323-328 / utils/module.py:36-42
+            if embedding_mask_proba == 1:
+                drop = torch.ones((b, 1, 1), device=dev, dtype=torch.bool)
+            else:
+                drop = torch.bernoulli(torch.full((b, 1, 1), float(embedding_mask_proba), device=embedding.device)).to(torch.bool)
+        self.set_context(embedding, embedding_mask)
+        rows = self.engine.rows_for(time.reshape(-1).tolist())
+        return self.engine.forward(x, channels, rows, drop=drop, causal=bool(causal),
+                                   embedding_scale=float(embedding_scale), scale_cfg=bool(scale_cfg),
+                                   scale_phi=float(scale_phi))
+
+    forward = __call__

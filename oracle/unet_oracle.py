@@ -181,7 +181,7 @@ def unet_cfg_forward(desc, sd: Dict[str, Tensor], x: Tensor, time: Tensor, *, em
                      embedding_mask: Optional[Tensor] = None, embedding_scale: float = 1.0,
                      embedding_mask_proba: float = 0.0, batch_cfg: bool = False, scale_cfg: bool = False,
                      scale_phi: float = 0.7, channels_list: List[Tensor] = None, causal: bool = False,
-                     features=None, drop_mask: Optional[Tensor] = None) -> Tensor:
+                     features=None, drop_mask: Optional[Tensor] = None, taps: Optional[dict] = None) -> Tensor:
     """jen1/model/model.py:299-376 UNetCFG1d.forward.  `drop_mask` (bool [B]) overrides the bernoulli draw of
     utils/module.py:36-42 so tests can fix the cond-dropout pattern; when None the draw is made with the
     global torch RNG exactly where the reference makes it (model.py:325)."""
@@ -199,7 +199,7 @@ def unet_cfg_forward(desc, sd: Dict[str, Tensor], x: Tensor, time: Tensor, *, em
             else:
                 drop_mask = torch.bernoulli(torch.full((b, 1, 1), embedding_mask_proba)).to(torch.bool)
         embedding = torch.where(drop_mask.view(b, 1, 1), fixed, embedding)
-    kw = dict(causal=causal)
+    kw = dict(causal=causal, taps=taps)
     if embedding_scale == 1.0:
         return unet_forward(desc, sd, x, time, embedding=embedding, embedding_mask=embedding_mask,
                             channels_list=channels_list, **kw)

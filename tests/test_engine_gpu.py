@@ -1,0 +1,137 @@
+"""GPU parity tests: the CUDA engine (through the C ABI) against the CPU oracle and the committed golden
+fixtures (outputs of the unmodified reference).  Run on the B200 box with `pytest -m gpu`.
+
+Tolerances (stated per precision mode, SURVEY.md section 7 "hard parts" 3):
+  fp32 strict mode : max-abs error <= 2e-4 * max|ref| for one UNet evaluation (fp32 FMA, different summation order)
+  bf16 mode        : rel-L2 error  <= 2e-2 for one UNet evaluation (bf16 storage, fp32 accumulate); the reference's
+                     own bf16-autocast run sits at 8.9e-3, random-init weights.
+"""
+import os
+
+import pytest
+import torch
+
+from jen1_b200.config import UNetDesc, tiny_desc
+from jen1_b200.weights import random_state_dict
+from oracle.make_golden import VARIANTS, make_inputs
+from oracle.unet_oracle import unet_cfg_forward
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def rel_l2(a, b):
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+
+
+@pytest.fixture(scope="module")
+def tiny_models():
+    from jen1_b200.model import UNetCFG1d
+    desc = tiny_desc()
+    sd = random_state_dict(desc, 7)
+    out = {}
+    for dt in ("fp32", "bf16"):
+        out[dt] = UNetCFG1d(desc, device=DEV, dtype=dt).load_state_dict(sd)
+    return desc, sd, out
+
+
+@pytest.fixture(scope="module")
+def full_model_fp32():
+    from jen1_b200.model import UNetCFG1d
+    desc = UNetDesc()
+    sd = random_state_dict(desc, 0)
+    return desc, sd, UNetCFG1d(desc, device=DEV, dtype="fp32").load_state_dict(sd)
+
+
+def _run_engine(model, x, t, emb, mask, cc, **kw):
+    y = model(x.to(DEV), t.to(DEV), embedding=emb.to(DEV), embedding_mask=mask.to(DEV), features=None,
+              channels_list=[cc.to(DEV)], **kw)
+    torch.cuda.synchronize()
+    return y.cpu()
+
+
+def _check_taps(model, taps, tol, tag):
+    """Per-stage comparison to localise a failure (oracle taps are [B, C, L], engine taps [Bt, L, C])."""
+    for name in ["to_in"] + [k for k in taps if k.startswith("down")] + ["mid"] + [k for k in taps if k.startswith("up")]:
+        ref = taps[name]
+        got = model.engine.debug_tensor(name).permute(0, 2, 1)
+        ref = ref[: got.shape[0]]
+        assert got.shape == ref.shape, (tag, name, got.shape, ref.shape)
+        err = rel_l2(got, ref)
+        assert err < tol, "%s: stage %s rel-L2 %.3e" % (tag, name, err)
+
+
+@pytest.mark.parametrize("dtype,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
+def test_tiny_unet_matches_reference_golden(tiny_models, golden_dir, dtype, tol):
+    desc, sd, models = tiny_models
+    model = models[dtype]
+    fx = torch.load(os.path.join(golden_dir, "unet_tiny.pt"))
+    for name, rec in fx["cases"].items():
+        x, t, emb, mask, cc = make_inputs(desc, rec["B"], rec["T"], rec["seed"], rec["masked_tail"])
+        for v, ref in rec["outputs"].items():
+            if v.startswith("cfg_dropout"):
+                continue
+            kw = dict(VARIANTS[v])
+            taps = {}
+            with torch.no_grad():
+                unet_cfg_forward(desc, sd, x, t, embedding=emb, embedding_mask=mask, channels_list=[cc], taps=taps, **kw)
+            y = _run_engine(model, x, t, emb, mask, cc, **kw)
+            _check_taps(model, taps, tol, "%s/%s/%s" % (dtype, name, v))
+            err = rel_l2(y, ref)
+            assert err < tol, "%s %s %s: rel-L2 %.3e vs reference golden" % (dtype, name, v, err)
+            if dtype == "fp32":
+                assert (y - ref).abs().max().item() < 2e-4 * max(1.0, ref.abs().max().item()), (name, v)
+
+
+def test_tiny_unet_cond_dropout_matches_oracle(tiny_models):
+    """Explicit drop pattern: dropped samples must use the learned null embedding incl. its time-token row."""
+    desc, sd, models = tiny_models
+    x, t, emb, mask, cc = make_inputs(desc, 3, 20, 55, 4)
+    drop = torch.tensor([True, False, True])
+    with torch.no_grad():
+        ref = unet_cfg_forward(desc, sd, x, t, embedding=emb, embedding_mask=mask, channels_list=[cc],
+                               embedding_scale=0.8, batch_cfg=True, scale_cfg=True, embedding_mask_proba=0.5,
+                               drop_mask=drop)
+    eng = models["fp32"].engine
+    models["fp32"].set_context(emb.to(DEV), mask.to(DEV))
+    rows = eng.rows_for(t.tolist())
+    y = eng.forward(x.to(DEV), cc.to(DEV), rows, drop=drop.to(DEV), causal=False, embedding_scale=0.8,
+                    scale_cfg=True, scale_phi=0.7).cpu()
+    assert rel_l2(y, ref) < 1e-4
+
+
+def test_full_unet_fp32_matches_reference_golden(full_model_fp32, golden_dir):
+    desc, sd, model = full_model_fp32
+    fx = torch.load(os.path.join(golden_dir, "unet_full.pt"))
+    for name, rec in fx["cases"].items():
+        x, t, emb, mask, cc = make_inputs(desc, rec["B"], rec["T"], rec["seed"], rec["masked_tail"])
+        for v, ref in rec["outputs"].items():
+            if v.startswith("cfg_dropout"):
+                continue
+            y = _run_engine(model, x, t, emb, mask, cc, **dict(VARIANTS[v]))
+            err = rel_l2(y, ref)
+            assert err < 2e-4, "full fp32 %s %s rel-L2 %.3e" % (name, v, err)
+
+
+def test_ddim_trajectory_matches_oracle(tiny_models):
+    """25-step DDIM with CFG + stochastic cond-dropout, RNG drawn on the CPU generator in the reference order."""
+    from jen1_b200.diffusion import create_gaussian_diffusion
+    from oracle.gdm_oracle import OracleDiffusion
+    from oracle.unet_oracle import OracleUNet
+    desc, sd, models = tiny_models
+    B, T, S = 2, 50, 25
+    x, t, emb, mask, cc = make_inputs(desc, B, T, 21, 4)
+    cond = dict(cross_attn_cond=emb, cross_attn_masks=mask, global_cond=None, input_concat_cond=cc)
+    torch.manual_seed(99)
+    ref = OracleDiffusion(sampling_timesteps=S).sample(OracleUNet(desc, sd), (B, desc.in_channels, T), cond,
+                                                       return_all_timesteps=True)
+    cond_d = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in cond.items()}
+    for graph in (False, True):
+        d = create_gaussian_diffusion(steps=1000, noise_schedule="linear", objective="noise", device=DEV,
+                                      cfg_dropout_proba=0.2, embedding_scale=0.8, batch_cfg=True, scale_cfg=True,
+                                      sampling_steps=S, rng_device="cpu", use_cuda_graph=graph)
+        torch.manual_seed(99)
+        got = d.sample(models["fp32"], (B, desc.in_channels, T), cond_d, return_all_timesteps=True).cpu()
+        assert got.shape == ref.shape
+        assert rel_l2(got, ref) < 2e-3, "graph=%s rel-L2 %.3e" % (graph, rel_l2(got, ref))
