@@ -42,7 +42,7 @@ Engine::~Engine() {
 }
 
 int Engine::fail(const std::string& m) {
-  err_ = m;
+  if (ok_) err_ = m;  // keep the first failure of a call
   ok_ = false;
   return 1;
 }
@@ -55,6 +55,7 @@ bool Engine::ck(cudaError_t e, const char* what) {
 
 // ============================================================================================ weights
 int Engine::load_tensor(const char* name, const float* data, const int64_t* shape, int ndim) {
+  ok_ = true;
   if (finalized_) return fail("load_tensor after finalize");
   HostTensor t;
   int64_t n = 1;
@@ -244,6 +245,7 @@ DTransformer Engine::pack_transformer(const std::string& p, int C, int layers) {
 }
 
 int Engine::finalize() {
+  ok_ = true;
   if (finalized_) return fail("finalize called twice");
   if (cudaSetDevice(device_) != cudaSuccess) return fail("cudaSetDevice failed (no CUDA device? there is no CPU fallback)");
   FilmAcc film;
@@ -374,7 +376,9 @@ Act Engine::new_act(int Bt, int L, int C, bool f32) {
   return a;
 }
 
-static int fine_groups(int C) { return (C % 32 == 0) ? 32 : 0; }
+// GroupNorm partial statistics are kept per "fine group": 32 per tensor (covers GN(8), GN(32), GN(1) and the
+// 4+4 split of GN(8) over a channel concat); narrow tensors (C | 64) keep one whole-tensor group (GN(1) only).
+static int fine_groups(int C) { return (C % 32 == 0) ? 32 : ((C > 0 && 64 % C == 0) ? 1 : 0); }
 
 void Engine::add_stats(Act& a, int n_ent) {
   a.FG = fine_groups(a.C);
@@ -584,7 +588,7 @@ Act Engine::conv_build(const DConv& W, int Bout, const Act& a0, const Act* a1, f
   }
   if (o.want_stats) {
     if (fine_groups(W.Cout) == 0) {
-      fail("internal: statistics requested for a channel count that is not a multiple of 32");
+      fail("statistics requested for an unsupported channel count (need C % 32 == 0 or C | 64)");
       return out;
     }
     add_stats(out, cdivi(o.Lm, TMr) * o.nphase);
@@ -825,7 +829,7 @@ bool Engine::unet(const Act& xpk, const Act& ccpk, int B, int B2, int T, bool ca
     x = conv_op(U.up, Bcur, x, nullptr, 1.f, o);
     char nm[32];
     snprintf(nm, sizeof nm, "up%d", u);
-    tap(nm, x);
+    tap(i == 0 ? "pre_out" : nm, x);  // the last up-conv already carries the `x += skip` of model.py:261
   }
   *y = resblock(to_out_, x, nullptr, 1.f, 1, false, B2, true);  // Unpatcher, fp32 channels-last output
   return ok_;
@@ -851,6 +855,7 @@ bool Engine::pack_inputs(const float* x, int B, int T, Act* xpk, bool with_cc, c
 
 // ============================================================================================ caches
 int Engine::set_timesteps(const int64_t* t_host, int n, cudaStream_t st) {
+  ok_ = true;
   if (!finalized_) return fail("engine not finalized");
   if (n < 1) return fail("set_timesteps: n must be >= 1");
   cudaSetDevice(device_);
@@ -929,6 +934,7 @@ int Engine::set_timesteps(const int64_t* t_host, int n, cudaStream_t st) {
 }
 
 int Engine::set_context(const float* emb, const float* mask, int B, int S, cudaStream_t st) {
+  ok_ = true;
   if (!finalized_) return fail("engine not finalized");
   if (B < 1 || B > 128) return fail("set_context: batch must be in [1, 128]");
   if (S < 1 || S > d_.context_embedding_max_length) return fail("set_context: context length exceeds context_embedding_max_length");
@@ -1009,6 +1015,7 @@ size_t Engine::workspace_bytes(int B, int T) {
 }
 
 int Engine::reserve(int B, int T) {
+  ok_ = true;
   if (!finalized_) return fail("engine not finalized");
   cudaSetDevice(device_);
   ok_ = true;
@@ -1019,6 +1026,7 @@ int Engine::reserve(int B, int T) {
 
 int Engine::forward(const float* x, const float* cc, const int32_t* cond_rows, const uint8_t* drop, int B, int T,
                     int causal, float emb_scale, int scale_cfg, float phi, float* out, cudaStream_t st) {
+  ok_ = true;
   if (!finalized_) return fail("engine not finalized");
   cudaSetDevice(device_);
   ok_ = true;
@@ -1071,6 +1079,7 @@ int Engine::forward(const float* x, const float* cc, const int32_t* cond_rows, c
 // ============================================================================================ sampler
 int Engine::sample_begin(const float* coef_host, int S, const float* cc, int B, int T, int causal, float emb_scale,
                          int scale_cfg, float phi, int objective, int use_graph, cudaStream_t st) {
+  ok_ = true;
   if (!finalized_) return fail("engine not finalized");
   cudaSetDevice(device_);
   ok_ = true;
@@ -1124,6 +1133,7 @@ int Engine::sample_begin(const float* coef_host, int S, const float* cc, int B, 
 }
 
 int Engine::sample_step(int step, float* x, const float* noise, const uint8_t* drop, cudaStream_t st) {
+  ok_ = true;
   if (!smp_.active) return fail("sample_step without sample_begin");
   cudaSetDevice(device_);
   ok_ = true;
@@ -1202,6 +1212,7 @@ int Engine::sample_step(int step, float* x, const float* noise, const uint8_t* d
 
 // ============================================================================================ debug
 int Engine::debug_tensor(const char* name, float* host_out, int64_t capacity, int64_t* shape3) {
+  ok_ = true;
   auto it = taps_.find(name);
   if (it == taps_.end()) return fail(std::string("no such tap: ") + name);
   cudaSetDevice(device_);

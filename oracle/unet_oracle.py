@@ -172,6 +172,8 @@ def unet_forward(desc, sd: Dict[str, Tensor], x: Tensor, time: Tensor, *, embedd
         if taps is not None:
             taps["up%d" % u] = x
     x = x + skips_list.pop()[0]
+    if taps is not None:
+        taps["pre_out"] = x
     x = resnet_block(sd, "to_out.block", x, mapping, 1, False)  # Unpatcher
     return x
 
