@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstddef>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 
@@ -36,7 +37,7 @@ Engine::~Engine() {
   if (smp_.exec) cudaGraphExecDestroy(smp_.exec);
   for (void* p : wallocs_) cudaFree(p);
   void* bufs[] = {kv_cond_, ctx_mask_, ctx_rowpart_, tt_t_, tt_tfm_, tt_tft_, tt_m1_, tt_m2_, tt_map_, tt_film_,
-                  tt_tok_, tt_tokrp_, tt_kv_, d_ctl_, arena_, smp_.coef};
+                  tt_tok_, tt_tokrp_, tt_kv_, d_ctl_, arena_, smp_.coef, umma_ws_, umma_counters_};
   for (void* p : bufs)
     if (p) cudaFree(p);
 }
@@ -119,7 +120,31 @@ DConv Engine::pack_conv(const std::string& prefix, bool transposed, bool count) 
   c.w = upload_w(pk, false);
   c.bias = upload_f32(b.data);
   if (count) step_weight_bytes_ += (int64_t)pk.size() * (int64_t)esz();
+  pack_umma(c, pk, transposed && k > 3);
   return c;
+}
+
+// Second copy of a bf16 weight in the tcgen05 blob order (see conv_umma.cu).  A ConvTranspose1d(k=2f, stride f)
+// is consumed as f output phases of two taps {z, z+f}; everything else as one phase of `ntaps` taps.
+void Engine::pack_umma(DConv& c, const std::vector<float>& pk, bool transposed) {
+  if (!use_umma_ || c.w_f32 || c.Cout % 128 != 0) return;
+  if (transposed) {
+    const int f = c.ntaps / 2;
+    c.u_nphase = f;
+    c.u_tpp = 2;
+    c.u_wtap_phase = 1;
+    c.u_wtap_step = f;
+  } else {
+    c.u_nphase = 1;
+    c.u_tpp = c.ntaps;
+    c.u_wtap_phase = 0;
+    c.u_wtap_step = 1;
+  }
+  std::vector<uint16_t> blob(conv_umma_packed_elems(c.Cin, c.Cout, c.u_nphase * c.u_tpp));
+  conv_umma_pack(pk.data(), c.Cin, c.Cout, c.u_nphase, c.u_tpp, 0, c.u_wtap_phase, c.u_wtap_step, blob.data());
+  c.wu = wmalloc(blob.size() * 2);
+  if (cudaMemcpy(c.wu, blob.data(), blob.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess)
+    throw EngineError("cudaMemcpy failed (tcgen05 weight upload)");
 }
 
 // Linear weight [O][I] -> [1][I][O]
@@ -136,6 +161,7 @@ DConv Engine::pack_linear_raw(const std::vector<float>& w, const std::vector<flo
   c.w = upload_w(pk, f32);
   if (bias) c.bias = upload_f32(*bias);
   if (count) step_weight_bytes_ += (int64_t)pk.size() * (int64_t)(c.w_f32 ? 4 : 2);
+  pack_umma(c, pk, false);
   return c;
 }
 
@@ -252,6 +278,23 @@ int Engine::finalize() {
   KvcAcc kvc;
   g_film = &film;
   g_kvc = &kvc;
+  {
+    const char* impl = getenv("JEN1_CONV_IMPL");  // "generic" forces the fp32-FMA kernel everywhere (A/B testing)
+    const char* pdl = getenv("JEN1_PDL");
+    use_umma_ = dtype_ == JEN1_DTYPE_BF16 && !(impl && strcmp(impl, "generic") == 0);
+    use_pdl_ = !(pdl && strcmp(pdl, "0") == 0);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device_) == cudaSuccess) {
+      num_sms_ = prop.multiProcessorCount;
+      if (prop.major != 10) use_umma_ = false;  // tcgen05 needs sm_100
+    }
+    if (use_umma_) {
+      umma_ws_cap_ = (size_t)64 << 20;
+      if (cudaMalloc((void**)&umma_ws_, umma_ws_cap_) != cudaSuccess || cudaMalloc((void**)&umma_counters_, 65536 * 4) != cudaSuccess ||
+          cudaMemset(umma_counters_, 0, 65536 * 4) != cudaSuccess || conv_umma_init() != cudaSuccess)
+        return fail("tcgen05 path initialisation failed");
+    }
+  }
   try {
     const int nl = d_.num_layers;
     if (nl < 1 || nl > JEN1_MAX_LEVELS) throw EngineError("bad num_layers");
@@ -577,29 +620,58 @@ Act Engine::conv_build(const DConv& W, int Bout, const Act& a0, const Act* a1, f
     p.res_bmod = 1;
   }
   const int TMr = conv_generic_row_tile(), TNc = conv_generic_col_tile();
+  const bool out_is_f32 = o.out_f32 || dtype_ == JEN1_DTYPE_F32;
+  if (o.want_stats && fine_groups(W.Cout) == 0) {
+    fail("statistics requested for an unsupported channel count (need C % 32 == 0 or C | 64)");
+    return out;
+  }
+  if (o.want_stats) p.FGo = fine_groups(W.Cout);
+  // kernel selection: tcgen05 path for bf16 storage when the shape fits, else the generic fp32-FMA kernel
+  UmmaPlan plan;
+  memset(&plan, 0, sizeof(plan));
+  if (use_umma_ && !a0.f32 && W.wu && (!W2 || W2->wu) && W.u_nphase == o.nphase && W.u_tpp == o.ntaps &&
+      (o.nphase == 1 ? (o.wtap0 == 0 && o.wtap_step == 1) : (o.wtap0 == 0 && o.wtap_phase == W.u_wtap_phase && o.wtap_step == W.u_wtap_step))) {
+    p.out = (void*)1;  // planning only looks at which of out / out_ncl is set
+    plan = conv_umma_plan(p, o.want_stats, umma_ws_cap_, num_sms_);
+    p.out = nullptr;
+  }
   if (into) {
     out.ptr = into;
     out.Bt = Bout;
     out.L = o.Lout;
     out.C = W.Cout;
-    out.f32 = o.out_f32 || dtype_ == JEN1_DTYPE_F32;
+    out.f32 = out_is_f32;
   } else {
     out = new_act(Bout, o.Lout, W.Cout, o.out_f32);
   }
   if (o.want_stats) {
-    if (fine_groups(W.Cout) == 0) {
-      fail("statistics requested for an unsupported channel count (need C % 32 == 0 or C | 64)");
-      return out;
-    }
-    add_stats(out, cdivi(o.Lm, TMr) * o.nphase);
+    add_stats(out, plan.ok ? plan.E_max * o.nphase : cdivi(o.Lm, TMr) * o.nphase);
     p.stats_out = out.stats;
-    p.FGo = out.FG;
   }
   if (o.want_rowpart) {
-    add_rowpart(out, cdivi(W.Cout, TNc));
+    add_rowpart(out, plan.ok ? plan.m_tiles : cdivi(W.Cout, TNc));
     p.rowpart_out = out.rowpart;
   }
   p.out = out.ptr;
+  if (debug_ && !dry_) {
+    char nm[32];
+    snprintf(nm, sizeof nm, "op%03d", op_index_);
+    taps_[nm] = out;
+    if (trace_)
+      fprintf(stderr, "[jen1] op%03d %s B=%d Lm=%d Lout=%d Cin=%d(+%d) Cout=%d taps=%d stride=%d phases=%d G=%d mode=%d | NT=%d tiles=%dx%d splitk=%d stages=%d\n",
+              op_index_, plan.ok ? "umma   " : "generic", Bout, o.Lm, o.Lout, s.Cin, W2 ? W2->Cin : 0, W.Cout, o.ntaps,
+              o.in_stride, o.nphase, o.G, o.mode, plan.NT, plan.n_tiles, plan.m_tiles, plan.splitk, plan.stages);
+    ++op_index_;
+  }
+  if (plan.ok) {
+    if (dry_) return out;
+    if (!ok_) return out;
+    cudaError_t e = launch_conv_umma(p, plan, W.wu, W2 ? W2->wu : nullptr, umma_ws_, umma_counters_, out.f32, use_pdl_, st_);
+    ++launches_;
+    ++umma_launches_;
+    ck(e, "tcgen05 conv launch");
+    return out;
+  }
   run_conv(p, a0.f32, W.w_f32 || dtype_ == JEN1_DTYPE_F32, out.f32);
   return out;
 }
@@ -1049,6 +1121,8 @@ int Engine::forward(const float* x, const float* cc, const int32_t* cond_rows, c
   st_ = st;
   dry_ = false;
   debug_ = true;
+  op_index_ = 0;
+  trace_ = getenv("JEN1_TRACE") != nullptr;
   taps_.clear();
   arena_off_ = 0;
   if (!upload_ctl(c, st)) return 1;
@@ -1188,7 +1262,7 @@ int Engine::sample_step(int step, float* x, const float* noise, const uint8_t* d
     }
     if (noise == nullptr) return fail("sample_step: the first graph-captured step needs a noise buffer");
     cudaGraph_t graph = nullptr;
-    const int64_t l0 = launches_;
+    const int64_t l0 = launches_, u0 = umma_launches_;
     if (!ck(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal), "begin capture")) return 1;
     const bool good = body();
     cudaError_t e = cudaStreamEndCapture(st, &graph);
@@ -1198,7 +1272,9 @@ int Engine::sample_step(int step, float* x, const float* noise, const uint8_t* d
       return 1;
     }
     smp_.launches_per_step = launches_ - l0;
+    smp_.umma_per_step = umma_launches_ - u0;
     launches_ = l0;
+    umma_launches_ = u0;
     e = cudaGraphInstantiate(&smp_.exec, graph, 0);
     cudaGraphDestroy(graph);
     if (!ck(e, "graph instantiate")) return 1;
@@ -1207,6 +1283,7 @@ int Engine::sample_step(int step, float* x, const float* noise, const uint8_t* d
   }
   if (!ck(cudaGraphLaunch(smp_.exec, st), "graph launch")) return 1;
   launches_ += smp_.launches_per_step;
+  umma_launches_ += smp_.umma_per_step;
   return 0;
 }
 

@@ -23,6 +23,8 @@ struct DConv {          // one packed conv / linear: W [ntaps][Cin][Cout] (+ bia
   float* bias = nullptr;
   int Cin = 0, Cout = 0, ntaps = 1;
   bool w_f32 = false;
+  void* wu = nullptr;   // tcgen05 blob stream (conv_umma.cu), bf16 engines only
+  int u_nphase = 1, u_tpp = 1, u_wtap_phase = 0, u_wtap_step = 1;  // tap order the blob stream was packed for
 };
 struct DNorm {
   float* gamma = nullptr;
@@ -102,6 +104,7 @@ class Engine {
   const char* last_error() const { return err_.c_str(); }
   int64_t launch_count() const { return launches_; }
   int64_t weight_bytes() const { return step_weight_bytes_; }
+  int64_t umma_launch_count() const { return umma_launches_; }
 
  private:
   // ---- errors
@@ -146,6 +149,7 @@ class Engine {
   Act conv_build(const DConv& W, int Bout, const Act& a0, const Act* a1, float scale1, const ConvOpts& o,
                  const DConv* W2, const Act* r0, const Act* r1, float rscale1, void* into);
   bool run_conv(const ConvParams& p, bool act_f32, bool w_f32, bool out_f32);
+  void pack_umma(DConv& c, const std::vector<float>& tap_cin_cout, bool transposed);
   Act resblock(const DRes& R, const Act& x, const Act* skip, float sscale, int groups, bool causal, int Bout,
                bool out_f32);
   Act transformer(const DTransformer& Tr, const Act& x, bool causal, int Bout);
@@ -195,6 +199,13 @@ class Engine {
   void* tt_kv_ = nullptr;
   // control
   CtlBlock* d_ctl_ = nullptr;
+  // tcgen05 path
+  bool use_umma_ = false, use_pdl_ = true;
+  int num_sms_ = 148;
+  float* umma_ws_ = nullptr;
+  size_t umma_ws_cap_ = 0;
+  int* umma_counters_ = nullptr;
+  int64_t umma_launches_ = 0;
   // arena
   char* arena_ = nullptr;
   size_t arena_cap_ = 0, arena_off_ = 0;
@@ -202,7 +213,8 @@ class Engine {
   cudaStream_t st_ = nullptr;
   bool ok_ = true;
   // debug taps
-  bool debug_ = false;
+  bool debug_ = false, trace_ = false;
+  int op_index_ = 0;
   std::map<std::string, Act> taps_;
   // sampler state
   struct Sampler {
@@ -217,7 +229,7 @@ class Engine {
     cudaGraphExec_t exec = nullptr;
     float* g_x = nullptr;
     const float* g_noise = nullptr;
-    int64_t launches_per_step = 0;
+    int64_t launches_per_step = 0, umma_per_step = 0;
   } smp_;
 };
 

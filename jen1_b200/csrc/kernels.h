@@ -18,9 +18,27 @@ cudaError_t launch_conv_generic(const ConvParams& p, cudaStream_t stream);
 int conv_generic_row_tile();
 int conv_generic_col_tile();
 
-// tcgen05 / TMEM / TMA implementation for bf16 storage; returns false if the shape is not supported.
-bool conv_umma_supported(const ConvParams& p);
-cudaError_t launch_conv_umma(const ConvParams& p, const void* packed_w, cudaStream_t stream);
+// ---- tcgen05 / TMEM implementation for bf16 storage (conv_umma.cu): swap-AB implicit GEMM, weights streamed as
+//      pre-packed 16 KB blobs by bulk async copies, split-K over an L2 workspace, PDL-aware.
+struct UmmaPlan {
+  int ok;                 // 0: shape not supported -> generic kernel
+  int NT, n_tiles;        // accumulator columns (padded flat positions) per CTA, number of N tiles
+  int m_tiles;            // Cout / 128
+  int splitk;
+  int Lq, amin, halo;     // padded positions per batch row; tap row-offset range
+  int R, PS, panel_bytes; // panel rows, panel stride (16-byte units), bytes of one panel (all sub-panels)
+  int steps0, steps1;     // 64-channel K blocks of segment 0 / 1
+  int stages, tmem_cols;
+  int E_max;              // GroupNorm partial entries per batch row (per phase) this launch writes
+  size_t smem, ws_bytes;
+};
+UmmaPlan conv_umma_plan(const ConvParams& p, bool want_stats, size_t ws_capacity_bytes, int num_sms);
+size_t conv_umma_packed_elems(int Cin, int Cout, int ntaps);
+void conv_umma_pack(const float* w_tap_cin_cout, int Cin, int Cout, int nphase, int taps_per_phase, int wtap0,
+                    int wtap_phase, int wtap_step, uint16_t* out_bf16);
+cudaError_t conv_umma_init();
+cudaError_t launch_conv_umma(const ConvParams& p, const UmmaPlan& plan, const void* w0_packed, const void* w1_packed,
+                             float* ws, int* counters, bool out_f32, bool pdl, cudaStream_t stream);
 
 // ---- boundary: [Bx][C][L] fp32 (reference layout) -> channels-last T [Bx][L][C] + GroupNorm partials (FG = 1)
 template <typename T>

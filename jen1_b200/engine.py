@@ -182,6 +182,9 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.jen1_engine_launch_count(self._h))
 
+    def umma_launch_count(self) -> int:
+        return int(self.lib.jen1_engine_umma_launch_count(self._h))
+
     def weight_bytes(self) -> int:
         return int(self.lib.jen1_engine_weight_bytes(self._h))
 
