@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(NT) conv_generic_kernel(const ConvParams p) {
           }
           off += sr.C;
         }
-        const double n = (double)cpg * (double)s0.L;
+        const double n = (double)(p.gn_real_c > 0 ? p.gn_real_c / p.G : cpg) * (double)s0.L;
         const double mean = a / n;
         double var = q / n - mean * mean;
         if (var < 0.0) var = 0.0;

@@ -52,6 +52,8 @@ struct ConvParams {
   // ---- prologue of seg[0] (seg[1] is always raw * scale)
   int mode;            // PRO_AFFINE: y = act(a[b][c]*x + s[b][c]);  PRO_ROWNORM: y = (x - mu[row]) * rstd[row]
   int G;               // GroupNorm groups over the concatenated channels (0 = no norm)
+  int gn_real_c;       // > 0: channels that really exist (the rest is zero padding): element count of a group is
+                       //      gn_real_c / G * L instead of Cin / G * L (only used with G = 1)
   float eps;
   const float* gamma;  // [Cin]
   const float* beta;   // [Cin]

@@ -173,6 +173,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   int* ticket_slot = reinterpret_cast<int*>(tmem_slot + 1);         // [1]
   float* gmean = reinterpret_cast<float*>(misc + 256);              // [kMaxSlots][32]
   float* grstd = gmean + kMaxSlots * 32;                            // [kMaxSlots][32]
+  double* fine = reinterpret_cast<double*>(grstd + kMaxSlots * 32); // [2 sources][32 fine groups][2]
   // epilogue scratch aliases the weight ring (all MMAs have completed by then)
   float* sred = reinterpret_cast<float*>(a_ring);                   // [kMaxSlots][128][2]
   float* rowred = sred + kMaxSlots * 128 * 2;                       // [4][NT][2]
@@ -272,44 +273,62 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     if (b_last > p.B - 1) b_last = p.B - 1;
     const int nbl = b_last - b_first + 1;
 
-    // ---- GroupNorm statistics of the input for the batch rows this tile touches (fixed-order reduce)
+    // ---- GroupNorm statistics of the input for the batch rows this tile touches.  Deterministic two-level reduce:
+    //      128 threads = 64 (source, fine group) items x 2 interleaved halves of the producer's per-tile partials,
+    //      combined by one shuffle; then one thread per group folds its fine groups.
     if (p.mode == PRO_AFFINE && p.G > 0) {
       const int cpg = Ct / p.G;
-      for (int idx = tid; idx < nbl * p.G; idx += kProducers) {
-        const int bl = idx / p.G, g = idx - bl * p.G;
+      const int item = tid >> 1, part = tid & 1;
+      const int fs = item >> 5, ffg = item & 31;
+      const ConvSrc& fsr = S0.s[fs];
+      for (int bl = 0; bl < nbl; ++bl) {
         const int b = b_first + bl;
-        const int lo = g * cpg, hi = lo + cpg;
         double a = 0.0, q = 0.0;
-        int off = 0;
-        for (int s = 0; s < 2; ++s) {
-          const ConvSrc& sr = S0.s[s];
-          if (sr.C > 0) {
-            const int olo = max(lo, off), ohi = min(hi, off + sr.C);
-            if (ohi > olo) {
-              const int gs = sr.C / sr.FG;
-              const float* st = sr.stats + (size_t)(b % sr.bmod) * sr.n_ent * sr.FG * 2;
-              const double sc = (double)sr.scale;
-              for (int fg = (olo - off) / gs; fg < (ohi - off) / gs; ++fg) {
-                double fa = 0.0, fq = 0.0;
-                for (int e = 0; e < sr.n_ent; ++e) {
-                  fa += (double)st[(e * sr.FG + fg) * 2];
-                  fq += (double)st[(e * sr.FG + fg) * 2 + 1];
+        if (fsr.C > 0 && ffg < fsr.FG) {
+          const float2* st = reinterpret_cast<const float2*>(fsr.stats) + (size_t)(b % fsr.bmod) * fsr.n_ent * fsr.FG + ffg;
+#pragma unroll 4
+          for (int e = part; e < fsr.n_ent; e += 2) {
+            const float2 v = __ldg(st + (size_t)e * fsr.FG);
+            a += (double)v.x;
+            q += (double)v.y;
+          }
+        }
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        q += __shfl_xor_sync(0xffffffffu, q, 1);
+        if (part == 0) {
+          const double sc = (double)fsr.scale;
+          fine[item * 2] = a * sc;
+          fine[item * 2 + 1] = q * sc * sc;
+        }
+        bar_sync_producers();
+        if (tid < p.G) {
+          const int g = tid;
+          const int lo = g * cpg, hi = lo + cpg;
+          double ga = 0.0, gq = 0.0;
+          int off = 0;
+          for (int s = 0; s < 2; ++s) {
+            const ConvSrc& sr = S0.s[s];
+            if (sr.C > 0) {
+              const int olo = max(lo, off), ohi = min(hi, off + sr.C);
+              if (ohi > olo) {
+                const int gs = sr.C / sr.FG;
+                for (int fg = (olo - off) / gs; fg < (ohi - off) / gs; ++fg) {
+                  ga += fine[(s * 32 + fg) * 2];
+                  gq += fine[(s * 32 + fg) * 2 + 1];
                 }
-                a += fa * sc;
-                q += fq * sc * sc;
               }
             }
+            off += sr.C;
           }
-          off += sr.C;
+          const double n = (double)(p.gn_real_c > 0 ? p.gn_real_c / p.G : cpg) * (double)S0.L;
+          const double mean = ga / n;
+          double var = gq / n - mean * mean;
+          if (var < 0.0) var = 0.0;
+          gmean[bl * 32 + g] = (float)mean;
+          grstd[bl * 32 + g] = (float)(1.0 / sqrt(var + (double)p.eps));
         }
-        const double n = (double)cpg * (double)S0.L;
-        const double mean = a / n;
-        double var = q / n - mean * mean;
-        if (var < 0.0) var = 0.0;
-        gmean[bl * 32 + g] = (float)mean;
-        grstd[bl * 32 + g] = (float)(1.0 / sqrt(var + (double)p.eps));
+        bar_sync_producers();
       }
-      bar_sync_producers();
     }
 
     // ---- panels
@@ -457,10 +476,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
         } else {
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = 0.f;
-          for (int s = 0; s < pl.splitk; ++s) {
-            const float* wp = wsbase + (size_t)s * NT * 128;
+          for (int s0 = 0; s0 < pl.splitk; s0 += 4) {  // 64 independent L2 loads in flight, summed in split order
+            float tv[4][16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] += __ldcg(wp + (size_t)(c0 + j) * 128 + cl);
+            for (int u = 0; u < 4; ++u) {
+              const float* wp = wsbase + (size_t)(s0 + u) * NT * 128 + (size_t)c0 * 128 + cl;
+              const bool on = s0 + u < pl.splitk;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) tv[u][j] = on ? __ldcg(wp + (size_t)j * 128) : 0.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] += tv[u][j];
           }
         }
 #pragma unroll
@@ -618,8 +646,12 @@ UmmaPlan conv_umma_plan(const ConvParams& p, bool want_stats, size_t ws_capacity
   if ((long long)NT > round_up((int)nq, 16)) NT = round_up((int)nq, 16);
   if (NT < 16) NT = 16;
   // distinct batch rows per tile must fit the epilogue scratch
-  while (NT > 16 && (NT + pl.halo + pl.Lq - 1) / pl.Lq + 1 > kMaxSlots) NT -= 16;
-  if ((NT + pl.halo + pl.Lq - 1) / pl.Lq + 1 > kMaxSlots) return pl;
+  auto slots = [&](int nt) {
+    const int s = (nt + pl.halo + pl.Lq - 1) / pl.Lq + 1;
+    return s < p.B ? s : p.B;
+  };
+  while (NT > 16 && slots(NT) > kMaxSlots) NT -= 16;
+  if (slots(NT) > kMaxSlots) return pl;
   pl.NT = NT;
   pl.n_tiles = (int)((nq + NT - 1) / NT);
   pl.R = NT + pl.halo;
@@ -642,7 +674,7 @@ UmmaPlan conv_umma_plan(const ConvParams& p, bool want_stats, size_t ws_capacity
   pl.splitk = sk;
   pl.ws_bytes = sk > 1 ? (size_t)tiles * sk * NT * 128 * sizeof(float) : 0;
   // shared memory: two panels + as many 16 KB weight stages as fit in ~half an SM (two CTAs co-reside under PDL)
-  const int misc = 256 + 2 * kMaxSlots * 32 * 4;
+  const int misc = 256 + 2 * kMaxSlots * 32 * 4 + 2 * 32 * 2 * 8;
   const int budget = 110 * 1024;
   int stages = (budget - 2 * pl.panel_bytes - misc) / kABytes;
   const int scratch = (kMaxSlots * 128 * 2 + 4 * NT * 2) * 4;  // epilogue scratch aliases the ring

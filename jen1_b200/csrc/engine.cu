@@ -101,26 +101,27 @@ void* Engine::upload_w(const std::vector<float>& v, bool f32) {
 }
 
 // Conv1d weight [Cout][Cin][k] (or ConvTranspose1d [Cin][Cout][k]) -> [k][Cin][Cout]
-DConv Engine::pack_conv(const std::string& prefix, bool transposed, bool count) {
+DConv Engine::pack_conv(const std::string& prefix, bool transposed, bool count, int cin_pad) {
   const HostTensor& w = ht(prefix + ".weight");
   const HostTensor& b = ht(prefix + ".bias");
   if (w.shape.size() != 3) throw EngineError("conv weight must be 3-D: " + prefix);
   DConv c;
   const int d0 = (int)w.shape[0], d1 = (int)w.shape[1], k = (int)w.shape[2];
   c.Cout = transposed ? d1 : d0;
-  c.Cin = transposed ? d0 : d1;
+  const int cin_real = transposed ? d0 : d1;
+  c.Cin = cin_pad > cin_real ? cin_pad : cin_real;  // extra input channels (zero weights) match zero-padded inputs
   c.ntaps = k;
-  std::vector<float> pk((size_t)k * c.Cin * c.Cout);
+  std::vector<float> pk((size_t)k * c.Cin * c.Cout, 0.0f);
   for (int o = 0; o < c.Cout; ++o)
-    for (int i = 0; i < c.Cin; ++i)
+    for (int i = 0; i < cin_real; ++i)
       for (int t = 0; t < k; ++t) {
-        const float v = transposed ? w.data[((size_t)i * c.Cout + o) * k + t] : w.data[((size_t)o * c.Cin + i) * k + t];
+        const float v = transposed ? w.data[((size_t)i * c.Cout + o) * k + t] : w.data[((size_t)o * cin_real + i) * k + t];
         pk[((size_t)t * c.Cin + i) * c.Cout + o] = v;
       }
   c.w = upload_w(pk, false);
   c.bias = upload_f32(b.data);
-  if (count) step_weight_bytes_ += (int64_t)pk.size() * (int64_t)esz();
-  pack_umma(c, pk, transposed && k > 3);
+  if (count) step_weight_bytes_ += (int64_t)k * cin_real * c.Cout * (int64_t)esz();
+  pack_umma(c, pk, transposed);
   return c;
 }
 
@@ -165,10 +166,15 @@ DConv Engine::pack_linear_raw(const std::vector<float>& w, const std::vector<flo
   return c;
 }
 
-DNorm Engine::pack_norm(const std::string& prefix) {
+DNorm Engine::pack_norm(const std::string& prefix, int pad_to) {
   DNorm n;
-  n.gamma = upload_f32(ht(prefix + ".weight").data);
-  n.beta = upload_f32(ht(prefix + ".bias").data);
+  std::vector<float> g = ht(prefix + ".weight").data, b = ht(prefix + ".bias").data;
+  if (pad_to > (int)g.size()) {  // zero affine on zero-padded channels
+    g.resize(pad_to, 0.0f);
+    b.resize(pad_to, 0.0f);
+  }
+  n.gamma = upload_f32(g);
+  n.beta = upload_f32(b);
   return n;
 }
 
@@ -183,12 +189,14 @@ FilmAcc* g_film = nullptr;  // set during finalize (single-threaded per handle)
 KvcAcc* g_kvc = nullptr;
 }  // namespace
 
-DRes Engine::pack_res(const std::string& p, int cin, int cout) {
+DRes Engine::pack_res(const std::string& p, int cin, int cout, int cin_pad) {
   DRes r;
-  r.cin = cin;
   r.cout = cout;
-  r.gn1 = pack_norm(p + ".block1.groupnorm");
-  r.c1 = pack_conv(p + ".block1.project.conv");
+  if (cin_pad > cin) r.gn_real_c = cin;
+  r.gn1 = pack_norm(p + ".block1.groupnorm", cin_pad);
+  r.c1 = pack_conv(p + ".block1.project.conv", false, true, cin_pad);
+  if (cin_pad > cin) cin = cin_pad;
+  r.cin = cin;
   r.gn2 = pack_norm(p + ".block2.groupnorm");
   const HostTensor& fw = ht(p + ".to_scale_shift.to_scale_shift.1.weight");
   const HostTensor& fb = ht(p + ".to_scale_shift.to_scale_shift.1.bias");
@@ -202,7 +210,7 @@ DRes Engine::pack_res(const std::string& p, int cin, int cout) {
     HostTensor& b2 = host_[p + ".block2.project.conv.bias"];
     const HostTensor& bo = ht(p + ".to_out.conv.bias");
     for (size_t i = 0; i < b2.data.size(); ++i) b2.data[i] += bo.data[i];
-    r.co = pack_conv(p + ".to_out.conv");
+    r.co = pack_conv(p + ".to_out.conv", false, true, cin_pad);
   }
   r.c2 = pack_conv(p + ".block2.project.conv");
   if (r.c1.Cin != cin || r.c1.Cout != cout || r.c2.Cin != cout) throw EngineError("resblock shape mismatch at " + p);
@@ -317,7 +325,9 @@ int Engine::finalize() {
     tw_map_ = upload_f32(ht("to_time.0.0.weights").data);
     tw_tok_ = upload_f32(ht("to_time_embedding.0.0.weights").data);
 
-    to_in_ = pack_res("to_in.block", d_.in_channels + d_.context_channels, lc(0));
+    cc_pad_ = use_umma_ ? (d_.context_channels + 7) / 8 * 8 : d_.context_channels;
+    if (use_umma_ && d_.in_channels % 8 != 0) cc_pad_ = d_.context_channels;  // rows would not be 16-byte aligned anyway
+    to_in_ = pack_res("to_in.block", d_.in_channels + d_.context_channels, lc(0), d_.in_channels + cc_pad_);
     for (int i = 0; i < nl; ++i) {
       DDown D;
       const std::string p = "downsamples." + std::to_string(i);
@@ -556,6 +566,7 @@ Act Engine::conv_build(const DConv& W, int Bout, const Act& a0, const Act* a1, f
   }
   p.mode = o.mode;
   p.G = o.G;
+  p.gn_real_c = o.gn_real_c;
   p.eps = o.eps;
   if (o.norm) {
     p.gamma = o.norm->gamma;
@@ -691,8 +702,10 @@ Act Engine::resblock(const DRes& R, const Act& x, const Act* skip, float sscale,
   o1.norm = &R.gn1;
   o1.act = ACT_SILU;
   o1.want_stats = true;
+  o1.gn_real_c = R.gn_real_c;
   Act h = conv_op(R.c1, Bout, x, skip, sscale, o1);
   ConvOpts o2 = o1;
+  o2.gn_real_c = 0;
   o2.norm = &R.gn2;
   o2.film = tt_film_ + R.film_off;
   o2.want_stats = !out_f32;
@@ -909,19 +922,19 @@ bool Engine::unet(const Act& xpk, const Act& ccpk, int B, int B2, int T, bool ca
 
 bool Engine::pack_inputs(const float* x, int B, int T, Act* xpk, bool with_cc, const float* cc, Act* ccpk) {
   const int pr = pack_rows_per_entry();
-  auto one = [&](const float* src, int C, Act* a) {
-    *a = new_act(B, T, C);
+  auto one = [&](const float* src, int C, int Cp, Act* a) {
+    *a = new_act(B, T, Cp);
     a->FG = 1;
     a->n_ent = cdivi(T, pr);
     a->stats = (float*)aalloc((size_t)B * a->n_ent * 2 * sizeof(float));
     if (dry_ || !ok_) return;
-    cudaError_t e = (dtype_ == JEN1_DTYPE_F32) ? launch_pack_ncl<float>(src, (float*)a->ptr, a->stats, B, C, T, st_)
-                                               : launch_pack_ncl<bf16>(src, (bf16*)a->ptr, a->stats, B, C, T, st_);
+    cudaError_t e = (dtype_ == JEN1_DTYPE_F32) ? launch_pack_ncl<float>(src, (float*)a->ptr, a->stats, B, C, Cp, T, st_)
+                                               : launch_pack_ncl<bf16>(src, (bf16*)a->ptr, a->stats, B, C, Cp, T, st_);
     ++launches_;
     ck(e, "pack launch");
   };
-  if (with_cc) one(cc, d_.context_channels, ccpk);
-  one(x, d_.in_channels, xpk);
+  if (with_cc) one(cc, d_.context_channels, cc_pad_, ccpk);
+  one(x, d_.in_channels, d_.in_channels, xpk);
   return ok_;
 }
 
@@ -1190,13 +1203,13 @@ int Engine::sample_begin(const float* coef_host, int S, const float* cc, int B, 
   dry_ = false;
   arena_off_ = 0;
   const int pr = pack_rows_per_entry();
-  smp_.ccpk = new_act(B, T, d_.context_channels);
+  smp_.ccpk = new_act(B, T, cc_pad_);
   smp_.ccpk.FG = 1;
   smp_.ccpk.n_ent = cdivi(T, pr);
   smp_.ccpk.stats = (float*)aalloc((size_t)B * smp_.ccpk.n_ent * 2 * sizeof(float));
   cudaError_t e = (dtype_ == JEN1_DTYPE_F32)
-                      ? launch_pack_ncl<float>(cc, (float*)smp_.ccpk.ptr, smp_.ccpk.stats, B, d_.context_channels, T, st)
-                      : launch_pack_ncl<bf16>(cc, (bf16*)smp_.ccpk.ptr, smp_.ccpk.stats, B, d_.context_channels, T, st);
+                      ? launch_pack_ncl<float>(cc, (float*)smp_.ccpk.ptr, smp_.ccpk.stats, B, d_.context_channels, cc_pad_, T, st)
+                      : launch_pack_ncl<bf16>(cc, (bf16*)smp_.ccpk.ptr, smp_.ccpk.stats, B, d_.context_channels, cc_pad_, T, st);
   ++launches_;
   if (!ck(e, "pack(cc)")) return 1;
   smp_.arena_base = arena_off_;

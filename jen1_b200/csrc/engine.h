@@ -35,6 +35,7 @@ struct DRes {  // ResnetBlock1d (reference blocks.py:168-231)
   DConv c1, c2, co;  // co: to_out 1x1 (fused into c2's launch as a second K segment; its bias is folded into c2.bias)
   bool has_out = false;
   int cin = 0, cout = 0;
+  int gn_real_c = 0;  // block1's input carries zero-padded channels: real channel count for the GroupNorm size
   int64_t film_off = 0;
 };
 struct DAttn {     // Attention (reference blocks.py:383-437) with the LayerNorm affines folded into the projections
@@ -116,11 +117,11 @@ class Engine {
   void* wmalloc(size_t bytes);
   float* upload_f32(const std::vector<float>& v);
   void* upload_w(const std::vector<float>& v, bool f32);
-  DConv pack_conv(const std::string& prefix, bool transposed = false, bool count = true);
+  DConv pack_conv(const std::string& prefix, bool transposed = false, bool count = true, int cin_pad = 0);
   DConv pack_linear_raw(const std::vector<float>& w, const std::vector<float>* bias, int O, int I, bool f32,
                         bool count = true);
-  DNorm pack_norm(const std::string& prefix);
-  DRes pack_res(const std::string& prefix, int cin, int cout);
+  DNorm pack_norm(const std::string& prefix, int pad_to = 0);
+  DRes pack_res(const std::string& prefix, int cin, int cout, int cin_pad = 0);
   DTransformer pack_transformer(const std::string& prefix, int C, int layers);
   DAttn pack_attention(const std::string& prefix, int C, bool cross);
 
@@ -140,6 +141,7 @@ class Engine {
     const DNorm* norm = nullptr;
     const float* film = nullptr;
     int act = ACT_NONE, epi_act = ACT_NONE;
+    int gn_real_c = 0;
     const Act* res = nullptr;
     bool want_stats = false, want_rowpart = false, out_f32 = false;
   };
@@ -177,6 +179,7 @@ class Engine {
   std::vector<DUp> ups_;
   int64_t film_total_ = 0, kvc_total_ = 0;
   int Fm_ = 0, E_ = 0, tdim_ = 0;
+  int cc_pad_ = 0;  // stored channel count of the packed input-concat conditioning (multiple of 8 on the tcgen05 path)
   // conditioning networks (fp32)
   DConv to_time_, map0_, map2_, film_lin_, to_tok_;
   float *tw_map_ = nullptr, *tw_tok_ = nullptr;

@@ -40,9 +40,10 @@ cudaError_t conv_umma_init();
 cudaError_t launch_conv_umma(const ConvParams& p, const UmmaPlan& plan, const void* w0_packed, const void* w1_packed,
                              float* ws, int* counters, bool out_f32, bool pdl, cudaStream_t stream);
 
-// ---- boundary: [Bx][C][L] fp32 (reference layout) -> channels-last T [Bx][L][C] + GroupNorm partials (FG = 1)
+// ---- boundary: [Bx][C][L] fp32 (reference layout) -> channels-last T [Bx][L][Cp] (channels C..Cp-1 zero-filled so
+//      rows stay 16-byte aligned for the tcgen05 path) + GroupNorm partials (FG = 1)
 template <typename T>
-cudaError_t launch_pack_ncl(const float* x, T* out, float* stats, int Bx, int C, int L, cudaStream_t stream);
+cudaError_t launch_pack_ncl(const float* x, T* out, float* stats, int Bx, int C, int Cp, int L, cudaStream_t stream);
 int pack_rows_per_entry();
 
 // ---- per-row (sum, sumsq) of a [R][C] matrix -> rowpart [R][1][2]

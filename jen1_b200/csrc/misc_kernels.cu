@@ -17,7 +17,7 @@ int pack_rows_per_entry() { return PK_ROWS; }
 
 template <typename T>
 __global__ void __launch_bounds__(256) pack_ncl_kernel(const float* __restrict__ x, T* __restrict__ out,
-                                                      float* __restrict__ stats, int C, int L) {
+                                                      float* __restrict__ stats, int C, int Cp, int L) {
   extern __shared__ float tile[];  // [PK_ROWS][C + 1]
   __shared__ float red[8][2];
   const int b = blockIdx.y, l0 = blockIdx.x * PK_ROWS;
@@ -38,9 +38,9 @@ __global__ void __launch_bounds__(256) pack_ncl_kernel(const float* __restrict__
     red[warp][1] = q;
   }
   __syncthreads();
-  for (int idx = threadIdx.x; idx < PK_ROWS * C; idx += 256) {
-    const int r = idx / C, c = idx - r * C;
-    if (l0 + r < L) stf(out + ((size_t)b * L + l0 + r) * C + c, tile[r * ld + c]);
+  for (int idx = threadIdx.x; idx < PK_ROWS * Cp; idx += 256) {
+    const int r = idx / Cp, c = idx - r * Cp;
+    if (l0 + r < L) stf(out + ((size_t)b * L + l0 + r) * Cp + c, c < C ? tile[r * ld + c] : 0.0f);
   }
   if (stats && threadIdx.x == 0) {
     float a = 0.f, qq = 0.f;
@@ -55,14 +55,14 @@ __global__ void __launch_bounds__(256) pack_ncl_kernel(const float* __restrict__
 }
 
 template <typename T>
-cudaError_t launch_pack_ncl(const float* x, T* out, float* stats, int Bx, int C, int L, cudaStream_t stream) {
+cudaError_t launch_pack_ncl(const float* x, T* out, float* stats, int Bx, int C, int Cp, int L, cudaStream_t stream) {
   dim3 grid((L + PK_ROWS - 1) / PK_ROWS, Bx);
   size_t smem = (size_t)PK_ROWS * (C + 1) * sizeof(float);
-  pack_ncl_kernel<T><<<grid, 256, smem, stream>>>(x, out, stats, C, L);
+  pack_ncl_kernel<T><<<grid, 256, smem, stream>>>(x, out, stats, C, Cp, L);
   return cudaGetLastError();
 }
-template cudaError_t launch_pack_ncl<float>(const float*, float*, float*, int, int, int, cudaStream_t);
-template cudaError_t launch_pack_ncl<bf16>(const float*, bf16*, float*, int, int, int, cudaStream_t);
+template cudaError_t launch_pack_ncl<float>(const float*, float*, float*, int, int, int, int, cudaStream_t);
+template cudaError_t launch_pack_ncl<bf16>(const float*, bf16*, float*, int, int, int, int, cudaStream_t);
 
 // =====================================================================================================
 // per-row (sum, sumsq): one warp per row
@@ -118,13 +118,28 @@ cudaError_t launch_time_features(const int64_t* t, const float* weights, float* 
 
 // =====================================================================================================
 // attention core.  One CTA = 16 query rows of one (batch row, head); 4 warps, each warp walks 4 query rows.
-// Keys are visited in tiles of 32 (one key per lane for the logits, one value column set per lane for PV)
+// Keys are visited in tiles of 64: K/V rows are fetched with 16-byte loads (8 channels), four independent
+// loads in flight per thread, into fp32 shared tiles; logits use one key per lane, PV one column set per lane,
 // with an fp32 online softmax.  Padded keys are multiplied by the context mask (logit 0, value 0) and stay in
 // the softmax, as the reference does; causal masking uses -FLT_MAX like reference add_mask (blocks.py:304-312).
 // =====================================================================================================
 namespace {
-constexpr int AT_QB = 16, AT_KT = 32, AT_MAXD = 128;
+constexpr int AT_QB = 16, AT_KT = 64, AT_MAXD = 128;
+
+__device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
+__device__ __forceinline__ void ld8(const bf16* p, float (&v)[8]) {
+  const uint4 t = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    v[2 * e] = __low2float(h[e]);
+    v[2 * e + 1] = __high2float(h[e]);
+  }
+}
+}  // namespace
 
 template <typename T>
 __global__ void __launch_bounds__(128) attention_kernel(const AttnParams p) {
@@ -138,11 +153,15 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnParams p) {
   const int bc = r % p.Bc;
   const bool fixed = p.cross && ((r >= p.Bc) || (p.drop && p.drop[bc]));
   const int S = p.M - 1;
+  const int cpr = d >> 3;  // 16-byte chunks per head row
 
-  for (int idx = tid; idx < AT_QB * d; idx += 128) {
-    const int qi = idx / d, e = idx - qi * d;
+  for (int idx = tid; idx < AT_QB * cpr; idx += 128) {
+    const int qi = idx / cpr, part = idx - qi * cpr;
     const int i = i0 + qi;
-    Qs[idx] = (i < p.N) ? ldf((const T*)p.q + ((size_t)r * p.N + i) * p.q_ld + p.q_off + h * d + e) : 0.f;
+    float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (i < p.N) ld8((const T*)p.q + ((size_t)r * p.N + i) * p.q_ld + p.q_off + h * d + part * 8, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) Qs[qi * d + part * 8 + e] = v[e];
   }
 
   float m_run[4], l_run[4], acc[4][AT_MAXD / 32];
@@ -156,64 +175,89 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnParams p) {
 
   for (int j0 = 0; j0 < p.M; j0 += AT_KT) {
     __syncthreads();
-    for (int idx = tid; idx < AT_KT * d; idx += 128) {
-      const int jj = idx / d, e = idx - jj * d;
-      const int j = j0 + jj;
-      float kv = 0.f, vv = 0.f;
-      if (j < p.M) {
-        const T* rowp;
-        float mk = 1.f;
-        int ko, vo;
-        if (!p.cross) {
-          rowp = (const T*)p.kv + ((size_t)r * p.N + j) * p.kv_ld;
-          ko = p.k_off;
-          vo = p.v_off;
-        } else {
-          if (j < S) {
-            rowp = fixed ? (const T*)p.kv_fixed + (size_t)j * p.kvc_ld
-                         : (const T*)p.kv_cond + ((size_t)bc * S + j) * p.kvc_ld;
-            if (p.mask) mk = p.mask[(size_t)bc * S + j];
+    const int nchunk = AT_KT * cpr;
+    for (int base = 0; base < nchunk; base += 128 * 2) {
+      float kv[2][8], vv[2][8];
+      float mk[2];
+      int jj[2], part[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int idx = base + u * 128 + tid;
+        jj[u] = idx / cpr;
+        part[u] = idx - jj[u] * cpr;
+        const int j = j0 + jj[u];
+        mk[u] = 1.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) kv[u][e] = vv[u][e] = 0.f;
+        if (idx < nchunk && j < p.M) {
+          const T* rowp;
+          int ko, vo;
+          if (!p.cross) {
+            rowp = (const T*)p.kv + ((size_t)r * p.N + j) * p.kv_ld;
+            ko = p.k_off;
+            vo = p.v_off;
           } else {
-            rowp = fixed ? (const T*)p.kv_fixed + (size_t)S * p.kvc_ld
-                         : (const T*)p.kv_time + (size_t)p.cond_row[r] * p.kvc_ld;
+            if (j < S) {
+              rowp = fixed ? (const T*)p.kv_fixed + (size_t)j * p.kvc_ld
+                           : (const T*)p.kv_cond + ((size_t)bc * S + j) * p.kvc_ld;
+              if (p.mask) mk[u] = p.mask[(size_t)bc * S + j];
+            } else {
+              rowp = fixed ? (const T*)p.kv_fixed + (size_t)S * p.kvc_ld
+                           : (const T*)p.kv_time + (size_t)p.cond_row[r] * p.kvc_ld;
+            }
+            ko = p.kvc_off;
+            vo = p.kvc_off + p.C;
           }
-          ko = p.kvc_off;
-          vo = p.kvc_off + p.C;
+          ld8(rowp + ko + h * d + part[u] * 8, kv[u]);
+          ld8(rowp + vo + h * d + part[u] * 8, vv[u]);
         }
-        kv = ldf(rowp + ko + h * d + e) * mk;
-        vv = ldf(rowp + vo + h * d + e) * mk;
       }
-      Ks[jj * ldk + e] = kv;
-      Vs[jj * ldk + e] = vv;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (base + u * 128 + tid < nchunk) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            Ks[jj[u] * ldk + part[u] * 8 + e] = kv[u][e] * mk[u];
+            Vs[jj[u] * ldk + part[u] * 8 + e] = vv[u][e] * mk[u];
+          }
+        }
+      }
     }
     __syncthreads();
-    const int j = j0 + lane;
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      const int qi = warp * 4 + a;
-      const int i = i0 + qi;
-      if (i >= p.N) continue;  // warp-uniform
-      float s = 0.f;
-      const float* qrow = Qs + qi * d;
-      const float* krow = Ks + lane * ldk;
-      for (int e = 0; e < d; ++e) s = fmaf(qrow[e], krow[e], s);
-      s *= p.scale;
-      if (p.causal && j > i + (p.M - p.N)) s = -FLT_MAX;
-      if (j >= p.M) s = -INFINITY;
-      const float mt = warp_max(s);
-      const float m_new = fmaxf(m_run[a], mt);
-      const float corr = expf(m_run[a] - m_new);
-      const float pj = expf(s - m_new);
-      l_run[a] = l_run[a] * corr + warp_sum(pj);
-      m_run[a] = m_new;
+    for (int half = 0; half < AT_KT / 32; ++half) {
+      const int jb = j0 + half * 32;
+      if (jb >= p.M) break;  // CTA-uniform
+      const int j = jb + lane;
 #pragma unroll
-      for (int t = 0; t < AT_MAXD / 32; ++t) acc[a][t] *= corr;
-      for (int jj = 0; jj < AT_KT; ++jj) {
-        const float pb = __shfl_sync(0xffffffffu, pj, jj);
+      for (int a = 0; a < 4; ++a) {
+        const int qi = warp * 4 + a;
+        const int i = i0 + qi;
+        if (i >= p.N) continue;  // warp-uniform
+        float s = 0.f;
+        const float* qrow = Qs + qi * d;
+        const float* krow = Ks + (half * 32 + lane) * ldk;
+        for (int e = 0; e < d; ++e) s = fmaf(qrow[e], krow[e], s);
+        s *= p.scale;
+        if (p.causal && j > i + (p.M - p.N)) s = -FLT_MAX;
+        if (j >= p.M) s = -INFINITY;
+        const float mt = warp_max(s);
+        const float m_new = fmaxf(m_run[a], mt);
+        const float corr = expf(m_run[a] - m_new);
+        const float pj = expf(s - m_new);
+        l_run[a] = l_run[a] * corr + warp_sum(pj);
+        m_run[a] = m_new;
 #pragma unroll
-        for (int t = 0; t < AT_MAXD / 32; ++t) {
-          const int e = lane + 32 * t;
-          if (e < d) acc[a][t] = fmaf(pb, Vs[jj * ldk + e], acc[a][t]);
+        for (int t = 0; t < AT_MAXD / 32; ++t) acc[a][t] *= corr;
+        const int kmax = min(32, p.M - jb);
+        for (int k2 = 0; k2 < kmax; ++k2) {
+          const float pb = __shfl_sync(0xffffffffu, pj, k2);
+          const float* vrow = Vs + (half * 32 + k2) * ldk;
+#pragma unroll
+          for (int t = 0; t < AT_MAXD / 32; ++t) {
+            const int e = lane + 32 * t;
+            if (e < d) acc[a][t] = fmaf(pb, vrow[e], acc[a][t]);
+          }
         }
       }
     }
@@ -233,9 +277,17 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnParams p) {
 
 template <typename T>
 cudaError_t launch_attention(const AttnParams& p, cudaStream_t stream) {
-  if (p.d > AT_MAXD) return cudaErrorInvalidValue;
+  if (p.d > AT_MAXD || (p.d & 7) || (p.q_ld & 7) || (p.q_off & 7) || (p.C & 7)) return cudaErrorInvalidValue;
+  if (!p.cross && ((p.kv_ld & 7) || (p.k_off & 7) || (p.v_off & 7))) return cudaErrorInvalidValue;
+  if (p.cross && ((p.kvc_ld & 7) || (p.kvc_off & 7))) return cudaErrorInvalidValue;
   dim3 grid((p.N + AT_QB - 1) / AT_QB, p.H, p.B2);
   size_t smem = (size_t)(AT_QB * p.d + 2 * AT_KT * (p.d + 1)) * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(attention_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(attention_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    attr = true;
+  }
   attention_kernel<T><<<grid, 128, smem, stream>>>(p);
   return cudaGetLastError();
 }
@@ -243,39 +295,58 @@ template cudaError_t launch_attention<float>(const AttnParams&, cudaStream_t);
 template cudaError_t launch_attention<bf16>(const AttnParams&, cudaStream_t);
 
 // =====================================================================================================
-// sampler epilogue: one thread per (sample, frame); channels walked three times (means, deviations, update).
+// sampler epilogue.  One CTA = 32 frames of one sample: the channels-last UNet output rows are staged through
+// shared memory (coalesced on both sides: [frame][channel] in, [channel][frame] out), one warp computes the
+// per-frame channel statistics, then every thread updates its (channel, frame) elements.
 // The arithmetic order of the reference expressions is kept (explicit _rn intrinsics, no FMA contraction):
 //   out_cfg = out_masked + (out - out_masked) * scale                               model.py:362
 //   pred    = phi * (out_cfg * (std(out) / std(out_cfg))) + (1 - phi) * out_cfg      model.py:366-369
 //   x0      = clamp(sqrt_recip_ac * x - sqrt_recipm1_ac * pred)                      gdm.py:89-93, 131
 //   x'      = x0 * sqrt(alpha_next) + c * pred + sigma * noise                       gdm.py:220-222
 // =====================================================================================================
-__global__ void __launch_bounds__(128) sampler_kernel(const SamplerParams p) {
-  const int l = blockIdx.x * blockDim.x + threadIdx.x;
-  const int b = blockIdx.y;
-  if (l >= p.L) return;
-  const int C = p.C;
-  const float* yc = p.y + ((size_t)b * p.L + l) * C;
-  const float* yu = p.y + ((size_t)(b + p.B) * p.L + l) * C;
-  float ratio = 1.0f;
+namespace {
+constexpr int SP_TL = 32;
+}
+__global__ void __launch_bounds__(256) sampler_kernel(const SamplerParams p) {
+  extern __shared__ float ssm[];  // yc [SP_TL][C+1] | yu [SP_TL][C+1] | ratio [SP_TL]
+  const int C = p.C, ld = C + 1;
+  float* yc = ssm;
+  float* yu = yc + SP_TL * ld;
+  float* ratio = yu + SP_TL * ld;
+  const int b = blockIdx.y, l0 = blockIdx.x * SP_TL;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nl = min(SP_TL, p.L - l0);
+  for (int idx = tid; idx < nl * C; idx += 256) {
+    const int fr = idx / C, c = idx - fr * C;
+    const float o = p.y[((size_t)b * p.L + l0 + fr) * C + c];
+    yc[fr * ld + c] = o;
+    if (p.cfg) {
+      const float u = p.y[((size_t)(b + p.B) * p.L + l0 + fr) * C + c];
+      yu[fr * ld + c] = __fadd_rn(u, __fmul_rn(__fsub_rn(o, u), p.emb_scale));  // out_cfg
+    }
+  }
+  __syncthreads();
   if (p.cfg && p.scale_cfg) {
-    float s1 = 0.f, s2 = 0.f;
-    for (int c = 0; c < C; ++c) {
-      const float o = ldf(yc + c), u = ldf(yu + c);
-      const float g = __fadd_rn(u, __fmul_rn(__fsub_rn(o, u), p.emb_scale));
-      s1 += o;
-      s2 += g;
+    for (int fr = warp; fr < nl; fr += 8) {
+      float s1 = 0.f, s2 = 0.f;
+      for (int c = lane; c < C; c += 32) {
+        s1 += yc[fr * ld + c];
+        s2 += yu[fr * ld + c];
+      }
+      s1 = warp_sum(s1);
+      s2 = warp_sum(s2);
+      const float m1 = s1 / (float)C, m2 = s2 / (float)C;
+      float v1 = 0.f, v2 = 0.f;
+      for (int c = lane; c < C; c += 32) {
+        const float a = yc[fr * ld + c] - m1, g = yu[fr * ld + c] - m2;
+        v1 += a * a;
+        v2 += g * g;
+      }
+      v1 = warp_sum(v1);
+      v2 = warp_sum(v2);
+      if (lane == 0) ratio[fr] = __fdiv_rn(sqrtf(v1 / (float)(C - 1)), sqrtf(v2 / (float)(C - 1)));
     }
-    const float m1 = s1 / (float)C, m2 = s2 / (float)C;
-    float v1 = 0.f, v2 = 0.f;
-    for (int c = 0; c < C; ++c) {
-      const float o = ldf(yc + c), u = ldf(yu + c);
-      const float g = __fadd_rn(u, __fmul_rn(__fsub_rn(o, u), p.emb_scale));
-      v1 += (o - m1) * (o - m1);
-      v2 += (g - m2) * (g - m2);
-    }
-    const float sd1 = sqrtf(v1 / (float)(C - 1)), sd2 = sqrtf(v2 / (float)(C - 1));
-    ratio = __fdiv_rn(sd1, sd2);
+    __syncthreads();
   }
   float k0 = 0, k1 = 0, k2 = 0, k3 = 0, k4 = 0, k5 = 0, k6 = 0;
   bool last = false;
@@ -284,48 +355,53 @@ __global__ void __launch_bounds__(128) sampler_kernel(const SamplerParams p) {
     k0 = cf[0]; k1 = cf[1]; k2 = cf[2]; k3 = cf[3]; k4 = cf[4]; k5 = cf[5]; k6 = cf[6];
     last = cf[7] != 0.f;
   }
-  for (int c = 0; c < C; ++c) {
-    float pred;
-    if (p.cfg) {
-      const float o = ldf(yc + c), u = ldf(yu + c);
-      const float g = __fadd_rn(u, __fmul_rn(__fsub_rn(o, u), p.emb_scale));
-      pred = p.scale_cfg ? __fadd_rn(__fmul_rn(p.phi, __fmul_rn(g, ratio)), __fmul_rn(p.one_minus_phi, g)) : g;
-    } else {
-      pred = ldf(yc + c);
-    }
-    const size_t xi = ((size_t)b * C + c) * p.L + l;
-    if (p.mode == 0) {
-      p.pred_out[xi] = pred;
-      continue;
-    }
-    const float xv = p.x[xi];
-    float x0, eps;
-    if (p.objective == 0) {
-      eps = pred;
-      x0 = __fsub_rn(__fmul_rn(k0, xv), __fmul_rn(k1, eps));
-      x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
-    } else {
-      if (p.objective == 1) {
-        x0 = pred;
+  const int fr = lane;
+  if (fr < nl) {
+    const float rt = (p.cfg && p.scale_cfg) ? ratio[fr] : 1.0f;
+    for (int c = warp; c < C; c += 8) {
+      float pred;
+      if (p.cfg) {
+        const float g = yu[fr * ld + c];
+        pred = p.scale_cfg ? __fadd_rn(__fmul_rn(p.phi, __fmul_rn(g, rt)), __fmul_rn(p.one_minus_phi, g)) : g;
       } else {
-        x0 = __fsub_rn(__fmul_rn(k2, xv), __fmul_rn(k3, pred));
+        pred = yc[fr * ld + c];
       }
-      x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
-      eps = __fdiv_rn(__fsub_rn(__fmul_rn(k0, xv), x0), k1);
+      const size_t xi = ((size_t)b * C + c) * p.L + l0 + fr;
+      if (p.mode == 0) {
+        p.pred_out[xi] = pred;
+        continue;
+      }
+      const float xv = p.x[xi];
+      float x0, eps;
+      if (p.objective == 0) {
+        eps = pred;
+        x0 = __fsub_rn(__fmul_rn(k0, xv), __fmul_rn(k1, eps));
+        x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
+      } else {
+        if (p.objective == 1) {
+          x0 = pred;
+        } else {
+          x0 = __fsub_rn(__fmul_rn(k2, xv), __fmul_rn(k3, pred));
+        }
+        x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
+        eps = __fdiv_rn(__fsub_rn(__fmul_rn(k0, xv), x0), k1);
+      }
+      float xn;
+      if (last) {
+        xn = x0;
+      } else {
+        xn = __fadd_rn(__fadd_rn(__fmul_rn(x0, k4), __fmul_rn(k5, eps)), __fmul_rn(k6, p.noise[xi]));
+      }
+      p.x_out[xi] = xn;
     }
-    float xn;
-    if (last) {
-      xn = x0;
-    } else {
-      xn = __fadd_rn(__fadd_rn(__fmul_rn(x0, k4), __fmul_rn(k5, eps)), __fmul_rn(k6, p.noise[xi]));
-    }
-    p.x_out[xi] = xn;
   }
 }
 
 cudaError_t launch_sampler(const SamplerParams& p, cudaStream_t stream) {
-  dim3 grid((p.L + 127) / 128, p.B);
-  sampler_kernel<<<grid, 128, 0, stream>>>(p);
+  dim3 grid((p.L + SP_TL - 1) / SP_TL, p.B);
+  const size_t smem = (size_t)(2 * SP_TL * (p.C + 1) + SP_TL) * sizeof(float);
+  if (smem > 48 * 1024) return cudaErrorInvalidValue;
+  sampler_kernel<<<grid, 256, smem, stream>>>(p);
   return cudaGetLastError();
 }
 
