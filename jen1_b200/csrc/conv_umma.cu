@@ -6,7 +6,7 @@
 //     D[cout, q] = sum_{seg} sum_{tap j} sum_{cin}  W_seg[wtap(z,j)][cout, cin] * P_seg[q + off(j), cin]
 //
 //   * A operand = weights.  Pre-packed at load time into 16 KB blobs (128 cout x 64 cin, the canonical K-major
-//     no-swizzle core-matrix layout) in exactly the order a CTA consumes them, so one thread streams them with
+//     128-byte-swizzle layout) in exactly the order a CTA consumes them, so one thread streams them with
 //     1-D bulk async copies (cp.async.bulk -> UBLKCP) through an mbarrier ring -- and starts doing so BEFORE the
 //     programmatic-dependent-launch wait, i.e. while the previous layer is still running.
 //   * B operand = the activation panel.  Producer warps read raw channels-last bf16 rows once, apply the
@@ -23,6 +23,7 @@
 //
 // Warp roles (192 threads): warps 0-3 build panels, then run the epilogue (TMEM lane quarter = warp index);
 // warp 4 lane 0 streams weights; warp 5 allocates TMEM and its lane 0 issues tcgen05.mma.
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -45,6 +46,7 @@ struct UmmaArgs {
   float* ws;       // split-K partial tiles
   int* counters;   // split-K tickets (zero between launches)
   int out_f32;
+  long long* timeline;  // optional per-launch phase clocks of CTA (0,0,0) (JEN1_TIMELINE debugging), else nullptr
 };
 
 // ---------------------------------------------------------------------------------------------- PTX helpers
@@ -53,13 +55,15 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+// Pure polling (test_wait): try_wait's hardware suspend was measured to wake ~1.5 us late when the phase is
+// completed by tcgen05.commit / bulk-copy transactions, which is as long as a whole layer of the deep UNet levels.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t a = smem_u32(bar);
   uint32_t done;
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
         : "r"(a), "r"(parity)
@@ -121,6 +125,18 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= (uint64_t)1 << 46;
   return d;
 }
+// K-major, 128-byte swizzle: rows of 128 B (64 bf16), the 16-byte chunk c of row r lives at chunk c ^ (r & 7);
+// SBO = 1024 B between 8-row groups; K advances inside the swizzle atom by adding bytes to the start address.
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t base_offset = 0) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024u >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(base_offset & 7u) << 49;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 
 struct TapGeom {
   int rho, off;
@@ -136,17 +152,25 @@ __device__ __forceinline__ TapGeom tap_geom(int shift0, int shift_step, int j, i
   return g;
 }
 
+__device__ __forceinline__ float ldf_cg(const bf16* p) {
+  const unsigned short u = __ldcg(reinterpret_cast<const unsigned short*>(p));
+  return __uint_as_float((uint32_t)u << 16);
+}
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
 // ---------------------------------------------------------------------------------------------- the kernel
-__global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_constant__ UmmaArgs A) {
+__global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_constant__ UmmaArgs A) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const ConvParams& p = A.p;
   const UmmaPlan& pl = A.pl;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  long long* tl = (A.timeline && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? A.timeline : nullptr;
+#define TL_MARK(i) do { if (tl) tl[i] = clock64(); } while (0)
+#define TL_GLOBAL(i) do { if (tl) { unsigned long long g_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_)); tl[i] = (long long)g_; } } while (0)
+  if (tid == 0) TL_MARK(0);
 
   // ---- work item
   const int nt = blockIdx.x, mt = blockIdx.y;
@@ -173,7 +197,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   int* ticket_slot = reinterpret_cast<int*>(tmem_slot + 1);         // [1]
   float* gmean = reinterpret_cast<float*>(misc + 256);              // [kMaxSlots][32]
   float* grstd = gmean + kMaxSlots * 32;                            // [kMaxSlots][32]
-  double* fine = reinterpret_cast<double*>(grstd + kMaxSlots * 32); // [2 sources][32 fine groups][2]
+  double* fine = reinterpret_cast<double*>(grstd + kMaxSlots * 32); // [kMaxSlots][2 sources][32 fine groups][2]
+  int* scrow = reinterpret_cast<int*>(fine + kMaxSlots * 2 * 32 * 2);  // [kMaxSlots] conditioning-table row per batch row
   // epilogue scratch aliases the weight ring (all MMAs have completed by then)
   float* sred = reinterpret_cast<float*>(a_ring);                   // [kMaxSlots][128][2]
   float* rowred = sred + kMaxSlots * 128 * 2;                       // [4][NT][2]
@@ -202,6 +227,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
   const uint32_t tmem_base = *tmem_slot;
   // TMEM is held: dependents may now be scheduled next to us without a TMEM-allocation deadlock.
   pdl_launch_dependents();
+  if (tid == 0) TL_MARK(1);
 
   if (warp == 4) {
     // ======================================================================== weight streamer
@@ -248,12 +274,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
           }
           mbar_wait(&a_full[s], (uint32_t)(k & 1));
           tc_fence_after();
+          if (i == 0) TL_MARK(9);
           const uint32_t abase = smem_u32(a_ring + (size_t)s * kABytes);
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
-            const uint64_t ad = make_desc(abase + (uint32_t)kk * 2u * 2048u, 2048u, 128u);
-            const uint64_t bd =
-                make_desc(pbase + ((uint32_t)(g.rho * 8 + kk * 2) * (uint32_t)pl.PS + (uint32_t)g.off) * 16u, lbo_b, 128u);
+            const uint64_t ad = make_desc_sw128(abase + (uint32_t)kk * 32u);
+            uint64_t bd;
+            if (pl.bsw == 0) {
+              bd = make_desc(pbase + ((uint32_t)(g.rho * 8 + kk * 2) * (uint32_t)pl.PS + (uint32_t)g.off) * 16u, lbo_b, 128u);
+            } else {  // swizzled panel: a tap is a whole-row (128 B) shift of the start address
+              const uint32_t sa = pbase + ((uint32_t)g.rho * (uint32_t)pl.PS + (uint32_t)g.off) * 128u + (uint32_t)kk * 32u;
+              bd = make_desc_sw128(sa, pl.bsw == 2 ? (sa >> 7) & 7u : 0u);
+            }
             umma_bf16(tmem_base, ad, bd, idesc, acc);
             acc = 1;
           }
@@ -262,79 +294,132 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
         umma_commit(&p_empty[pb]);
       }
       umma_commit(acc_full);
+      TL_MARK(10);
+      if (tl) {
+        mbar_wait(acc_full, 0);
+        TL_MARK(13);
+      }
     }
   } else {
     // ======================================================================== panel producers, then epilogue
-    pdl_wait();  // everything below reads what the previous kernels wrote
+    // Every load below is batched: addresses and validity are computed first, then all loads of a batch are issued
+    // back to back, then consumed -- a dependent L2/HBM round trip costs ~0.4-1 us and the layer chain is long.
     const ConvSeg& S0 = p.seg[0];
     const int Ct = S0.Cin;
     const int b_first = q0 / Lq;
     int b_last = (q0 + NT + pl.halo - 1) / Lq;
     if (b_last > p.B - 1) b_last = p.B - 1;
     const int nbl = b_last - b_first + 1;
+    const int kc = tid & 7, rr = tid >> 3;
+    const bool affine = p.mode == PRO_AFFINE;
+    const bool has_gn = affine && p.G > 0;
+    const bool has_film = affine && p.film != nullptr;
+    const int cpg = has_gn ? Ct / p.G : 1;
+    const int cl = tid;             // channel within the 128-wide M tile (== TMEM lane)
+    const int nch = mt * 128 + cl;  // output channel
+    float gam[8], bet[8];
+    auto load_gamma_beta = [&](int t) {  // GroupNorm affine of this thread's 8 channels in K step t (weights)
+      const int c0 = t * 64 + kc * 8;
+      if (has_gn && t < pl.steps0 && c0 < Ct) {
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + c0));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + c0 + 4));
+        const float4 e0 = __ldg(reinterpret_cast<const float4*>(p.beta + c0));
+        const float4 e1 = __ldg(reinterpret_cast<const float4*>(p.beta + c0 + 4));
+        gam[0] = g0.x; gam[1] = g0.y; gam[2] = g0.z; gam[3] = g0.w; gam[4] = g1.x; gam[5] = g1.y; gam[6] = g1.z; gam[7] = g1.w;
+        bet[0] = e0.x; bet[1] = e0.y; bet[2] = e0.z; bet[3] = e0.w; bet[4] = e1.x; bet[5] = e1.y; bet[6] = e1.z; bet[7] = e1.w;
+      }
+    };
+    // constants that do not depend on earlier kernels are fetched before the PDL wait
+    const float bias = p.bias ? __ldg(p.bias + nch) : 0.0f;
+    load_gamma_beta(st0);
 
+    pdl_wait();  // everything below reads what the previous kernels wrote
+    if (tid == 0) { TL_MARK(2); TL_GLOBAL(11); }
+
+    if (tid < nbl) scrow[tid] = p.cond_row ? __ldcg(p.cond_row + b_first + tid) : 0;
     // ---- GroupNorm statistics of the input for the batch rows this tile touches.  Deterministic two-level reduce:
     //      128 threads = 64 (source, fine group) items x 2 interleaved halves of the producer's per-tile partials,
     //      combined by one shuffle; then one thread per group folds its fine groups.
-    if (p.mode == PRO_AFFINE && p.G > 0) {
-      const int cpg = Ct / p.G;
-      const int item = tid >> 1, part = tid & 1;
-      const int fs = item >> 5, ffg = item & 31;
-      const ConvSrc& fsr = S0.s[fs];
-      for (int bl = 0; bl < nbl; ++bl) {
-        const int b = b_first + bl;
+    if (has_gn) {
+      // pass 1: fine-group sums of every (batch row, source, fine group) item; an item is split over `parts`
+      // lanes (interleaved entries) that are combined with shuffles in a fixed order
+      const int nitem = nbl * 64;
+      int parts = 1;
+      while (parts < 8 && nitem * parts * 2 <= kProducers) parts *= 2;
+      for (int base = 0; base < nitem * parts; base += kProducers) {
+        const int idx = base + tid;
+        const int item = idx / parts, part = idx - item * parts;
+        const int bl = item >> 6, fs = (item >> 5) & 1, ffg = item & 31;
         double a = 0.0, q = 0.0;
-        if (fsr.C > 0 && ffg < fsr.FG) {
-          const float2* st = reinterpret_cast<const float2*>(fsr.stats) + (size_t)(b % fsr.bmod) * fsr.n_ent * fsr.FG + ffg;
-#pragma unroll 4
-          for (int e = part; e < fsr.n_ent; e += 2) {
-            const float2 v = __ldg(st + (size_t)e * fsr.FG);
-            a += (double)v.x;
-            q += (double)v.y;
+        if (item < nitem) {
+          const ConvSrc& fsr = S0.s[fs];
+          if (fsr.C > 0 && ffg < fsr.FG) {
+            const int b = b_first + bl;
+            const float2* st = reinterpret_cast<const float2*>(fsr.stats) + (size_t)(b % fsr.bmod) * fsr.n_ent * fsr.FG + ffg;
+            for (int e0 = part; e0 < fsr.n_ent; e0 += parts * 16) {  // 16 independent L2 loads in flight
+              float2 buf[16];
+#pragma unroll
+              for (int u = 0; u < 16; ++u) {
+                const int e = e0 + u * parts;
+                buf[u] = e < fsr.n_ent ? __ldcg(st + (size_t)e * fsr.FG) : make_float2(0.f, 0.f);
+              }
+#pragma unroll
+              for (int u = 0; u < 16; ++u) {
+                a += (double)buf[u].x;
+                q += (double)buf[u].y;
+              }
+            }
           }
         }
-        a += __shfl_xor_sync(0xffffffffu, a, 1);
-        q += __shfl_xor_sync(0xffffffffu, q, 1);
-        if (part == 0) {
-          const double sc = (double)fsr.scale;
+        if (tid == 0 && base == 0) TL_MARK(14);
+        for (int o = 1; o < parts; o <<= 1) {
+          a += __shfl_xor_sync(0xffffffffu, a, o);
+          q += __shfl_xor_sync(0xffffffffu, q, o);
+        }
+        if (item < nitem && part == 0) {
+          const double sc = (double)S0.s[fs].scale;
           fine[item * 2] = a * sc;
           fine[item * 2 + 1] = q * sc * sc;
         }
-        bar_sync_producers();
-        if (tid < p.G) {
-          const int g = tid;
-          const int lo = g * cpg, hi = lo + cpg;
-          double ga = 0.0, gq = 0.0;
-          int off = 0;
-          for (int s = 0; s < 2; ++s) {
-            const ConvSrc& sr = S0.s[s];
-            if (sr.C > 0) {
-              const int olo = max(lo, off), ohi = min(hi, off + sr.C);
-              if (ohi > olo) {
-                const int gs = sr.C / sr.FG;
-                for (int fg = (olo - off) / gs; fg < (ohi - off) / gs; ++fg) {
-                  ga += fine[(s * 32 + fg) * 2];
-                  gq += fine[(s * 32 + fg) * 2 + 1];
-                }
+      }
+      bar_sync_producers();
+      if (tid == 0) TL_MARK(15);
+      // pass 2: one thread per (batch row, group)
+      for (int idx = tid; idx < nbl * p.G; idx += kProducers) {
+        const int bl = idx / p.G, g = idx - bl * p.G;
+        const int lo = g * cpg, hi = lo + cpg;
+        double ga = 0.0, gq = 0.0;
+        int off = 0;
+        for (int s = 0; s < 2; ++s) {
+          const ConvSrc& sr = S0.s[s];
+          if (sr.C > 0) {
+            const int olo = max(lo, off), ohi = min(hi, off + sr.C);
+            if (ohi > olo) {
+              const int gs = sr.C / sr.FG;
+              for (int fg = (olo - off) / gs; fg < (ohi - off) / gs; ++fg) {
+                ga += fine[((bl * 2 + s) * 32 + fg) * 2];
+                gq += fine[((bl * 2 + s) * 32 + fg) * 2 + 1];
               }
             }
-            off += sr.C;
           }
-          const double n = (double)(p.gn_real_c > 0 ? p.gn_real_c / p.G : cpg) * (double)S0.L;
-          const double mean = ga / n;
-          double var = gq / n - mean * mean;
-          if (var < 0.0) var = 0.0;
-          gmean[bl * 32 + g] = (float)mean;
-          grstd[bl * 32 + g] = (float)(1.0 / sqrt(var + (double)p.eps));
+          off += sr.C;
         }
-        bar_sync_producers();
+        const double n = (double)(p.gn_real_c > 0 ? p.gn_real_c / p.G : cpg) * (double)S0.L;
+        const double mean = ga / n;
+        double var = gq / n - mean * mean;
+        if (var < 0.0) var = 0.0;
+        gmean[bl * 32 + g] = (float)mean;
+        grstd[bl * 32 + g] = rsqrtf((float)var + p.eps);
       }
+      bar_sync_producers();
+    } else if (has_film) {
+      bar_sync_producers();  // scrow
     }
 
+    if (tid == 0) TL_MARK(3);
     // ---- panels
-    const int kc = tid & 7, rr = tid >> 3;
     float ca[8], cs[8];
-    int coef_b = -1, coef_t = -1;
+    int coef_b = -1;
     for (int t = st0; t < st1; ++t) {
       const int n = t - st0, pb = n & 1;
       const bool s1 = t >= pl.steps0;
@@ -348,96 +433,181 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
       const ConvSrc& sr = second ? S.s[1] : S.s[0];
       const int cc = second ? c0 - S.s[0].C : c0;
       const bool chan_ok = cc < sr.C;
+      if (n > 0) load_gamma_beta(t);
+      coef_b = -1;
+      // affine coefficients of (batch row b, this thread's 8 channels): a = gamma*rstd*scale*(film_s+1), ...
+      // split in two so the FiLM loads fly together with the first batch of activation loads
+      float fsv[8], fhv[8];
+      auto film_issue = [&](int b) {
+        if (has_film) {
+          const float* fp = p.film + (size_t)scrow[b - b_first] * p.film_stride + c0;
+          const float4 a0 = __ldcg(reinterpret_cast<const float4*>(fp)), a1 = __ldcg(reinterpret_cast<const float4*>(fp + 4));
+          const float4 h0 = __ldcg(reinterpret_cast<const float4*>(fp + Ct)), h1 = __ldcg(reinterpret_cast<const float4*>(fp + Ct + 4));
+          fsv[0] = a0.x; fsv[1] = a0.y; fsv[2] = a0.z; fsv[3] = a0.w; fsv[4] = a1.x; fsv[5] = a1.y; fsv[6] = a1.z; fsv[7] = a1.w;
+          fhv[0] = h0.x; fhv[1] = h0.y; fhv[2] = h0.z; fhv[3] = h0.w; fhv[4] = h1.x; fhv[5] = h1.y; fhv[6] = h1.z; fhv[7] = h1.w;
+        }
+      };
+      auto coef_finish = [&](int b) {
+        const int bl = b - b_first;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float a = sr.scale, sft = 0.0f;
+          if (has_gn) {
+            const int g = (c0 + e) / cpg;
+            const float ga = gam[e] * grstd[bl * 32 + g];
+            a = ga * sr.scale;
+            sft = bet[e] - gmean[bl * 32 + g] * ga;
+          }
+          if (has_film) {
+            const float fs1 = fsv[e] + 1.0f;
+            a = a * fs1;
+            sft = sft * fs1 + fhv[e];
+          }
+          ca[e] = a;
+          cs[e] = sft;
+        }
+        coef_b = b;
+      };
+      const bool need_coef = !s1 && affine && chan_ok && (has_gn || has_film);
+      if (need_coef) film_issue(b_first);  // common case: one batch row per tile
       if (n >= 2) mbar_wait(&p_empty[pb], (uint32_t)(((n >> 1) - 1) & 1));
       uint8_t* pan = panels + (size_t)pb * panel_bytes;
-      for (int rho = 0; rho < f; ++rho) {
-        for (int r = rr; r < R; r += 16) {
+      const int rows_all = f * R;  // (residue, row) pairs flattened: idx = rho * R + r
+      for (int i0 = rr; i0 < rows_all; i0 += 128) {
+        uint4 raw[8];
+        int bb[8];
+        bool ok[8];
+        float mu[8], rs[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int idx = i0 + 16 * u;
+          const int rho = idx / R, r = idx - rho * R;
           const int q = q0 + r;
           const int b = q / Lq;
           const int ml = q - b * Lq;
           const int irow = (ml + amin) * f + rho;
-          uint4 o = make_uint4(0u, 0u, 0u, 0u);
-          if (chan_ok && b < p.B && irow >= 0 && irow < S.L) {
-            const bf16* src = (const bf16*)sr.ptr + ((size_t)(b % sr.bmod) * S.L + irow) * sr.C + cc;
-            const uint4 raw = *reinterpret_cast<const uint4*>(src);
-            float v[8];
-            {
-              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                v[2 * e] = __low2float(h[e]);
-                v[2 * e + 1] = __high2float(h[e]);
+          bb[u] = b;
+          ok[u] = (idx < rows_all) && chan_ok && b < p.B && irow >= 0 && irow < S.L;
+          raw[u] = make_uint4(0u, 0u, 0u, 0u);
+          mu[u] = 0.f;
+          rs[u] = 1.f;
+          if (ok[u]) {
+            const size_t rowi = (size_t)(b % sr.bmod) * S.L + irow;
+            raw[u] = __ldcg(reinterpret_cast<const uint4*>((const bf16*)sr.ptr + rowi * sr.C + cc));
+            if (!s1 && !affine) {  // LayerNorm statistics of the row from the producer's per-tile partials
+              const float2* rp = reinterpret_cast<const float2*>(p.rowpart) + rowi * p.rp_nct;
+              float a = 0.f, qq = 0.f;
+#pragma unroll 8
+              for (int jj = 0; jj < p.rp_nct; ++jj) {
+                const float2 v2 = __ldcg(rp + jj);
+                a += v2.x;
+                qq += v2.y;
               }
+              const float inv = 1.0f / (float)sr.C;
+              const float m1 = a * inv;
+              float var = qq * inv - m1 * m1;
+              if (var < 0.0f) var = 0.0f;
+              mu[u] = m1;
+              rs[u] = 1.0f / sqrtf(var + p.ln_eps);
+            }
+          }
+        }
+        if (need_coef && i0 == rr) coef_finish(b_first);
+        if (tl && tid == 0 && n == 0 && i0 == rr) {
+          if (raw[0].x == 0x12345678u) tl[31] = 1;  // consume the load
+          TL_MARK(16);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int idx = i0 + 16 * u;
+          if (idx >= rows_all) break;
+          const int rho = idx / R, r = idx - rho * R;
+          uint4 o = make_uint4(0u, 0u, 0u, 0u);
+          if (ok[u]) {
+            float v[8];
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[u]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              v[2 * e] = __low2float(h[e]);
+              v[2 * e + 1] = __high2float(h[e]);
             }
             if (s1) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) v[e] *= sr.scale;
-            } else if (p.mode == PRO_AFFINE) {
-              if (coef_b != b || coef_t != t) {  // per-(batch row, channel chunk) affine coefficients
-                coef_b = b;
-                coef_t = t;
-                const int row = p.cond_row ? p.cond_row[b] : 0;
-                const int bl = b - b_first;
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  const int c = c0 + e;
-                  float a = sr.scale, s = 0.0f;
-                  if (p.G > 0) {
-                    const int g = c / (Ct / p.G);
-                    const float ga = p.gamma[c] * grstd[bl * 32 + g];
-                    a = ga * sr.scale;
-                    s = p.beta[c] - gmean[bl * 32 + g] * ga;
-                  }
-                  if (p.film) {
-                    const float fs = p.film[(size_t)row * p.film_stride + c] + 1.0f;
-                    const float fh = p.film[(size_t)row * p.film_stride + Ct + c];
-                    a = a * fs;
-                    s = s * fs + fh;
-                  }
-                  ca[e] = a;
-                  cs[e] = s;
+            } else if (affine) {
+              if (has_gn || has_film) {
+                if (coef_b != bb[u]) {
+                  film_issue(bb[u]);
+                  coef_finish(bb[u]);
                 }
-              }
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                float y = fmaf(ca[e], v[e], cs[e]);
-                if (p.act == ACT_SILU) y = silu_f(y);
-                v[e] = y;
-              }
-            } else {  // PRO_ROWNORM
-              const float* rp = p.rowpart + ((size_t)(b % sr.bmod) * S.L + irow) * p.rp_nct * 2;
-              float a = 0.f, qq = 0.f;
-              for (int jj = 0; jj < p.rp_nct; ++jj) {
-                a += rp[2 * jj];
-                qq += rp[2 * jj + 1];
-              }
-              const float inv = 1.0f / (float)sr.C;
-              const float mu = a * inv;
-              float var = qq * inv - mu * mu;
-              if (var < 0.0f) var = 0.0f;
-              const float rs = 1.0f / sqrtf(var + p.ln_eps);
+                for (int e = 0; e < 8; ++e) v[e] = fmaf(ca[e], v[e], cs[e]);
+              } else {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = (v[e] - mu) * rs;
+                for (int e = 0; e < 8; ++e) v[e] *= sr.scale;
+              }
+              if (p.act == ACT_SILU) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = silu_f(v[e]);
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = (v[e] - mu[u]) * rs[u];
             }
             o.x = pack2(v[0], v[1]);
             o.y = pack2(v[2], v[3]);
             o.z = pack2(v[4], v[5]);
             o.w = pack2(v[6], v[7]);
           }
-          *reinterpret_cast<uint4*>(pan + ((size_t)(rho * 8 + kc) * pl.PS + r) * 16) = o;
+          if (pl.bsw == 0) {
+            *reinterpret_cast<uint4*>(pan + ((size_t)(rho * 8 + kc) * pl.PS + r) * 16) = o;
+          } else {
+            *reinterpret_cast<uint4*>(pan + ((size_t)rho * pl.PS + r) * 128 + (size_t)((kc ^ (r & 7)) * 16)) = o;
+          }
         }
       }
+      if (tid == 0 && n == 0) TL_MARK(17);
       fence_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
       mbar_arrive(&p_full[pb]);
+      if (tid == 0 && n == 0) TL_MARK(4);
     }
+    if (tid == 0) TL_MARK(5);
 
-    // ---- epilogue
-    mbar_wait(acc_full, 0);
-    tc_fence_after();
-    const int cl = tid;                 // channel within the 128-wide M tile (== TMEM lane)
-    const int nch = mt * 128 + cl;      // output channel
+    // ---- epilogue.  Column metadata and residual values of a 16-column chunk are fetched as one batch; for the
+    //      first chunk that happens while the tensor core is still working.
     const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
     const int tile_id = (z * pl.m_tiles + mt) * pl.n_tiles + nt;
+    const int zoff = p.out_off0 + z * p.out_off_phase;
+    const bool want_stats = p.stats_out != nullptr;
+    const bool want_rows = p.rowpart_out != nullptr;
+    int eb = q0 / Lq, eml = q0 - eb * Lq;  // running (batch row, padded position) of the next column
+    int oi[16];
+    float rv[16];
+    uint32_t vmask = 0, bmask = 0;
+    auto chunk_meta = [&]() {
+      vmask = 0;
+      bmask = 0;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int o = eml * p.out_stride + zoff;
+        const bool valid = (eb < p.B) && (eml < p.Lm) && (o >= 0) && (o < p.Lout);
+        oi[j] = valid ? (eb * p.Lout + o) * p.Cout + nch : 0;
+        int ro = valid ? ((eb % p.res_bmod) * p.Lout + o) * p.Cout + nch : 0;
+        if (valid) vmask |= 1u << j;
+        ++eml;
+        if (eml == Lq) {
+          bmask |= 1u << j;
+          eml = 0;
+          ++eb;
+        }
+        rv[j] = (p.res && valid) ? ldf_cg((const bf16*)p.res + ro) : 0.0f;
+      }
+    };
+    chunk_meta();
+
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    if (tid == 0) TL_MARK(6);
     bool final_cta = true;
     const float* wsbase = nullptr;
     if (pl.splitk > 1) {
@@ -446,7 +616,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
         float v[16];
         tmem_ld16(trow + (uint32_t)c0, v);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) wp[(size_t)(c0 + j) * 128 + cl] = v[j];
+        for (int j = 0; j < 16; ++j) __stcg(wp + (size_t)(c0 + j) * 128 + cl, v[j]);
       }
       __threadfence();
       bar_sync_producers();
@@ -457,19 +627,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
       }
       bar_sync_producers();
       final_cta = (*ticket_slot == pl.splitk - 1);
+      if (tid == 0) TL_MARK(7);
       if (final_cta) {
         __threadfence();
         wsbase = A.ws + (size_t)tile_id * pl.splitk * NT * 128;
       }
     }
     if (final_cta) {
-      const float bias = p.bias ? p.bias[nch] : 0.0f;
-      const int zoff = p.out_off0 + z * p.out_off_phase;
-      const bool want_stats = p.stats_out != nullptr;
-      const bool want_rows = p.rowpart_out != nullptr;
-      int b = q0 / Lq, ml = q0 - b * Lq;
+      int sb = q0 / Lq;  // batch row of the statistics run in progress
       float colS = 0.f, colQ = 0.f;
       for (int c0 = 0; c0 < NT; c0 += 16) {
+        if (c0 > 0) chunk_meta();
         float v[16];
         if (wsbase == nullptr) {
           tmem_ld16(trow + (uint32_t)c0, v);
@@ -483,7 +651,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
               const float* wp = wsbase + (size_t)(s0 + u) * NT * 128 + (size_t)c0 * 128 + cl;
               const bool on = s0 + u < pl.splitk;
 #pragma unroll
-              for (int j = 0; j < 16; ++j) tv[u][j] = on ? __ldcg(wp + (size_t)j * 128) : 0.0f;
+              for (int j = 0; j < 16; ++j) tv[u][j] = (on && ((vmask >> j) & 1u)) ? __ldcg(wp + (size_t)j * 128) : 0.0f;
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u)
@@ -493,18 +661,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
         }
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const int o = ml * p.out_stride + zoff;
-          const bool valid = (b < p.B) && (ml < p.Lm) && (o >= 0) && (o < p.Lout);
+          const bool valid = (vmask >> j) & 1u;
           float x = 0.0f;
           if (valid) {
             x = v[j] + bias;
             if (p.epi_act == ACT_GELU) x = gelu_f(x);
-            const size_t oi = ((size_t)b * p.Lout + o) * p.Cout + nch;
-            if (p.res) x += ldf((const bf16*)p.res + ((size_t)(b % p.res_bmod) * p.Lout + o) * p.Cout + nch);
+            x += rv[j];
             if (A.out_f32) {
-              ((float*)p.out)[oi] = x;
+              ((float*)p.out)[oi[j]] = x;
             } else {
-              ((bf16*)p.out)[oi] = __float2bfloat16_rn(x);
+              ((bf16*)p.out)[oi[j]] = __float2bfloat16_rn(x);
             }
           }
           colS += x;
@@ -516,20 +682,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
               rowred[((size_t)warp * NT + c0 + j) * 2 + 1] = rq;
             }
           }
-          // advance to the next padded position; flush the per-batch-row column sums at a row boundary
-          ++ml;
+          // flush the per-batch-row column sums at a row boundary / at the end of the tile
           const bool last_col = (c0 + j == NT - 1);
-          if (ml == Lq || last_col) {
-            if (want_stats && b <= b_last && b - b_first < kMaxSlots) {
-              sred[((size_t)(b - b_first) * 128 + cl) * 2] = colS;
-              sred[((size_t)(b - b_first) * 128 + cl) * 2 + 1] = colQ;
+          const bool bnd = (bmask >> j) & 1u;
+          if (bnd || last_col) {
+            if (want_stats && sb <= b_last && sb - b_first < kMaxSlots) {
+              sred[((size_t)(sb - b_first) * 128 + cl) * 2] = colS;
+              sred[((size_t)(sb - b_first) * 128 + cl) * 2 + 1] = colQ;
             }
             colS = 0.f;
             colQ = 0.f;
-            if (ml == Lq) {
-              ml = 0;
-              ++b;
-            }
+            if (bnd) ++sb;
           }
         }
       }
@@ -586,6 +749,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_umma_kernel(const __grid_con
     }
   }
 
+  if (tid == 0) { TL_MARK(8); TL_GLOBAL(12); }
   tc_fence_before();
   __syncthreads();
   if (warp == 5) {
@@ -655,9 +819,19 @@ UmmaPlan conv_umma_plan(const ConvParams& p, bool want_stats, size_t ws_capacity
   pl.NT = NT;
   pl.n_tiles = (int)((nq + NT - 1) / NT);
   pl.R = NT + pl.halo;
-  pl.PS = pl.R | 1;  // odd panel stride (in 16-byte units): conflict-free producer stores
-  pl.panel_bytes = f * 8 * pl.PS * 16;
-  pl.panel_bytes = round_up(pl.panel_bytes, 128);
+  static int bsw_env = -1;
+  if (bsw_env < 0) {
+    const char* e = getenv("JEN1_BSW");
+    bsw_env = e ? atoi(e) : 1;
+  }
+  pl.bsw = bsw_env;
+  if (pl.bsw == 0) {
+    pl.PS = pl.R | 1;  // odd panel stride (in 16-byte units): conflict-free producer stores
+    pl.panel_bytes = round_up(f * 8 * pl.PS * 16, 1024);
+  } else {
+    pl.PS = round_up(pl.R, 8);  // rows per sub-panel (128-byte rows, 128-byte swizzle, 1024-byte aligned)
+    pl.panel_bytes = f * pl.PS * 128;
+  }
   int tc = 32;
   while (tc < NT) tc <<= 1;
   pl.tmem_cols = tc;
@@ -674,7 +848,7 @@ UmmaPlan conv_umma_plan(const ConvParams& p, bool want_stats, size_t ws_capacity
   pl.splitk = sk;
   pl.ws_bytes = sk > 1 ? (size_t)tiles * sk * NT * 128 * sizeof(float) : 0;
   // shared memory: two panels + as many 16 KB weight stages as fit in ~half an SM (two CTAs co-reside under PDL)
-  const int misc = 256 + 2 * kMaxSlots * 32 * 4 + 2 * 32 * 2 * 8;
+  const int misc = 256 + 2 * kMaxSlots * 32 * 4 + kMaxSlots * 2 * 32 * 2 * 8 + kMaxSlots * 4;
   const int budget = 110 * 1024;
   int stages = (budget - 2 * pl.panel_bytes - misc) / kABytes;
   const int scratch = (kMaxSlots * 128 * 2 + 4 * NT * 2) * 4;  // epilogue scratch aliases the ring
@@ -694,8 +868,8 @@ size_t conv_umma_packed_elems(int Cin, int Cout, int ntaps) {
 }
 
 // Host-side packing of a conv weight W[tap][cin][cout] (fp32, the engine's logical layout) into the blob stream
-// consumed by the kernel: blob (mt, phase z, cin block cb, tap j) = rows cout (128) x k cin (64), element (r, k) at
-// ((k / 8) * 128 + r) * 8 + (k % 8).  `wtap(z, j) = wtap0 + z * wtap_phase + j * wtap_step` selects the source tap.
+// consumed by the kernel: blob (mt, phase z, cin block cb, tap j) = rows cout (128) x k cin (64) in the 128-byte
+// swizzled K-major layout: element (r, k) at r * 64 + ((k / 8) ^ (r % 8)) * 8 + (k % 8).  `wtap(z, j) = wtap0 + z * wtap_phase + j * wtap_step` selects the source tap.
 void conv_umma_pack(const float* w, int Cin, int Cout, int nphase, int taps_per_phase, int wtap0, int wtap_phase,
                     int wtap_step, uint16_t* out_bf16) {
   const int ncb = (Cin + 63) / 64, nmt = Cout / 128;
@@ -712,7 +886,7 @@ void conv_umma_pack(const float* w, int Cin, int Cout, int nphase, int taps_per_
               float v = 0.0f;
               if (cin < Cin) v = w[((size_t)tap * Cin + cin) * Cout + mt * 128 + r];
               __nv_bfloat16 h = __float2bfloat16_rn(v);
-              dst[((size_t)(k / 8) * 128 + r) * 8 + (k % 8)] = *reinterpret_cast<uint16_t*>(&h);
+              dst[(size_t)r * 64 + (size_t)(((k / 8) ^ (r & 7)) * 8) + (k % 8)] = *reinterpret_cast<uint16_t*>(&h);
             }
           }
         }
@@ -723,7 +897,7 @@ cudaError_t conv_umma_init() {
 }
 
 cudaError_t launch_conv_umma(const ConvParams& p, const UmmaPlan& pl, const void* w0, const void* w1, float* ws,
-                             int* counters, bool out_f32, bool pdl, cudaStream_t stream) {
+                             int* counters, bool out_f32, bool pdl, cudaStream_t stream, long long* timeline) {
   UmmaArgs a;
   a.p = p;
   a.pl = pl;
@@ -732,6 +906,7 @@ cudaError_t launch_conv_umma(const ConvParams& p, const UmmaPlan& pl, const void
   a.ws = ws;
   a.counters = counters;
   a.out_f32 = out_f32 ? 1 : 0;
+  a.timeline = timeline;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(pl.n_tiles, pl.m_tiles, p.nphase * pl.splitk);

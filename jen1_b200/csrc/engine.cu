@@ -677,7 +677,8 @@ Act Engine::conv_build(const DConv& W, int Bout, const Act& a0, const Act* a1, f
   if (plan.ok) {
     if (dry_) return out;
     if (!ok_) return out;
-    cudaError_t e = launch_conv_umma(p, plan, W.wu, W2 ? W2->wu : nullptr, umma_ws_, umma_counters_, out.f32, use_pdl_, st_);
+    long long* tl = (timeline_ && tl_ops_ < 1024) ? timeline_ + (size_t)(tl_ops_++) * 32 : nullptr;
+    cudaError_t e = launch_conv_umma(p, plan, W.wu, W2 ? W2->wu : nullptr, umma_ws_, umma_counters_, out.f32, use_pdl_, st_, tl);
     ++launches_;
     ++umma_launches_;
     ck(e, "tcgen05 conv launch");
@@ -1136,6 +1137,11 @@ int Engine::forward(const float* x, const float* cc, const int32_t* cond_rows, c
   debug_ = true;
   op_index_ = 0;
   trace_ = getenv("JEN1_TRACE") != nullptr;
+  if (getenv("JEN1_TIMELINE") && !timeline_) {
+    cudaMalloc((void**)&timeline_, 1024 * 32 * sizeof(long long));
+  }
+  if (timeline_) cudaMemsetAsync(timeline_, 0, 1024 * 32 * sizeof(long long), st);
+  tl_ops_ = 0;
   taps_.clear();
   arena_off_ = 0;
   if (!upload_ctl(c, st)) return 1;
@@ -1160,13 +1166,41 @@ int Engine::forward(const float* x, const float* cc, const int32_t* cond_rows, c
   sp.pred_out = out;
   ck(launch_sampler(sp, st), "sampler launch");
   ++launches_;
+  if (timeline_ && ok_) dump_timeline(st);
   return ok_ ? 0 : 1;
+}
+
+// Debugging aid (JEN1_TIMELINE): per-op phase clocks of CTA (0,0,0) of every tcgen05 conv launch.
+void Engine::dump_timeline(cudaStream_t st) {
+  std::vector<long long> h(1024 * 32);
+  cudaStreamSynchronize(st);
+  cudaMemcpy(h.data(), timeline_, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+  long long prev_end = 0, sum_gap = 0, sum_body = 0;
+  for (int i = 0; i < tl_ops_ && i < 1024; ++i) {
+    const long long* t = &h[(size_t)i * 32];
+    if (t[0] == 0) continue;
+    // cycles relative to the return of griddepcontrol.wait; "gap" = ns between the previous op's CTA-0 end and
+    // this op's wait return; "body" = ns from wait return to CTA-0 end
+    const long long gap = prev_end ? t[11] - prev_end : 0;
+    sum_gap += gap;
+    sum_body += t[12] - t[11];
+    fprintf(stderr, "[jen1-tl] u%03d gap_ns %lld body_ns %lld | cyc: early %lld st_loads %lld st_bar1 %lld stats %lld raw0 %lld xform0 %lld panel0 %lld panels %lld accfull %lld ticket %lld end %lld | mma first_a %lld issued %lld done %lld\n",
+            i, gap, t[12] - t[11], t[2] - t[0], t[14] ? t[14] - t[2] : 0, t[15] ? t[15] - t[2] : 0, t[3] - t[2],
+            t[16] - t[2], t[17] - t[2], t[4] - t[2], t[5] - t[2], t[6] - t[2],
+            t[7] ? t[7] - t[2] : 0, t[8] - t[2], t[9] - t[2], t[10] - t[2], t[13] - t[2]);
+    prev_end = t[12];
+  }
+  fprintf(stderr, "[jen1-tl] total: %d tcgen05 ops, sum gap %.1f us, sum body %.1f us\n", tl_ops_, sum_gap / 1e3, sum_body / 1e3);
 }
 
 // ============================================================================================ sampler
 int Engine::sample_begin(const float* coef_host, int S, const float* cc, int B, int T, int causal, float emb_scale,
                          int scale_cfg, float phi, int objective, int use_graph, cudaStream_t st) {
   ok_ = true;
+  if (getenv("JEN1_TIMELINE") && !timeline_) {
+    cudaMalloc((void**)&timeline_, 1024 * 32 * sizeof(long long));
+    cudaMemset(timeline_, 0, 1024 * 32 * sizeof(long long));
+  }
   if (!finalized_) return fail("engine not finalized");
   cudaSetDevice(device_);
   ok_ = true;
@@ -1237,6 +1271,7 @@ int Engine::sample_step(int step, float* x, const float* noise, const uint8_t* d
 
   auto body = [&]() -> bool {
     arena_off_ = smp_.arena_base;
+    tl_ops_ = 0;
     Act xpk, y, unused;
     if (!pack_inputs(x, B, T, &xpk, false, nullptr, &unused)) return false;
     if (!unet(xpk, smp_.ccpk, B, B2, T, smp_.causal != 0, &y)) return false;
@@ -1297,6 +1332,10 @@ int Engine::sample_step(int step, float* x, const float* noise, const uint8_t* d
   if (!ck(cudaGraphLaunch(smp_.exec, st), "graph launch")) return 1;
   launches_ += smp_.launches_per_step;
   umma_launches_ += smp_.umma_per_step;
+  if (timeline_) {
+    const char* e = getenv("JEN1_TIMELINE_STEP");
+    if (e && atoi(e) == step) dump_timeline(st);
+  }
   return 0;
 }
 

@@ -209,6 +209,9 @@ class Engine {
   size_t umma_ws_cap_ = 0;
   int* umma_counters_ = nullptr;
   int64_t umma_launches_ = 0;
+  long long* timeline_ = nullptr;
+  int tl_ops_ = 0;
+  void dump_timeline(cudaStream_t st);
   // arena
   char* arena_ = nullptr;
   size_t arena_cap_ = 0, arena_off_ = 0;

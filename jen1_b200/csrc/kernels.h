@@ -29,6 +29,7 @@ struct UmmaPlan {
   int R, PS, panel_bytes; // panel rows, panel stride (16-byte units), bytes of one panel (all sub-panels)
   int steps0, steps1;     // 64-channel K blocks of segment 0 / 1
   int stages, tmem_cols;
+  int bsw;                // activation-panel layout: 0 = no swizzle (chunk-major row panels), 1/2 = 128-byte swizzle
   int E_max;              // GroupNorm partial entries per batch row (per phase) this launch writes
   size_t smem, ws_bytes;
 };
@@ -38,7 +39,8 @@ void conv_umma_pack(const float* w_tap_cin_cout, int Cin, int Cout, int nphase, 
                     int wtap_phase, int wtap_step, uint16_t* out_bf16);
 cudaError_t conv_umma_init();
 cudaError_t launch_conv_umma(const ConvParams& p, const UmmaPlan& plan, const void* w0_packed, const void* w1_packed,
-                             float* ws, int* counters, bool out_f32, bool pdl, cudaStream_t stream);
+                             float* ws, int* counters, bool out_f32, bool pdl, cudaStream_t stream,
+                             long long* timeline = nullptr);
 
 // ---- boundary: [Bx][C][L] fp32 (reference layout) -> channels-last T [Bx][L][Cp] (channels C..Cp-1 zero-filled so
 //      rows stay 16-byte aligned for the tcgen05 path) + GroupNorm partials (FG = 1)
