@@ -57,6 +57,7 @@ class GaussianDiffusion:
         self.use_fp16 = use_fp16  # kept for signature parity; the engine's precision is set on the model
         self.rng_device = rng_device
         self.use_cuda_graph = use_cuda_graph
+        self.shard = None  # (lo, hi, global_batch) while a sharded sample() is running (jen1_b200/sharding.py)
         self.num_timesteps = steps
         self.sampling_timesteps = steps if sampling_timesteps is None else sampling_timesteps
         assert self.sampling_timesteps <= self.num_timesteps
@@ -155,17 +156,30 @@ class GaussianDiffusion:
         return pred_noise, x_start
 
     # ---- RNG helpers ---------------------------------------------------------------------------------------
+    def _draw_shape(self, shape):
+        """With `self.shard = (lo, hi, B)` (jen1_b200.sharding) the FULL-batch tensor is drawn and sliced, so a
+        sharded run consumes the same random stream as the single-device run."""
+        sh = self.shard
+        if sh is not None and len(shape) > 0 and shape[0] == sh[1] - sh[0]:
+            return (sh[2],) + tuple(shape[1:]), slice(sh[0], sh[1])
+        return tuple(shape), None
+
     def _randn(self, shape, device):
+        full, sl = self._draw_shape(shape)
         if self.rng_device is not None and torch.device(self.rng_device) != torch.device(device):
-            return torch.randn(shape, device=self.rng_device).to(device)
-        return torch.randn(shape, device=device)
+            out = torch.randn(full, device=self.rng_device)
+            return (out if sl is None else out[sl]).to(device)
+        out = torch.randn(full, device=device)
+        return out if sl is None else out[sl].contiguous()
 
     def _bernoulli(self, b, device):
         p = float(self.cfg_dropout_proba)
         if p == 1:
             return torch.ones((b, 1, 1), device=device, dtype=torch.bool)
         rd = device if self.rng_device is None else self.rng_device
-        return torch.bernoulli(torch.full((b, 1, 1), p, device=rd)).to(torch.bool).to(device)
+        full, sl = self._draw_shape((b, 1, 1))
+        out = torch.bernoulli(torch.full(full, p, device=rd)).to(torch.bool)
+        return (out if sl is None else out[sl]).to(device)
 
     # ---- samplers ---------------------------------------------------------------------------------------------
     @torch.no_grad()
@@ -229,8 +243,8 @@ class GaussianDiffusion:
                     audios.append(x.clone())
                 last = time_next < 0
                 if not last:
-                    if self.rng_device is not None and torch.device(self.rng_device) != device:
-                        noise.copy_(torch.randn(tuple(x.shape), device=self.rng_device))
+                    if self.shard is not None or (self.rng_device is not None and torch.device(self.rng_device) != device):
+                        noise.copy_(self._randn(tuple(x.shape), device))
                     else:
                         noise.normal_()
                 eng.sample_step(i, x, noise, drop)
