@@ -104,7 +104,8 @@ int jen1_sample_step(void* handle, int step, float* x, const float* noise, const
 /* Introspection for tests / benchmarks. */
 int64_t jen1_engine_launch_count(void* handle);        /* kernels launched (or replayed) so far */
 int64_t jen1_engine_weight_bytes(void* handle);        /* device bytes of packed weights streamed per step */
-int64_t jen1_engine_umma_launch_count(void* handle);   /* how many of those launches were the tcgen05 kernel */
+int64_t jen1_engine_umma_launch_count(void* handle);   /* how many of those launches were the tcgen05 conv kernel */
+int64_t jen1_engine_umma_attn_launch_count(void* handle); /* ... and the tcgen05 attention kernel */
 int jen1_engine_debug_tensor(void* handle, const char* name, float* host_out, int64_t capacity, int64_t* shape3);
 
 #ifdef __cplusplus

@@ -1,0 +1,403 @@
+// tcgen05 / TMEM attention core for bf16 storage on sm_100a (reference jen1/model/blocks.py:355-380 with the
+// key/value masking of :431-434): softmax(q k^T * scale) v for one (batch row, head, 128-query tile) per CTA.
+//
+//   S[query, key] = Q K^T     tcgen05.mma, M = 128 queries (TMEM lanes), N = keys padded to 16 (<= 256 TMEM columns),
+//                             K = head dim; Q and K staged K-major in 128-byte-swizzled shared-memory tiles
+//   P = softmax(S * scale)    warp-specialised: the four softmax warps own one query row per thread (TMEM lane ==
+//                             thread), two passes over the TMEM row (max, then exp / sum), fp32; P is written bf16
+//                             into a K-major swizzled tile that aliases the (now dead) Q / K tiles
+//   O = P V                   tcgen05.mma, M = 128 queries, N = head dim, K = keys; V is consumed as an MN-major
+//                             operand straight from its [key][channel] layout (no transpose), O re-uses S's columns
+//   out = O / rowsum(P)       tcgen05.ld -> registers -> 16-byte bf16 stores
+//
+// Padded context keys are multiplied by the context mask (logit 0, value 0) and STAY in the softmax, exactly as the
+// reference does; causal masking uses -FLT_MAX like reference add_mask (blocks.py:304-312); keys beyond the real
+// key count are excluded (-inf).  Cross-attention keys/values come from the hoisted caches: per sample either the
+// prompt rows + the per-step time-token row, or (cond-dropout / unconditional CFG half) the learned null embedding.
+//
+// Warp roles (256 threads): all 8 warps stage Q / K / V (16-byte loads, 8 in flight per thread); warps 0-3 then
+// run softmax + epilogue; warp 4 allocates TMEM and its lane 0 issues the MMAs.  PDL-aware: the kernel signals its
+// dependents right after TMEM allocation and waits for its producer before the first activation load.
+#include <float.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace jen1 {
+
+namespace {
+
+constexpr int kAtThreads = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory matrix descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor, version 1).  For a K-major operand
+// the leading-dimension field is unused; for an MN-major operand it is the stride between 64-element MN blocks and
+// the stride field is the distance between groups of 8 K rows.
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+struct AttnGeom {
+  int KP;         // keys padded to a multiple of 16 (MMA N of S, MMA K extent of PV)
+  int KR;         // key rows of the K / V tiles (KP rounded up to 8)
+  int DB;         // 64-channel blocks of the head dim
+  int cpr_shift;  // log2(head dim / 8): 16-byte chunks per head row
+  int tmem_cols;
+  uint32_t off_k, off_v, off_p;  // byte offsets of the tiles (Q at 0; P aliases Q / K)
+  uint32_t smem;
+};
+
+__global__ void __launch_bounds__(kAtThreads, 1) attn_umma_kernel(const __grid_constant__ AttnParams p,
+                                                                   const __grid_constant__ AttnGeom g) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int i0 = blockIdx.x * 128, h = blockIdx.y, r = blockIdx.z;
+  const int d = p.d;
+  uint8_t* Qs = smem;
+  uint8_t* Ks = smem + g.off_k;
+  uint8_t* Vs = smem + g.off_v;
+  uint8_t* Ps = smem + g.off_p;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + g.smem - 64);  // in_full, s_full, p_full, o_full
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+
+  if (tid == 0) {
+    mbar_init(&bars[0], kAtThreads);
+    mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 128);
+    mbar_init(&bars[3], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)g.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  // ---- per-CTA key/value source (values written before this step's kernel chain: safe ahead of the wait)
+  const int bc = r % p.Bc;
+  const bool fixed = p.cross && ((r >= p.Bc) || (p.drop && p.drop[bc]));
+  const int S = p.M - 1;
+  const int trow_time = p.cross ? p.cond_row[r] : 0;
+  const int cpr = 1 << g.cpr_shift;
+
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  // ---- stage Q, K, V: items = 16-byte chunks; [0, nq) Q chunks, then K chunks, then V chunks
+  {
+    const int nq = 128 << g.cpr_shift;
+    const int nk = g.KR << g.cpr_shift;
+    const int total = nq + 2 * nk;
+    for (int base = 0; base < total; base += kAtThreads * 8) {
+      uint4 val[8];
+      float mk[8];
+      uint32_t dst[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int it = base + u * kAtThreads + tid;
+        val[u] = make_uint4(0u, 0u, 0u, 0u);
+        mk[u] = 1.0f;
+        dst[u] = 0xffffffffu;
+        if (it < total) {
+          int kind, idx;
+          if (it < nq) {
+            kind = 0;
+            idx = it;
+          } else if (it < nq + nk) {
+            kind = 1;
+            idx = it - nq;
+          } else {
+            kind = 2;
+            idx = it - nq - nk;
+          }
+          const int row = idx >> g.cpr_shift, part = idx & (cpr - 1);
+          const int blk = part >> 3, ch = part & 7;
+          const uint32_t tile = kind == 0 ? 0u : (kind == 1 ? g.off_k : g.off_v);
+          const uint32_t rows_per_blk = kind == 0 ? 128u : (uint32_t)g.KR;
+          dst[u] = tile + ((uint32_t)blk * rows_per_blk + (uint32_t)row) * 128u + (uint32_t)((ch ^ (row & 7)) * 16);
+          const bf16* src = nullptr;
+          if (kind == 0) {
+            const int i = i0 + row;
+            if (i < p.N) src = (const bf16*)p.q + ((size_t)r * p.N + i) * p.q_ld + p.q_off + h * d + part * 8;
+          } else if (row < p.M) {
+            const int j = row;
+            if (!p.cross) {
+              src = (const bf16*)p.kv + ((size_t)r * p.N + j) * p.kv_ld + (kind == 1 ? p.k_off : p.v_off) + h * d + part * 8;
+            } else {
+              const bf16* rowp;
+              if (j < S) {
+                rowp = fixed ? (const bf16*)p.kv_fixed + (size_t)j * p.kvc_ld
+                             : (const bf16*)p.kv_cond + ((size_t)bc * S + j) * p.kvc_ld;
+                if (p.mask) mk[u] = __ldg(p.mask + (size_t)bc * S + j);
+              } else {
+                rowp = fixed ? (const bf16*)p.kv_fixed + (size_t)S * p.kvc_ld
+                             : (const bf16*)p.kv_time + (size_t)trow_time * p.kvc_ld;
+              }
+              src = rowp + p.kvc_off + (kind == 2 ? p.C : 0) + h * d + part * 8;
+            }
+          }
+          if (src) val[u] = __ldcg(reinterpret_cast<const uint4*>(src));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (dst[u] != 0xffffffffu) {
+          uint4 o = val[u];
+          if (mk[u] != 1.0f) {
+            const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&val[u]);
+            o.x = pack2(__low2float(hh[0]) * mk[u], __high2float(hh[0]) * mk[u]);
+            o.y = pack2(__low2float(hh[1]) * mk[u], __high2float(hh[1]) * mk[u]);
+            o.z = pack2(__low2float(hh[2]) * mk[u], __high2float(hh[2]) * mk[u]);
+            o.w = pack2(__low2float(hh[3]) * mk[u], __high2float(hh[3]) * mk[u]);
+          }
+          *reinterpret_cast<uint4*>(smem + dst[u]) = o;
+        }
+      }
+    }
+    // chunks beyond the head dim inside the last 64-channel block must read as zero (d = 16 / 32)
+    if (cpr < 8) {
+      const int rows_all = 128 + 2 * g.KR;
+      const int zc = 8 - cpr;
+      for (int it = tid; it < rows_all * zc; it += kAtThreads) {
+        const int row_all = it / zc, ch = cpr + (it - row_all * zc);
+        uint32_t tile;
+        int row;
+        if (row_all < 128) {
+          tile = 0u;
+          row = row_all;
+        } else if (row_all < 128 + g.KR) {
+          tile = g.off_k;
+          row = row_all - 128;
+        } else {
+          tile = g.off_v;
+          row = row_all - 128 - g.KR;
+        }
+        *reinterpret_cast<uint4*>(smem + tile + (uint32_t)row * 128u + (uint32_t)((ch ^ (row & 7)) * 16)) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+    fence_async_smem();
+    mbar_arrive(&bars[0]);
+  }
+
+  if (warp == 4 && lane == 0) {
+    // ======================================================================== MMA issuer
+    // instruction descriptor: fp32 accumulate, bf16 A/B, M = 128; bit 16 = B operand is MN-major
+    const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(g.KP >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(d >> 3) << 17) | ((128u >> 4) << 24);
+    mbar_wait(&bars[0], 0);
+    tc_fence_after();
+    uint32_t acc = 0;
+    for (int db = 0; db < g.DB; ++db) {
+      const int kmax = min(4, (d - db * 64) / 16);
+      for (int kk = 0; kk < kmax; ++kk) {
+        const uint64_t ad = make_desc_sw128(smem_u32(Qs) + (uint32_t)db * 128u * 128u + (uint32_t)kk * 32u, 16u, 1024u);
+        const uint64_t bd = make_desc_sw128(smem_u32(Ks) + (uint32_t)db * (uint32_t)g.KR * 128u + (uint32_t)kk * 32u, 16u, 1024u);
+        umma_bf16(tmem_base, ad, bd, idesc_s, acc);
+        acc = 1;
+      }
+    }
+    umma_commit(&bars[1]);
+    mbar_wait(&bars[2], 0);
+    tc_fence_after();
+    acc = 0;
+    for (int k16 = 0; k16 < g.KP / 16; ++k16) {
+      const uint64_t ad = make_desc_sw128(smem_u32(Ps) + (uint32_t)(k16 >> 2) * 128u * 128u + (uint32_t)(k16 & 3) * 32u, 16u, 1024u);
+      const uint64_t bd = make_desc_sw128(smem_u32(Vs) + (uint32_t)k16 * 2048u, (uint32_t)g.KR * 128u, 1024u);
+      umma_bf16(tmem_base, ad, bd, idesc_o, acc);
+      acc = 1;
+    }
+    umma_commit(&bars[3]);
+  } else if (warp < 4) {
+    // ======================================================================== softmax + epilogue (thread == query row)
+    const int i = i0 + tid;
+    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const float sc = p.scale * 1.4426950408889634f;  // softmax in base 2
+    const int jmax = p.causal ? i + (p.M - p.N) : p.M - 1;  // last key this query may see
+    mbar_wait(&bars[1], 0);
+    tc_fence_after();
+    float mx = -INFINITY;
+    for (int c0 = 0; c0 < g.KP; c0 += 16) {
+      float v[16];
+      tmem_ld16(trow + (uint32_t)c0, v);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int key = c0 + j;
+        float s = v[j] * sc;
+        if (key > jmax) s = -FLT_MAX;
+        if (key < p.M) mx = fmaxf(mx, s);
+      }
+    }
+    float sum = 0.f;
+    for (int c0 = 0; c0 < g.KP; c0 += 16) {
+      float v[16];
+      tmem_ld16(trow + (uint32_t)c0, v);
+      float e[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int key = c0 + j;
+        float s = v[j] * sc;
+        if (key > jmax) s = -FLT_MAX;
+        float pj = (key < p.M) ? exp2f(s - mx) : 0.0f;
+        pj = bf16_round(pj);
+        sum += pj;
+        e[j] = pj;
+      }
+      uint8_t* prow = Ps + (size_t)(c0 >> 6) * 128 * 128 + (size_t)tid * 128;
+      const int ch = (c0 & 63) >> 3;
+      *reinterpret_cast<uint4*>(prow + (((ch) ^ (tid & 7)) * 16)) =
+          make_uint4(pack2(e[0], e[1]), pack2(e[2], e[3]), pack2(e[4], e[5]), pack2(e[6], e[7]));
+      *reinterpret_cast<uint4*>(prow + (((ch + 1) ^ (tid & 7)) * 16)) =
+          make_uint4(pack2(e[8], e[9]), pack2(e[10], e[11]), pack2(e[12], e[13]), pack2(e[14], e[15]));
+    }
+    tc_fence_before();
+    fence_async_smem();
+    mbar_arrive(&bars[2]);
+    const float inv = 1.0f / sum;
+    mbar_wait(&bars[3], 0);
+    tc_fence_after();
+    // tcgen05.ld is warp-collective: every lane loads, only rows < N store
+    bf16* orow = (bf16*)p.out + ((size_t)r * p.N + (i < p.N ? i : 0)) * p.C + h * d;
+    for (int c0 = 0; c0 < d; c0 += 16) {
+      float v[16];
+      tmem_ld16(trow + (uint32_t)c0, v);
+      if (i < p.N) {
+        uint4 o0 = make_uint4(pack2(v[0] * inv, v[1] * inv), pack2(v[2] * inv, v[3] * inv), pack2(v[4] * inv, v[5] * inv),
+                              pack2(v[6] * inv, v[7] * inv));
+        uint4 o1 = make_uint4(pack2(v[8] * inv, v[9] * inv), pack2(v[10] * inv, v[11] * inv),
+                              pack2(v[12] * inv, v[13] * inv), pack2(v[14] * inv, v[15] * inv));
+        *reinterpret_cast<uint4*>(orow + c0) = o0;
+        *reinterpret_cast<uint4*>(orow + c0 + 8) = o1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols)
+                 : "memory");
+  }
+}
+
+}  // namespace
+
+bool attn_umma_supported(const AttnParams& p) {
+  const int d = p.d;
+  if (!(d == 16 || d == 32 || d == 64 || d == 128)) return false;
+  if (p.M < 1 || p.M > 256 || p.N < 1) return false;
+  if ((p.q_ld & 7) || (p.q_off & 7) || (p.C & 7)) return false;
+  if (!p.cross && ((p.kv_ld & 7) || (p.k_off & 7) || (p.v_off & 7))) return false;
+  if (p.cross && ((p.kvc_ld & 7) || (p.kvc_off & 7))) return false;
+  return true;
+}
+
+cudaError_t launch_attention_umma(const AttnParams& p, bool pdl, cudaStream_t stream) {
+  if (!attn_umma_supported(p)) return cudaErrorInvalidValue;
+  AttnGeom g;
+  memset(&g, 0, sizeof(g));
+  g.KP = (p.M + 15) / 16 * 16;
+  g.KR = g.KP;  // multiple of 16, hence of 8
+  g.DB = (p.d + 63) / 64;
+  g.cpr_shift = p.d == 16 ? 1 : (p.d == 32 ? 2 : (p.d == 64 ? 3 : 4));
+  int tc = 32;
+  while (tc < g.KP || tc < p.d) tc <<= 1;
+  g.tmem_cols = tc;
+  const uint32_t q_bytes = (uint32_t)g.DB * 128u * 128u;
+  const uint32_t k_bytes = (uint32_t)g.DB * (uint32_t)g.KR * 128u;
+  const uint32_t p_bytes = (uint32_t)((g.KP + 63) / 64) * 128u * 128u;
+  g.off_k = q_bytes;
+  const uint32_t qk = (q_bytes + k_bytes + 1023u) / 1024u * 1024u;
+  const uint32_t pq = (p_bytes + 1023u) / 1024u * 1024u;
+  g.off_p = 0;  // P aliases Q / K (both dead once S has been computed)
+  g.off_v = qk > pq ? qk : pq;
+  g.smem = g.off_v + (k_bytes + 1023u) / 1024u * 1024u + 64u;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(attn_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  if (g.smem + 1024 > 227 * 1024) return cudaErrorInvalidValue;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((p.N + 127) / 128, p.H, p.B2);
+  cfg.blockDim = dim3(kAtThreads);
+  cfg.dynamicSmemBytes = g.smem + 1024;  // slack for the 1024-byte alignment of the dynamic window
+  cfg.stream = stream;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, attn_umma_kernel, p, g);
+}
+
+}  // namespace jen1

@@ -11,15 +11,21 @@
 //     programmatic-dependent-launch wait, i.e. while the previous layer is still running.
 //   * B operand = the activation panel.  Producer warps read raw channels-last bf16 rows once, apply the
 //     GroupNorm-apply / FiLM / SiLU (or LayerNorm, or skip-scale) prologue in fp32 registers, re-zero the conv
-//     padding rows AFTER the activation (reference blocks.py:137-145 -> :44-51) and store bf16 into a
-//     "row panel": for each 8-channel chunk a column of 16-byte rows.  In that layout (SBO = 128 B, LBO = panel
-//     stride) a conv tap is nothing but a 16-byte-granular shift of the descriptor start address, so the k taps
-//     reuse one panel; strided down-convs keep one sub-panel per residue (row mod stride).
+//     padding rows AFTER the activation (reference blocks.py:137-145 -> :44-51) and store bf16 into a K-major,
+//     128-byte-swizzled "row panel" (one 128-byte row = 64 channels of one position).  A conv tap is a whole-row
+//     shift of the descriptor start address, so the k taps reuse one panel; strided down-convs keep one
+//     sub-panel per residue (row mod stride).
 //   * Batch rows are folded into the position axis with a per-row halo (q = b*Lq + m, Lq = Lm + halo), so the deep
 //     UNet levels (L = 1..24) still fill an MMA N tile, and their weight streaming is spread over the whole GPU
-//     by split-K: partial tiles go to an L2-resident workspace and the last-arriving CTA of a tile (atomic ticket)
-//     reduces them in fixed order and runs the epilogue (bias / GELU / residual / GroupNorm + LayerNorm partial
-//     statistics for the next consumer).
+//     by split-K ACROSS A THREAD-BLOCK CLUSTER: the splitk CTAs of one output tile form a cluster (1,1,splitk),
+//     park their fp32 partial tiles in their own shared memory, and after one cluster barrier every CTA reduces
+//     and finishes a column slice of the tile by reading all partials over distributed shared memory in fixed
+//     order (deterministic) -- no global workspace, no atomics, and the epilogue itself is spread over the cluster.
+//   * Everything that is pure index arithmetic (which input row / batch row / panel row a panel slot maps to, which
+//     output row a column maps to, tap geometry) and every weight-only operand (bias, GroupNorm gamma/beta) is
+//     tabulated in shared memory BEFORE griddepcontrol.wait, i.e. off the critical path of the layer chain; after
+//     the wait the producers only do table look-ups, 16-byte loads and FMAs.  Loads of panel unit k+1 are in flight
+//     while unit k is transformed.
 //
 // Warp roles (192 threads): warps 0-3 build panels, then run the epilogue (TMEM lane quarter = warp index);
 // warp 4 lane 0 streams weights; warp 5 allocates TMEM and its lane 0 issues tcgen05.mma.
@@ -37,14 +43,21 @@ constexpr int kThreads = 192;
 constexpr int kProducers = 128;
 constexpr int kABytes = 128 * 64 * 2;  // one weight blob
 constexpr int kMaxSlots = 16;          // distinct batch rows one N tile may touch
+constexpr int kMaxCluster = 16;
+constexpr int kSredBytes = kMaxSlots * 128 * 2 * 4;
+// fixed part of the "misc" shared-memory block (see the carve-up in the kernel)
+constexpr int kMiscBar = 256;
+constexpr int kMiscStat = 2 * kMaxSlots * 32 * 4;            // gmean, grstd
+constexpr int kMiscFine = kMaxSlots * 2 * 32 * 2 * 8;        // fp64 fine-group sums
+constexpr int kMiscFixed = kMiscBar + kMiscStat + kMiscFine + kMaxSlots * 4 + 32 * 8;  // + scrow + tap table
+
+int g_max_cluster = 8;
 
 struct UmmaArgs {
   ConvParams p;
   UmmaPlan pl;
   const bf16* w0;  // packed blobs of seg 0: [m_tile][phase][cin block][tap]
   const bf16* w1;  // packed blobs of seg 1: [m_tile][cin block]
-  float* ws;       // split-K partial tiles
-  int* counters;   // split-K tickets (zero between launches)
   int out_f32;
   long long* timeline;  // optional per-launch phase clocks of CTA (0,0,0) (JEN1_TIMELINE debugging), else nullptr
 };
@@ -101,6 +114,25 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void bar_sync_producers() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// address of the same shared-memory location in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t map_cluster(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ float ld_cluster_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   uint32_t r[16];
@@ -115,41 +147,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// K-major, no swizzle: core matrix = 8 rows x 16 B contiguous; SBO = stride between 8-row groups, LBO = stride
-// between the two 8-element K chunks of one K=16 instruction.  (cute::UMMA::SmemDescriptor, version 1.)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  return d;
-}
 // K-major, 128-byte swizzle: rows of 128 B (64 bf16), the 16-byte chunk c of row r lives at chunk c ^ (r & 7);
 // SBO = 1024 B between 8-row groups; K advances inside the swizzle atom by adding bytes to the start address.
-__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t base_offset = 0) {
+// (cute::UMMA::SmemDescriptor, version 1.)
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)1 << 16;
   d |= (uint64_t)(1024u >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)(base_offset & 7u) << 49;
   d |= (uint64_t)2 << 61;
   return d;
-}
-
-struct TapGeom {
-  int rho, off;
-};
-__device__ __forceinline__ TapGeom tap_geom(int shift0, int shift_step, int j, int f, int amin) {
-  const int d = shift0 + j * shift_step;
-  int rho = d % f;
-  if (rho < 0) rho += f;
-  const int a = (d - rho) / f;
-  TapGeom g;
-  g.rho = rho;
-  g.off = a - amin;
-  return g;
 }
 
 __device__ __forceinline__ float ldf_cg(const bf16* p) {
@@ -160,6 +168,11 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
 }
+// SiLU whose result is rounded to bf16 right away: the fast exp / divide (rel. error ~1e-6) are invisible
+__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+
+inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
 // ---------------------------------------------------------------------------------------------- the kernel
 __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_constant__ UmmaArgs A) {
@@ -174,18 +187,25 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
 
   // ---- work item
   const int nt = blockIdx.x, mt = blockIdx.y;
-  const int z = blockIdx.z / pl.splitk, sk = blockIdx.z % pl.splitk;
+  const int SK = pl.splitk;
+  const int z = (SK > 1) ? (int)blockIdx.z / SK : (int)blockIdx.z;
+  const int sk = (SK > 1) ? (int)cluster_ctarank() : 0;  // cluster = (1,1,SK): rank == blockIdx.z % SK
   const int NT = pl.NT, Lq = pl.Lq;
   const int q0 = nt * NT;
   const int nsteps = pl.steps0 + pl.steps1;
-  const int st0 = (int)(((long long)sk * nsteps) / pl.splitk);
-  const int st1 = (int)(((long long)(sk + 1) * nsteps) / pl.splitk);
+  const int st0 = (int)(((long long)sk * nsteps) / SK);
+  const int st1 = (int)(((long long)(sk + 1) * nsteps) / SK);
   const int my_steps = st1 - st0;
   const int ntaps0 = p.seg[0].ntaps;
+  const int f0 = p.seg[0].in_stride;
+  const int rows0 = f0 * pl.R;  // panel slots of a seg-0 K step: idx = rho * R + r
+  // this CTA's slice of the seg-0 input channels
+  const int ch_base = st0 * 64;
+  const int my_ch = (min(st1, pl.steps0) - st0) * 64;  // <= 0: no seg-0 step in this split
 
   // ---- shared memory carve-up
-  uint8_t* a_ring = smem;                                           // stages * 16 KB
-  uint8_t* panels = a_ring + (size_t)pl.stages * kABytes;          // 2 * panel_bytes
+  uint8_t* a_ring = smem;                                  // pl.ring_bytes (>= stages * 16 KB)
+  uint8_t* panels = a_ring + (size_t)pl.ring_bytes;       // 2 * panel_bytes
   const uint32_t panel_bytes = (uint32_t)pl.panel_bytes;
   uint8_t* misc = panels + 2 * (size_t)panel_bytes;
   uint64_t* a_full = reinterpret_cast<uint64_t*>(misc);            // [8]
@@ -194,14 +214,23 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
   uint64_t* p_empty = p_full + 2;                                   // [2]
   uint64_t* acc_full = p_empty + 2;                                 // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);  // [1]
-  int* ticket_slot = reinterpret_cast<int*>(tmem_slot + 1);         // [1]
-  float* gmean = reinterpret_cast<float*>(misc + 256);              // [kMaxSlots][32]
+  float* gmean = reinterpret_cast<float*>(misc + kMiscBar);         // [kMaxSlots][32]
   float* grstd = gmean + kMaxSlots * 32;                            // [kMaxSlots][32]
   double* fine = reinterpret_cast<double*>(grstd + kMaxSlots * 32); // [kMaxSlots][2 sources][32 fine groups][2]
-  int* scrow = reinterpret_cast<int*>(fine + kMaxSlots * 2 * 32 * 2);  // [kMaxSlots] conditioning-table row per batch row
+  int* scrow = reinterpret_cast<int*>(fine + kMaxSlots * 2 * 32 * 2);  // [kMaxSlots] conditioning-table row per slot
+  int2* tapg = reinterpret_cast<int2*>(scrow + kMaxSlots);          // [32] (panel row offset, unused) per tap
+  uint8_t* tabs = misc + kMiscFixed;
+  int2* rowmeta = reinterpret_cast<int2*>(tabs);                           // [rows0]: (input row | -1, b | panel row << 8)
+  int2* rowmeta1 = reinterpret_cast<int2*>(tabs + pl.off_rowmeta1);        // [NT] same for the seg-1 K steps
+  int2* colmeta = reinterpret_cast<int2*>(tabs + pl.off_colmeta);          // [NT]: (output row | -1, batch row)
+  float2* rowstat = reinterpret_cast<float2*>(tabs + pl.off_rowstat);      // [rows0] LayerNorm (mean, rstd) per slot
+  float2* gb = reinterpret_cast<float2*>(tabs + pl.off_gb);                // [ch_cap] (gamma, beta)
+  float2* coef = reinterpret_cast<float2*>(tabs + pl.off_coef);            // [slots][ch_cap] (a, s): y = a*x + s
+  const int ch_cap = pl.ch_cap;
   // epilogue scratch aliases the weight ring (all MMAs have completed by then)
-  float* sred = reinterpret_cast<float*>(a_ring);                   // [kMaxSlots][128][2]
-  float* rowred = sred + kMaxSlots * 128 * 2;                       // [4][NT][2]
+  float* sred = reinterpret_cast<float*>(a_ring);                          // [kMaxSlots][128][2]
+  float* rowred = sred + kMaxSlots * 128 * 2;                              // [4][cols_own][2]
+  float* part = reinterpret_cast<float*>(a_ring + kSredBytes + 4 * NT * 8);  // [NT][128] fp32 partial tile (SK > 1)
 
   if (tid == kProducers) {  // warp 4 lane 0
     for (int i = 0; i < pl.stages; ++i) {
@@ -232,78 +261,72 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
   if (warp == 4) {
     // ======================================================================== weight streamer
     if (lane == 0) {
-      int i = 0;
+      int s = 0, k = 0;
       for (int t = st0; t < st1; ++t) {
         const bool s1 = t >= pl.steps0;
         const int ntp = s1 ? 1 : ntaps0;
         const bf16* src = s1 ? A.w1 + ((size_t)mt * pl.steps1 + (t - pl.steps0)) * (kABytes / 2)
                              : A.w0 + (((size_t)(mt * p.nphase + z) * pl.steps0 + t) * ntaps0) * (kABytes / 2);
-        for (int j = 0; j < ntp; ++j, ++i) {
-          const int s = i % pl.stages, k = i / pl.stages;
+        for (int j = 0; j < ntp; ++j) {
           if (k > 0) mbar_wait(&a_empty[s], (uint32_t)((k - 1) & 1));
           mbar_expect_tx(&a_full[s], kABytes);
           bulk_g2s(a_ring + (size_t)s * kABytes, src + (size_t)j * (kABytes / 2), kABytes, &a_full[s]);
+          if (++s == pl.stages) {
+            s = 0;
+            ++k;
+          }
         }
       }
     }
+    __syncwarp();
   } else if (warp == 5) {
     // ======================================================================== MMA issuer
     if (lane == 0) {
+      // tap geometry: panel row offset of tap j (sub-panel of its residue + whole-row shift)
+      for (int j = 0; j < ntaps0; ++j) {
+        const int d = p.seg[0].shift0 + j * p.seg[0].shift_step;
+        int rho = d % f0;
+        if (rho < 0) rho += f0;
+        const int a = (d - rho) / f0;
+        tapg[j] = make_int2(rho * pl.PS + (a - pl.amin), 0);
+      }
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
-      const uint32_t lbo_b = (uint32_t)pl.PS * 16u;
-      int i = 0;
+      int s = 0, k = 0;
       uint32_t acc = 0;
       for (int t = st0; t < st1; ++t) {
         const int n = t - st0, pb = n & 1;
         const bool s1 = t >= pl.steps0;
-        const ConvSeg& S = p.seg[s1 ? 1 : 0];
         const int ntp = s1 ? 1 : ntaps0;
-        const int f = s1 ? 1 : S.in_stride;
-        const int amin = s1 ? 0 : pl.amin;
         mbar_wait(&p_full[pb], (uint32_t)((n >> 1) & 1));
         tc_fence_after();
         const uint32_t pbase = smem_u32(panels + (size_t)pb * panel_bytes);
-        for (int j = 0; j < ntp; ++j, ++i) {
-          const int s = i % pl.stages, k = i / pl.stages;
-          TapGeom g;
-          if (s1) {
-            g.rho = 0;
-            g.off = 0;
-          } else {
-            g = tap_geom(S.shift0, S.shift_step, j, f, amin);
-          }
+        for (int j = 0; j < ntp; ++j) {
+          const uint32_t prow = s1 ? 0u : (uint32_t)tapg[j].x;
           mbar_wait(&a_full[s], (uint32_t)(k & 1));
           tc_fence_after();
-          if (i == 0) TL_MARK(9);
+          if (t == st0 && j == 0) TL_MARK(9);
           const uint32_t abase = smem_u32(a_ring + (size_t)s * kABytes);
+          const uint32_t bbase = pbase + prow * 128u;
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
-            const uint64_t ad = make_desc_sw128(abase + (uint32_t)kk * 32u);
-            uint64_t bd;
-            if (pl.bsw == 0) {
-              bd = make_desc(pbase + ((uint32_t)(g.rho * 8 + kk * 2) * (uint32_t)pl.PS + (uint32_t)g.off) * 16u, lbo_b, 128u);
-            } else {  // swizzled panel: a tap is a whole-row (128 B) shift of the start address
-              const uint32_t sa = pbase + ((uint32_t)g.rho * (uint32_t)pl.PS + (uint32_t)g.off) * 128u + (uint32_t)kk * 32u;
-              bd = make_desc_sw128(sa, pl.bsw == 2 ? (sa >> 7) & 7u : 0u);
-            }
-            umma_bf16(tmem_base, ad, bd, idesc, acc);
+            umma_bf16(tmem_base, make_desc_sw128(abase + (uint32_t)kk * 32u), make_desc_sw128(bbase + (uint32_t)kk * 32u),
+                      idesc, acc);
             acc = 1;
           }
           umma_commit(&a_empty[s]);
+          if (++s == pl.stages) {
+            s = 0;
+            ++k;
+          }
         }
         umma_commit(&p_empty[pb]);
       }
       umma_commit(acc_full);
       TL_MARK(10);
-      if (tl) {
-        mbar_wait(acc_full, 0);
-        TL_MARK(13);
-      }
     }
+    __syncwarp();
   } else {
     // ======================================================================== panel producers, then epilogue
-    // Every load below is batched: addresses and validity are computed first, then all loads of a batch are issued
-    // back to back, then consumed -- a dependent L2/HBM round trip costs ~0.4-1 us and the layer chain is long.
     const ConvSeg& S0 = p.seg[0];
     const int Ct = S0.Cin;
     const int b_first = q0 / Lq;
@@ -314,76 +337,239 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
     const bool affine = p.mode == PRO_AFFINE;
     const bool has_gn = affine && p.G > 0;
     const bool has_film = affine && p.film != nullptr;
+    const bool need_coef = (has_gn || has_film) && my_ch > 0;
     const int cpg = has_gn ? Ct / p.G : 1;
     const int cl = tid;             // channel within the 128-wide M tile (== TMEM lane)
     const int nch = mt * 128 + cl;  // output channel
-    float gam[8], bet[8];
-    auto load_gamma_beta = [&](int t) {  // GroupNorm affine of this thread's 8 channels in K step t (weights)
-      const int c0 = t * 64 + kc * 8;
-      if (has_gn && t < pl.steps0 && c0 < Ct) {
-        const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + c0));
-        const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + c0 + 4));
-        const float4 e0 = __ldg(reinterpret_cast<const float4*>(p.beta + c0));
-        const float4 e1 = __ldg(reinterpret_cast<const float4*>(p.beta + c0 + 4));
-        gam[0] = g0.x; gam[1] = g0.y; gam[2] = g0.z; gam[3] = g0.w; gam[4] = g1.x; gam[5] = g1.y; gam[6] = g1.z; gam[7] = g1.w;
-        bet[0] = e0.x; bet[1] = e0.y; bet[2] = e0.z; bet[3] = e0.w; bet[4] = e1.x; bet[5] = e1.y; bet[6] = e1.z; bet[7] = e1.w;
+    const int zoff = p.out_off0 + z * p.out_off_phase;
+
+    // ---- tables that do not depend on earlier kernels (built while the previous layer is still running)
+    const float bias = p.bias ? __ldg(p.bias + nch) : 0.0f;
+    for (int idx = tid; idx < rows0; idx += kProducers) {
+      const int rho = (f0 == 1) ? 0 : idx / pl.R;
+      const int r = idx - rho * pl.R;
+      const int q = q0 + r;
+      const int b = q / Lq;
+      const int ml = q - b * Lq;
+      const int irow = (ml + pl.amin) * f0 + rho;
+      const bool ok = b < p.B && irow >= 0 && irow < S0.L;
+      rowmeta[idx] = make_int2(ok ? irow : -1, (b & 255) | ((rho * pl.PS + r) << 8));
+    }
+    if (p.nseg > 1) {
+      for (int r = tid; r < NT; r += kProducers) {
+        const int q = q0 + r;
+        const int b = q / Lq;
+        const int ml = q - b * Lq;
+        const bool ok = b < p.B && ml < p.seg[1].L;
+        rowmeta1[r] = make_int2(ok ? ml : -1, (b & 255) | (r << 8));
+      }
+    }
+    for (int c = tid; c < NT; c += kProducers) {
+      const int q = q0 + c;
+      const int eb = q / Lq;
+      const int eml = q - eb * Lq;
+      const int o = eml * p.out_stride + zoff;
+      const bool valid = (eb < p.B) && (eml < p.Lm) && (o >= 0) && (o < p.Lout);
+      colmeta[c] = make_int2(valid ? o : -1, eb);
+    }
+    if (has_gn) {
+      for (int c = tid; c < my_ch; c += kProducers) {
+        const int ch = ch_base + c;
+        gb[c] = ch < Ct ? make_float2(__ldg(p.gamma + ch), __ldg(p.beta + ch)) : make_float2(0.f, 0.f);
+      }
+    }
+    bar_sync_producers();
+
+    // ---- panel unit helpers.  A unit = up to 128 panel slots (rows) of one K step; a thread owns the 16-byte
+    //      channel chunk `kc` of slots rr + 16u.
+    auto step_rows = [&](int n) { return (st0 + n >= pl.steps0) ? NT : rows0; };
+    auto issue = [&](int n, int ib, uint4 (&raw)[8], uint32_t& okm) {
+      const int t = st0 + n;
+      const bool s1 = t >= pl.steps0;
+      const ConvSeg& S = p.seg[s1 ? 1 : 0];
+      const int c0 = (s1 ? t - pl.steps0 : t) * 64 + kc * 8;
+      const bool second = c0 >= S.s[0].C;
+      const ConvSrc& sr = second ? S.s[1] : S.s[0];
+      const int cc = second ? c0 - S.s[0].C : c0;
+      const bool chan_ok = cc < sr.C;
+      const int2* meta = s1 ? rowmeta1 : rowmeta;
+      const int rows = s1 ? NT : rows0;
+      okm = 0;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int idx = ib * 128 + rr + 16 * u;
+        raw[u] = make_uint4(0u, 0u, 0u, 0u);
+        if (idx < rows && chan_ok) {
+          const int2 m = meta[idx];
+          if (m.x >= 0) {
+            int b = m.y & 255;
+            if (b >= sr.bmod) b -= sr.bmod;
+            raw[u] = __ldcg(reinterpret_cast<const uint4*>((const bf16*)sr.ptr + ((size_t)b * S.L + m.x) * sr.C + cc));
+            okm |= 1u << u;
+          }
+        }
       }
     };
-    // constants that do not depend on earlier kernels are fetched before the PDL wait
-    const float bias = p.bias ? __ldg(p.bias + nch) : 0.0f;
-    load_gamma_beta(st0);
+    auto consume = [&](int n, int ib, const uint4 (&raw)[8], uint32_t okm) {
+      const int t = st0 + n, pb = n & 1;
+      const bool s1 = t >= pl.steps0;
+      const ConvSeg& S = p.seg[s1 ? 1 : 0];
+      const int c0 = (s1 ? t - pl.steps0 : t) * 64 + kc * 8;
+      const bool second = c0 >= S.s[0].C;
+      const float sscale = (second ? S.s[1] : S.s[0]).scale;
+      const int2* meta = s1 ? rowmeta1 : rowmeta;
+      const int rows = s1 ? NT : rows0;
+      if (ib == 0 && n >= 2) mbar_wait(&p_empty[pb], (uint32_t)(((n >> 1) - 1) & 1));
+      uint8_t* pan = panels + (size_t)pb * panel_bytes;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int idx = ib * 128 + rr + 16 * u;
+        if (idx >= rows) break;
+        const int2 m = meta[idx];
+        const int prow = m.y >> 8;
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+        if ((okm >> u) & 1u) {
+          float v[8];
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[u]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            v[2 * e] = __low2float(h[e]);
+            v[2 * e + 1] = __high2float(h[e]);
+          }
+          if (s1) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] *= sscale;
+          } else if (affine) {
+            if (need_coef) {
+              const float4* cf = reinterpret_cast<const float4*>(coef + (size_t)((m.y & 255) - b_first) * ch_cap + (c0 - ch_base));
+              const float4 k0 = cf[0], k1 = cf[1], k2 = cf[2], k3 = cf[3];
+              v[0] = fmaf(k0.x, v[0], k0.y); v[1] = fmaf(k0.z, v[1], k0.w);
+              v[2] = fmaf(k1.x, v[2], k1.y); v[3] = fmaf(k1.z, v[3], k1.w);
+              v[4] = fmaf(k2.x, v[4], k2.y); v[5] = fmaf(k2.z, v[5], k2.w);
+              v[6] = fmaf(k3.x, v[6], k3.y); v[7] = fmaf(k3.z, v[7], k3.w);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] *= sscale;
+            }
+            if (p.act == ACT_SILU) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = silu_fast(v[e]);
+            }
+          } else {
+            const float2 ms = rowstat[idx];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = (v[e] - ms.x) * ms.y;
+          }
+          o.x = pack2(v[0], v[1]);
+          o.y = pack2(v[2], v[3]);
+          o.z = pack2(v[4], v[5]);
+          o.w = pack2(v[6], v[7]);
+        }
+        *reinterpret_cast<uint4*>(pan + (size_t)prow * 128 + (size_t)((kc ^ (prow & 7)) * 16)) = o;
+      }
+      if ((ib + 1) * 128 >= rows) {  // last unit of this K step
+        fence_async_smem();           // generic-proxy stores -> visible to the tensor core (async proxy)
+        mbar_arrive(&p_full[pb]);
+      }
+    };
+    auto advance = [&](int& n, int& ib) {
+      if ((ib + 1) * 128 >= step_rows(n)) {
+        ib = 0;
+        ++n;
+      } else {
+        ++ib;
+      }
+    };
 
     pdl_wait();  // everything below reads what the previous kernels wrote
     if (tid == 0) { TL_MARK(2); TL_GLOBAL(11); }
 
+    // ---- first loads: conditioning row, first panel unit (in flight during the statistics reduction)
     if (tid < nbl) scrow[tid] = p.cond_row ? __ldcg(p.cond_row + b_first + tid) : 0;
+    uint4 rA[8], rB[8];
+    uint32_t mA = 0, mB = 0;
+    issue(0, 0, rA, mA);
+
+    if (!affine) {
+      // LayerNorm statistics of every panel row from the producer's per-tile partials (once per CTA)
+      const ConvSrc& sr = S0.s[0];
+      const float inv = 1.0f / (float)sr.C;
+      for (int idx = tid; idx < rows0; idx += kProducers) {
+        const int2 m = rowmeta[idx];
+        float2 ms = make_float2(0.f, 1.f);
+        if (m.x >= 0) {
+          int b = m.y & 255;
+          if (b >= sr.bmod) b -= sr.bmod;
+          const float2* rp = reinterpret_cast<const float2*>(p.rowpart) + ((size_t)b * S0.L + m.x) * p.rp_nct;
+          float a = 0.f, qq = 0.f;
+          for (int j0 = 0; j0 < p.rp_nct; j0 += 8) {
+            float2 v2[8];
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) v2[jj] = (j0 + jj < p.rp_nct) ? __ldcg(rp + j0 + jj) : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+              a += v2[jj].x;
+              qq += v2[jj].y;
+            }
+          }
+          const float m1 = a * inv;
+          float var = qq * inv - m1 * m1;
+          if (var < 0.0f) var = 0.0f;
+          ms = make_float2(m1, 1.0f / sqrtf(var + p.ln_eps));
+        }
+        rowstat[idx] = ms;
+      }
+    }
+
     // ---- GroupNorm statistics of the input for the batch rows this tile touches.  Deterministic two-level reduce:
-    //      128 threads = 64 (source, fine group) items x 2 interleaved halves of the producer's per-tile partials,
-    //      combined by one shuffle; then one thread per group folds its fine groups.
+    //      fine-group sums of every (batch row, source, fine group) item from the producer's partial entries (an item
+    //      is split over `parts` lanes combined by shuffles in a fixed order), then one thread per group.
     if (has_gn) {
-      // pass 1: fine-group sums of every (batch row, source, fine group) item; an item is split over `parts`
-      // lanes (interleaved entries) that are combined with shuffles in a fixed order
       const int nitem = nbl * 64;
       int parts = 1;
       while (parts < 8 && nitem * parts * 2 <= kProducers) parts *= 2;
       for (int base = 0; base < nitem * parts; base += kProducers) {
         const int idx = base + tid;
-        const int item = idx / parts, part = idx - item * parts;
+        const int item = idx / parts, part_i = idx - item * parts;
         const int bl = item >> 6, fs = (item >> 5) & 1, ffg = item & 31;
         double a = 0.0, q = 0.0;
         if (item < nitem) {
           const ConvSrc& fsr = S0.s[fs];
           if (fsr.C > 0 && ffg < fsr.FG) {
-            const int b = b_first + bl;
-            const float2* st = reinterpret_cast<const float2*>(fsr.stats) + (size_t)(b % fsr.bmod) * fsr.n_ent * fsr.FG + ffg;
-            for (int e0 = part; e0 < fsr.n_ent; e0 += parts * 16) {  // 16 independent L2 loads in flight
+            int b = b_first + bl;
+            if (b >= fsr.bmod) b -= fsr.bmod;
+            const float2* st = reinterpret_cast<const float2*>(fsr.stats) + (size_t)b * fsr.n_ent * fsr.FG + ffg;
+            for (int e0 = part_i; e0 < fsr.n_ent; e0 += parts * 16) {  // 16 independent L2 loads in flight
               float2 buf[16];
 #pragma unroll
               for (int u = 0; u < 16; ++u) {
                 const int e = e0 + u * parts;
                 buf[u] = e < fsr.n_ent ? __ldcg(st + (size_t)e * fsr.FG) : make_float2(0.f, 0.f);
               }
+              double a0 = 0.0, a1 = 0.0, q0s = 0.0, q1s = 0.0;
 #pragma unroll
-              for (int u = 0; u < 16; ++u) {
-                a += (double)buf[u].x;
-                q += (double)buf[u].y;
+              for (int u = 0; u < 16; u += 2) {
+                a0 += (double)buf[u].x;
+                q0s += (double)buf[u].y;
+                a1 += (double)buf[u + 1].x;
+                q1s += (double)buf[u + 1].y;
               }
+              a += a0 + a1;
+              q += q0s + q1s;
             }
           }
         }
-        if (tid == 0 && base == 0) TL_MARK(14);
         for (int o = 1; o < parts; o <<= 1) {
           a += __shfl_xor_sync(0xffffffffu, a, o);
           q += __shfl_xor_sync(0xffffffffu, q, o);
         }
-        if (item < nitem && part == 0) {
+        if (item < nitem && part_i == 0) {
           const double sc = (double)S0.s[fs].scale;
           fine[item * 2] = a * sc;
           fine[item * 2 + 1] = q * sc * sc;
         }
       }
       bar_sync_producers();
-      if (tid == 0) TL_MARK(15);
       // pass 2: one thread per (batch row, group)
       for (int idx = tid; idx < nbl * p.G; idx += kProducers) {
         const int bl = idx / p.G, g = idx - bl * p.G;
@@ -411,266 +597,179 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
         gmean[bl * 32 + g] = (float)mean;
         grstd[bl * 32 + g] = rsqrtf((float)var + p.eps);
       }
-      bar_sync_producers();
-    } else if (has_film) {
-      bar_sync_producers();  // scrow
     }
-
+    bar_sync_producers();  // scrow, gmean / grstd, rowstat
     if (tid == 0) TL_MARK(3);
-    // ---- panels
-    float ca[8], cs[8];
-    int coef_b = -1;
-    for (int t = st0; t < st1; ++t) {
-      const int n = t - st0, pb = n & 1;
-      const bool s1 = t >= pl.steps0;
-      const ConvSeg& S = p.seg[s1 ? 1 : 0];
-      const int f = s1 ? 1 : S.in_stride;
-      const int amin = s1 ? 0 : pl.amin;
-      const int R = s1 ? NT : pl.R;
-      const int cb = s1 ? t - pl.steps0 : t;
-      const int c0 = cb * 64 + kc * 8;  // channel in the concatenated input
-      const bool second = c0 >= S.s[0].C;
-      const ConvSrc& sr = second ? S.s[1] : S.s[0];
-      const int cc = second ? c0 - S.s[0].C : c0;
-      const bool chan_ok = cc < sr.C;
-      if (n > 0) load_gamma_beta(t);
-      coef_b = -1;
-      // affine coefficients of (batch row b, this thread's 8 channels): a = gamma*rstd*scale*(film_s+1), ...
-      // split in two so the FiLM loads fly together with the first batch of activation loads
-      float fsv[8], fhv[8];
-      auto film_issue = [&](int b) {
-        if (has_film) {
-          const float* fp = p.film + (size_t)scrow[b - b_first] * p.film_stride + c0;
-          const float4 a0 = __ldcg(reinterpret_cast<const float4*>(fp)), a1 = __ldcg(reinterpret_cast<const float4*>(fp + 4));
-          const float4 h0 = __ldcg(reinterpret_cast<const float4*>(fp + Ct)), h1 = __ldcg(reinterpret_cast<const float4*>(fp + Ct + 4));
-          fsv[0] = a0.x; fsv[1] = a0.y; fsv[2] = a0.z; fsv[3] = a0.w; fsv[4] = a1.x; fsv[5] = a1.y; fsv[6] = a1.z; fsv[7] = a1.w;
-          fhv[0] = h0.x; fhv[1] = h0.y; fhv[2] = h0.z; fhv[3] = h0.w; fhv[4] = h1.x; fhv[5] = h1.y; fhv[6] = h1.z; fhv[7] = h1.w;
-        }
-      };
-      auto coef_finish = [&](int b) {
-        const int bl = b - b_first;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          float a = sr.scale, sft = 0.0f;
-          if (has_gn) {
-            const int g = (c0 + e) / cpg;
-            const float ga = gam[e] * grstd[bl * 32 + g];
-            a = ga * sr.scale;
-            sft = bet[e] - gmean[bl * 32 + g] * ga;
-          }
-          if (has_film) {
-            const float fs1 = fsv[e] + 1.0f;
-            a = a * fs1;
-            sft = sft * fs1 + fhv[e];
-          }
-          ca[e] = a;
-          cs[e] = sft;
-        }
-        coef_b = b;
-      };
-      const bool need_coef = !s1 && affine && chan_ok && (has_gn || has_film);
-      if (need_coef) film_issue(b_first);  // common case: one batch row per tile
-      if (n >= 2) mbar_wait(&p_empty[pb], (uint32_t)(((n >> 1) - 1) & 1));
-      uint8_t* pan = panels + (size_t)pb * panel_bytes;
-      const int rows_all = f * R;  // (residue, row) pairs flattened: idx = rho * R + r
-      for (int i0 = rr; i0 < rows_all; i0 += 128) {
-        uint4 raw[8];
-        int bb[8];
-        bool ok[8];
-        float mu[8], rs[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int idx = i0 + 16 * u;
-          const int rho = idx / R, r = idx - rho * R;
-          const int q = q0 + r;
-          const int b = q / Lq;
-          const int ml = q - b * Lq;
-          const int irow = (ml + amin) * f + rho;
-          bb[u] = b;
-          ok[u] = (idx < rows_all) && chan_ok && b < p.B && irow >= 0 && irow < S.L;
-          raw[u] = make_uint4(0u, 0u, 0u, 0u);
-          mu[u] = 0.f;
-          rs[u] = 1.f;
-          if (ok[u]) {
-            const size_t rowi = (size_t)(b % sr.bmod) * S.L + irow;
-            raw[u] = __ldcg(reinterpret_cast<const uint4*>((const bf16*)sr.ptr + rowi * sr.C + cc));
-            if (!s1 && !affine) {  // LayerNorm statistics of the row from the producer's per-tile partials
-              const float2* rp = reinterpret_cast<const float2*>(p.rowpart) + rowi * p.rp_nct;
-              float a = 0.f, qq = 0.f;
-#pragma unroll 8
-              for (int jj = 0; jj < p.rp_nct; ++jj) {
-                const float2 v2 = __ldcg(rp + jj);
-                a += v2.x;
-                qq += v2.y;
-              }
-              const float inv = 1.0f / (float)sr.C;
-              const float m1 = a * inv;
-              float var = qq * inv - m1 * m1;
-              if (var < 0.0f) var = 0.0f;
-              mu[u] = m1;
-              rs[u] = 1.0f / sqrtf(var + p.ln_eps);
+
+    // ---- per-(batch row, channel) affine coefficients of this CTA's channel slice:
+    //      y = a*x + s,  a = scale*gamma*rstd*(1+film_scale),  s = (beta - mean*gamma*rstd)*(1+film_scale) + film_shift
+    if (need_coef) {
+      for (int bl = 0; bl < nbl; ++bl) {
+        const float* fp = has_film ? p.film + (size_t)scrow[bl] * p.film_stride : nullptr;
+        for (int c = tid; c < my_ch; c += kProducers) {
+          const int ch = ch_base + c;
+          float a = 0.f, sft = 0.f;
+          if (ch < Ct) {
+            float fs = 0.f, fh = 0.f;
+            if (has_film) {
+              fs = __ldcg(fp + ch);
+              fh = __ldcg(fp + Ct + ch);
+            }
+            const float scale = (ch >= S0.s[0].C ? S0.s[1] : S0.s[0]).scale;
+            a = scale;
+            if (has_gn) {
+              const int g = ch / cpg;
+              const float2 gbv = gb[c];
+              const float ga = gbv.x * grstd[bl * 32 + g];
+              a = ga * scale;
+              sft = gbv.y - gmean[bl * 32 + g] * ga;
+            }
+            if (has_film) {
+              const float fs1 = fs + 1.0f;
+              a *= fs1;
+              sft = sft * fs1 + fh;
             }
           }
-        }
-        if (need_coef && i0 == rr) coef_finish(b_first);
-        if (tl && tid == 0 && n == 0 && i0 == rr) {
-          if (raw[0].x == 0x12345678u) tl[31] = 1;  // consume the load
-          TL_MARK(16);
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int idx = i0 + 16 * u;
-          if (idx >= rows_all) break;
-          const int rho = idx / R, r = idx - rho * R;
-          uint4 o = make_uint4(0u, 0u, 0u, 0u);
-          if (ok[u]) {
-            float v[8];
-            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[u]);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              v[2 * e] = __low2float(h[e]);
-              v[2 * e + 1] = __high2float(h[e]);
-            }
-            if (s1) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] *= sr.scale;
-            } else if (affine) {
-              if (has_gn || has_film) {
-                if (coef_b != bb[u]) {
-                  film_issue(bb[u]);
-                  coef_finish(bb[u]);
-                }
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = fmaf(ca[e], v[e], cs[e]);
-              } else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] *= sr.scale;
-              }
-              if (p.act == ACT_SILU) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = silu_f(v[e]);
-              }
-            } else {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = (v[e] - mu[u]) * rs[u];
-            }
-            o.x = pack2(v[0], v[1]);
-            o.y = pack2(v[2], v[3]);
-            o.z = pack2(v[4], v[5]);
-            o.w = pack2(v[6], v[7]);
-          }
-          if (pl.bsw == 0) {
-            *reinterpret_cast<uint4*>(pan + ((size_t)(rho * 8 + kc) * pl.PS + r) * 16) = o;
-          } else {
-            *reinterpret_cast<uint4*>(pan + ((size_t)rho * pl.PS + r) * 128 + (size_t)((kc ^ (r & 7)) * 16)) = o;
-          }
+          coef[(size_t)bl * ch_cap + c] = make_float2(a, sft);
         }
       }
-      if (tid == 0 && n == 0) TL_MARK(17);
-      fence_async_smem();  // generic-proxy stores -> visible to the tensor core (async proxy)
-      mbar_arrive(&p_full[pb]);
-      if (tid == 0 && n == 0) TL_MARK(4);
+      bar_sync_producers();
+    }
+    if (tid == 0) TL_MARK(4);
+
+    // ---- panels: loads of unit k+1 are in flight while unit k is transformed
+    {
+      int n = 0, ib = 0;
+      while (true) {
+        int n1 = n, ib1 = ib;
+        advance(n1, ib1);
+        const bool more1 = n1 < my_steps;
+        if (more1) issue(n1, ib1, rB, mB);
+        consume(n, ib, rA, mA);
+        if (!more1) break;
+        int n2 = n1, ib2 = ib1;
+        advance(n2, ib2);
+        const bool more2 = n2 < my_steps;
+        if (more2) issue(n2, ib2, rA, mA);
+        consume(n1, ib1, rB, mB);
+        if (!more2) break;
+        n = n2;
+        ib = ib2;
+      }
     }
     if (tid == 0) TL_MARK(5);
+  }
 
-    // ---- epilogue.  Column metadata and residual values of a 16-column chunk are fetched as one batch; for the
-    //      first chunk that happens while the tensor core is still working.
-    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
-    const int tile_id = (z * pl.m_tiles + mt) * pl.n_tiles + nt;
-    const int zoff = p.out_off0 + z * p.out_off_phase;
-    const bool want_stats = p.stats_out != nullptr;
-    const bool want_rows = p.rowpart_out != nullptr;
-    int eb = q0 / Lq, eml = q0 - eb * Lq;  // running (batch row, padded position) of the next column
-    int oi[16];
-    float rv[16];
-    uint32_t vmask = 0, bmask = 0;
-    auto chunk_meta = [&]() {
-      vmask = 0;
-      bmask = 0;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int o = eml * p.out_stride + zoff;
-        const bool valid = (eb < p.B) && (eml < p.Lm) && (o >= 0) && (o < p.Lout);
-        oi[j] = valid ? (eb * p.Lout + o) * p.Cout + nch : 0;
-        int ro = valid ? ((eb % p.res_bmod) * p.Lout + o) * p.Cout + nch : 0;
-        if (valid) vmask |= 1u << j;
-        ++eml;
-        if (eml == Lq) {
-          bmask |= 1u << j;
-          eml = 0;
-          ++eb;
-        }
-        rv[j] = (p.res && valid) ? ldf_cg((const bf16*)p.res + ro) : 0.0f;
-      }
-    };
-    chunk_meta();
+  // ============================================================================================ epilogue
+  // Column slice of this CTA: the whole tile without split-K, else columns [cb, ce) of the tile.
+  const int cols_per = (SK > 1) ? (NT + SK - 1) / SK : NT;
+  const int cb = (SK > 1) ? min(NT, sk * cols_per) : 0;
+  const int ce = min(NT, cb + cols_per);
+  const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
 
-    mbar_wait(acc_full, 0);
-    tc_fence_after();
-    if (tid == 0) TL_MARK(6);
-    bool final_cta = true;
-    const float* wsbase = nullptr;
-    if (pl.splitk > 1) {
-      float* wp = A.ws + ((size_t)tile_id * pl.splitk + sk) * NT * 128;
+  if (SK > 1) {
+    if (warp < 4) {
+      mbar_wait(acc_full, 0);
+      tc_fence_after();
+      if (tid == 0) TL_MARK(6);
       for (int c0 = 0; c0 < NT; c0 += 16) {
         float v[16];
         tmem_ld16(trow + (uint32_t)c0, v);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) __stcg(wp + (size_t)(c0 + j) * 128 + cl, v[j]);
-      }
-      __threadfence();
-      bar_sync_producers();
-      if (tid == 0) {
-        const int tk = atomicAdd(A.counters + tile_id, 1);
-        *ticket_slot = tk;
-        if (tk == pl.splitk - 1) A.counters[tile_id] = 0;  // ready for the next launch
-      }
-      bar_sync_producers();
-      final_cta = (*ticket_slot == pl.splitk - 1);
-      if (tid == 0) TL_MARK(7);
-      if (final_cta) {
-        __threadfence();
-        wsbase = A.ws + (size_t)tile_id * pl.splitk * NT * 128;
+        for (int j = 0; j < 16; ++j) part[(size_t)(c0 + j) * 128 + tid] = v[j];
       }
     }
-    if (final_cta) {
-      int sb = q0 / Lq;  // batch row of the statistics run in progress
-      float colS = 0.f, colQ = 0.f;
-      for (int c0 = 0; c0 < NT; c0 += 16) {
-        if (c0 > 0) chunk_meta();
-        float v[16];
-        if (wsbase == nullptr) {
-          tmem_ld16(trow + (uint32_t)c0, v);
-        } else {
+    cluster_sync_all();  // every CTA's partial tile is visible cluster-wide
+    if (tid == 0) TL_MARK(7);
+  }
+
+  if (warp < 4) {
+    const int cl = tid;
+    const int nch = mt * 128 + cl;
+    const int b_first = q0 / Lq;
+    const float bias = p.bias ? __ldg(p.bias + nch) : 0.0f;
+    const bool want_stats = p.stats_out != nullptr;
+    const bool want_rows = p.rowpart_out != nullptr;
+    const int nb_out = min(p.B - 1, (q0 + NT - 1) / Lq) - b_first + 1;
+    if (SK == 1) {
+      mbar_wait(acc_full, 0);
+      tc_fence_after();
+      if (tid == 0) TL_MARK(6);
+    }
+    if (want_stats) {
+      for (int bl = 0; bl < nb_out && bl < kMaxSlots; ++bl) {
+        sred[((size_t)bl * 128 + cl) * 2] = 0.f;
+        sred[((size_t)bl * 128 + cl) * 2 + 1] = 0.f;
+      }
+    }
+    uint32_t part_remote[kMaxCluster];
+    if (SK > 1) {
+      const uint32_t mine = smem_u32(part);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = 0.f;
-          for (int s0 = 0; s0 < pl.splitk; s0 += 4) {  // 64 independent L2 loads in flight, summed in split order
-            float tv[4][16];
+      for (int s = 0; s < kMaxCluster; ++s) part_remote[s] = s < SK ? map_cluster(mine, (uint32_t)s) : 0u;
+    }
+    int sb = -1;  // batch row of the statistics run in progress
+    float colS = 0.f, colQ = 0.f;
+    auto flush_stats = [&]() {
+      if (want_stats && sb >= b_first && sb < p.B && sb - b_first < kMaxSlots) {
+        sred[((size_t)(sb - b_first) * 128 + cl) * 2] = colS;
+        sred[((size_t)(sb - b_first) * 128 + cl) * 2 + 1] = colQ;
+      }
+      colS = 0.f;
+      colQ = 0.f;
+    };
+    for (int c0 = cb; c0 < ce; c0 += 16) {
+      const int ncol = min(16, ce - c0);
+      // column metadata and residual values of the chunk as one batch of loads
+      int orow[16], ebv[16];
+      float rv[16];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const float* wp = wsbase + (size_t)(s0 + u) * NT * 128 + (size_t)c0 * 128 + cl;
-              const bool on = s0 + u < pl.splitk;
-#pragma unroll
-              for (int j = 0; j < 16; ++j) tv[u][j] = (on && ((vmask >> j) & 1u)) ? __ldcg(wp + (size_t)j * 128) : 0.0f;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-#pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] += tv[u][j];
-          }
+      for (int j = 0; j < 16; ++j) {
+        const int2 cm = j < ncol ? colmeta[c0 + j] : make_int2(-1, -1);
+        orow[j] = cm.x;
+        ebv[j] = cm.y;
+        rv[j] = 0.f;
+        if (p.res && cm.x >= 0) {
+          int rb = cm.y;
+          if (rb >= p.res_bmod) rb -= p.res_bmod;
+          rv[j] = ldf_cg((const bf16*)p.res + ((size_t)rb * p.Lout + cm.x) * p.Cout + nch);
         }
+      }
+      float v[16];
+      if (SK == 1) {
+        tmem_ld16(trow + (uint32_t)c0, v);
+      } else {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const bool valid = (vmask >> j) & 1u;
+          float acc = 0.f;
+          if (j < ncol) {
+            const uint32_t off = (uint32_t)(((c0 + j) * 128 + cl) * 4);
+            float tv[kMaxCluster];
+#pragma unroll
+            for (int s = 0; s < kMaxCluster; ++s) tv[s] = s < SK ? ld_cluster_f32(part_remote[s] + off) : 0.f;
+#pragma unroll
+            for (int s = 0; s < kMaxCluster; ++s) acc += tv[s];  // fixed order: deterministic
+          }
+          v[j] = acc;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (j < ncol) {
+          if (ebv[j] != sb) {
+            flush_stats();
+            sb = ebv[j];
+          }
           float x = 0.0f;
-          if (valid) {
+          if (orow[j] >= 0) {
             x = v[j] + bias;
             if (p.epi_act == ACT_GELU) x = gelu_f(x);
             x += rv[j];
+            const size_t oi = ((size_t)ebv[j] * p.Lout + orow[j]) * p.Cout + nch;
             if (A.out_f32) {
-              ((float*)p.out)[oi[j]] = x;
+              ((float*)p.out)[oi] = x;
             } else {
-              ((bf16*)p.out)[oi[j]] = __float2bfloat16_rn(x);
+              ((bf16*)p.out)[oi] = __float2bfloat16_rn(x);
             }
           }
           colS += x;
@@ -678,78 +777,67 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
           if (want_rows) {
             const float rs = warp_sum(x), rq = warp_sum(x * x);
             if (lane == 0) {
-              rowred[((size_t)warp * NT + c0 + j) * 2] = rs;
-              rowred[((size_t)warp * NT + c0 + j) * 2 + 1] = rq;
+              rowred[((size_t)warp * cols_per + (c0 + j - cb)) * 2] = rs;
+              rowred[((size_t)warp * cols_per + (c0 + j - cb)) * 2 + 1] = rq;
             }
-          }
-          // flush the per-batch-row column sums at a row boundary / at the end of the tile
-          const bool last_col = (c0 + j == NT - 1);
-          const bool bnd = (bmask >> j) & 1u;
-          if (bnd || last_col) {
-            if (want_stats && sb <= b_last && sb - b_first < kMaxSlots) {
-              sred[((size_t)(sb - b_first) * 128 + cl) * 2] = colS;
-              sred[((size_t)(sb - b_first) * 128 + cl) * 2 + 1] = colQ;
-            }
-            colS = 0.f;
-            colQ = 0.f;
-            if (bnd) ++sb;
           }
         }
       }
-      if (want_stats || want_rows) bar_sync_producers();
-      if (want_stats) {
-        // per (batch row, fine group) partial of this tile -> entry e = nt - t_first(b); the last tile of a batch
-        // row also zeroes the unused trailing entries so consumers can sum a fixed n_ent.
-        const int gs = p.Cout / p.FGo;
-        const int ngl = 128 / gs;
-        const int n_ent = pl.E_max * p.nphase;
-        const int nb_out = min(p.B - 1, (q0 + NT - 1) / Lq) - b_first + 1;
-        for (int idx = tid; idx < nb_out * ngl; idx += kProducers) {
-          const int bl = idx / ngl, gl = idx - bl * ngl;
-          const int bb = b_first + bl;
-          float a = 0.f, q = 0.f;
+    }
+    flush_stats();
+    if (want_stats || want_rows) bar_sync_producers();
+    if (want_stats) {
+      // per (batch row, fine group) partial of this CTA's columns -> entry (tile index within the batch row, split
+      // rank); the last tile of a batch row also zeroes the unused trailing entries so consumers sum a fixed n_ent.
+      const int gs = p.Cout / p.FGo;
+      const int ngl = 128 / gs;
+      const int n_ent = pl.E_max * p.nphase;  // E_max = tiles per batch row (max) * SK
+      for (int idx = tid; idx < nb_out * ngl; idx += kProducers) {
+        const int bl = idx / ngl, gl = idx - bl * ngl;
+        const int bb = b_first + bl;
+        float a = 0.f, q = 0.f;
+        if (bl < kMaxSlots) {
           for (int c = gl * gs; c < (gl + 1) * gs; ++c) {
             a += sred[((size_t)bl * 128 + c) * 2];
             q += sred[((size_t)bl * 128 + c) * 2 + 1];
           }
-          const int t_first = (bb * Lq) / NT;
-          int t_last = ((bb + 1) * Lq - 1) / NT;
-          if (t_last > pl.n_tiles - 1) t_last = pl.n_tiles - 1;
-          const int e = nt - t_first;
-          const int fg = (mt * 128) / gs + gl;
-          float* so = p.stats_out + (((size_t)bb * n_ent + e * p.nphase + z) * p.FGo + fg) * 2;
-          so[0] = a;
-          so[1] = q;
-          if (nt == t_last) {
-            for (int e2 = e + 1; e2 < pl.E_max; ++e2) {
-              float* s2 = p.stats_out + (((size_t)bb * n_ent + e2 * p.nphase + z) * p.FGo + fg) * 2;
-              s2[0] = 0.f;
-              s2[1] = 0.f;
-            }
+        }
+        const int t_first = (bb * Lq) / NT;
+        int t_last = ((bb + 1) * Lq - 1) / NT;
+        if (t_last > pl.n_tiles - 1) t_last = pl.n_tiles - 1;
+        const int e = (nt - t_first) * SK + sk;
+        const int fg = (mt * 128) / gs + gl;
+        float* so = p.stats_out + (((size_t)bb * n_ent + (size_t)e * p.nphase + z) * p.FGo + fg) * 2;
+        so[0] = a;
+        so[1] = q;
+        if (nt == t_last) {
+          for (int e2 = e + SK; e2 < pl.E_max; e2 += SK) {
+            float* s2 = p.stats_out + (((size_t)bb * n_ent + (size_t)e2 * p.nphase + z) * p.FGo + fg) * 2;
+            s2[0] = 0.f;
+            s2[1] = 0.f;
           }
         }
       }
-      if (want_rows) {
-        for (int col = tid; col < NT; col += kProducers) {
-          const int q = q0 + col;
-          const int bb = q / Lq, m2 = q - bb * Lq;
-          const int o = m2 * p.out_stride + zoff;
-          if (bb < p.B && m2 < p.Lm && o >= 0 && o < p.Lout) {
-            float a = 0.f, qq = 0.f;
-            for (int w = 0; w < 4; ++w) {
-              a += rowred[((size_t)w * NT + col) * 2];
-              qq += rowred[((size_t)w * NT + col) * 2 + 1];
-            }
-            float* ro = p.rowpart_out + (((size_t)bb * p.Lout + o) * pl.m_tiles + mt) * 2;
-            ro[0] = a;
-            ro[1] = qq;
+    }
+    if (want_rows) {
+      for (int col = cb + tid; col < ce; col += kProducers) {
+        const int2 cm = colmeta[col];
+        if (cm.x >= 0) {
+          float a = 0.f, qq = 0.f;
+          for (int w = 0; w < 4; ++w) {
+            a += rowred[((size_t)w * cols_per + (col - cb)) * 2];
+            qq += rowred[((size_t)w * cols_per + (col - cb)) * 2 + 1];
           }
+          float* ro = p.rowpart_out + (((size_t)cm.y * p.Lout + cm.x) * pl.m_tiles + mt) * 2;
+          ro[0] = a;
+          ro[1] = qq;
         }
       }
     }
   }
 
   if (tid == 0) { TL_MARK(8); TL_GLOBAL(12); }
+  if (SK > 1) cluster_sync_all();  // nobody leaves while its partial tile may still be read remotely
   tc_fence_before();
   __syncthreads();
   if (warp == 5) {
@@ -759,23 +847,22 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
   }
 }
 
-inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
-inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
-
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------- planning
-UmmaPlan conv_umma_plan(const ConvParams& p, bool want_stats, size_t ws_capacity_bytes, int num_sms) {
+UmmaPlan conv_umma_plan(const ConvParams& p, bool want_stats, int num_sms) {
   UmmaPlan pl;
   memset(&pl, 0, sizeof(pl));
   const ConvSeg& S0 = p.seg[0];
   if (p.out == nullptr && p.out_ncl != nullptr) return pl;  // [B][C][L] output is a boundary format: generic path
-  if (p.Cout % 128 != 0 || p.B < 1) return pl;
+  if (p.Cout % 128 != 0 || p.B < 1 || p.B > 256) return pl;
   for (int sg = 0; sg < p.nseg; ++sg)
     for (int k = 0; k < 2; ++k) {
       const ConvSrc& sr = p.seg[sg].s[k];
       if (sr.C > 0 && (sr.C % 8 != 0)) return pl;
+      if (sr.C > 0 && (sr.bmod < 1 || p.B > 2 * sr.bmod)) return pl;  // `b % bmod` is one conditional subtract
     }
+  if (p.res && (p.res_bmod < 1 || p.B > 2 * p.res_bmod)) return pl;
   if (S0.s[0].C <= 0) return pl;
   if (p.G > 32) return pl;
   if (want_stats && (p.FGo <= 0 || p.Cout % p.FGo != 0 || 128 % (p.Cout / p.FGo) != 0)) return pl;
@@ -809,56 +896,74 @@ UmmaPlan conv_umma_plan(const ConvParams& p, bool want_stats, size_t ws_capacity
   if (NT > 128 && NT < 256) NT = round_up(NT, 32);
   if ((long long)NT > round_up((int)nq, 16)) NT = round_up((int)nq, 16);
   if (NT < 16) NT = 16;
-  // distinct batch rows per tile must fit the epilogue scratch
+  // distinct batch rows per tile must fit the per-slot tables
   auto slots = [&](int nt) {
     const int s = (nt + pl.halo + pl.Lq - 1) / pl.Lq + 1;
     return s < p.B ? s : p.B;
   };
   while (NT > 16 && slots(NT) > kMaxSlots) NT -= 16;
   if (slots(NT) > kMaxSlots) return pl;
-  pl.NT = NT;
-  pl.n_tiles = (int)((nq + NT - 1) / NT);
-  pl.R = NT + pl.halo;
-  static int bsw_env = -1;
-  if (bsw_env < 0) {
-    const char* e = getenv("JEN1_BSW");
-    bsw_env = e ? atoi(e) : 1;
-  }
-  pl.bsw = bsw_env;
-  if (pl.bsw == 0) {
-    pl.PS = pl.R | 1;  // odd panel stride (in 16-byte units): conflict-free producer stores
-    pl.panel_bytes = round_up(f * 8 * pl.PS * 16, 1024);
-  } else {
+  const int nsteps = pl.steps0 + pl.steps1;
+  const bool need_coef = p.mode == PRO_AFFINE && (p.G > 0 || p.film != nullptr);
+  for (;; NT -= 16) {
+    pl.NT = NT;
+    pl.n_tiles = (int)((nq + NT - 1) / NT);
+    pl.R = NT + pl.halo;
+    pl.bsw = 1;
     pl.PS = round_up(pl.R, 8);  // rows per sub-panel (128-byte rows, 128-byte swizzle, 1024-byte aligned)
     pl.panel_bytes = f * pl.PS * 128;
+    if (pl.panel_bytes < NT * 128) pl.panel_bytes = round_up(NT * 128, 1024);
+    int tc = 32;
+    while (tc < NT) tc <<= 1;
+    pl.tmem_cols = tc;
+    // split-K over a cluster: spread weight streaming over the GPU when the output tiles alone do not fill it
+    const long long tiles = (long long)pl.n_tiles * pl.m_tiles * p.nphase;
+    if (tiles > 65535) return pl;
+    int sk = (int)(num_sms / tiles);
+    if (sk < 1) sk = 1;
+    if (sk > nsteps) sk = nsteps;
+    if (sk > g_max_cluster) sk = g_max_cluster;
+    // the per-slot coefficient table of a CTA's channel slice must stay small: split K further if needed
+    const int nslot = slots(NT);
+    auto ch_cap_of = [&](int s) {
+      int ms = (nsteps + s - 1) / s;
+      if (ms > pl.steps0) ms = pl.steps0;
+      return ms * 64;
+    };
+    const int coef_budget = 24 * 1024;
+    while (need_coef && nslot * ch_cap_of(sk) * 8 > coef_budget && sk < nsteps && sk < g_max_cluster) ++sk;
+    const bool coef_ok = !need_coef || nslot * ch_cap_of(sk) * 8 <= coef_budget;
+    pl.splitk = sk;
+    pl.ch_cap = ch_cap_of(sk);
+    pl.E_max = ((pl.Lq - 1) / NT + 2) * sk;
+    // tables
+    const int rows0 = f * pl.R;
+    int off = round_up(rows0 * 8, 16);
+    pl.off_rowmeta1 = off;
+    off += p.nseg > 1 ? NT * 8 : 0;
+    pl.off_colmeta = off;
+    off += NT * 8;
+    pl.off_rowstat = off;
+    off += p.mode == PRO_ROWNORM ? round_up(rows0 * 8, 16) : 0;
+    pl.off_gb = off;
+    off += (p.mode == PRO_AFFINE && p.G > 0) ? pl.ch_cap * 8 : 0;
+    pl.off_coef = off;
+    off += need_coef ? nslot * pl.ch_cap * 8 : 0;
+    const int misc = kMiscFixed + off;
+    // shared memory: two panels + as many 16 KB weight stages as fit in ~half an SM (two CTAs co-reside under PDL);
+    // the epilogue scratch (+ the fp32 partial tile of the cluster reduction) aliases the ring
+    const int budget = 110 * 1024;
+    int stages = (budget - 2 * pl.panel_bytes - misc) / kABytes;
+    const int scratch = kSredBytes + 4 * NT * 8 + (sk > 1 ? NT * 512 : 0);
+    if (stages < 2) stages = 2;
+    if (stages > 6) stages = 6;
+    pl.stages = stages;
+    pl.ring_bytes = stages * kABytes;
+    if (pl.ring_bytes < scratch) pl.ring_bytes = round_up(scratch, 1024);
+    pl.smem = (size_t)pl.ring_bytes + 2 * (size_t)pl.panel_bytes + misc + 1024;
+    if (coef_ok && pl.smem <= (size_t)(sk > 1 ? 113 : 227) * 1024) break;
+    if (NT <= 16) return pl;
   }
-  int tc = 32;
-  while (tc < NT) tc <<= 1;
-  pl.tmem_cols = tc;
-  pl.E_max = (pl.Lq - 1) / NT + 2;
-  // split-K: spread weight streaming over the GPU when the output tiles alone do not fill it
-  const int nsteps = pl.steps0 + pl.steps1;
-  const long long tiles = (long long)pl.n_tiles * pl.m_tiles * p.nphase;
-  int sk = (int)(num_sms / tiles);
-  if (sk < 1) sk = 1;
-  if (sk > nsteps) sk = nsteps;
-  if (sk > 32) sk = 32;
-  while (sk > 1 && (size_t)tiles * sk * NT * 128 * sizeof(float) > ws_capacity_bytes) --sk;
-  if (tiles > 65536) return pl;
-  pl.splitk = sk;
-  pl.ws_bytes = sk > 1 ? (size_t)tiles * sk * NT * 128 * sizeof(float) : 0;
-  // shared memory: two panels + as many 16 KB weight stages as fit in ~half an SM (two CTAs co-reside under PDL)
-  const int misc = 256 + 2 * kMaxSlots * 32 * 4 + kMaxSlots * 2 * 32 * 2 * 8 + kMaxSlots * 4;
-  const int budget = 110 * 1024;
-  int stages = (budget - 2 * pl.panel_bytes - misc) / kABytes;
-  const int scratch = (kMaxSlots * 128 * 2 + 4 * NT * 2) * 4;  // epilogue scratch aliases the ring
-  const int min_stages = (scratch + kABytes - 1) / kABytes;
-  if (stages < 2) stages = 2;
-  if (stages < min_stages) stages = min_stages;
-  if (stages > 6) stages = 6;
-  pl.stages = stages;
-  pl.smem = (size_t)stages * kABytes + 2 * (size_t)pl.panel_bytes + misc + 1024;
-  if (pl.smem > 227 * 1024) return pl;
   pl.ok = 1;
   return pl;
 }
@@ -893,18 +998,42 @@ void conv_umma_pack(const float* w, int Cin, int Cout, int nphase, int taps_per_
 }
 
 cudaError_t conv_umma_init() {
-  return cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return e;
+  // clusters of 16 CTAs (non-portable size) if the device schedules them, else 8
+  g_max_cluster = 8;
+  const char* env = getenv("JEN1_MAX_CLUSTER");
+  const int want = env ? atoi(env) : kMaxCluster;
+  if (want >= 16 && cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(1, 8, 16);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = 113 * 1024;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 16;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int nclusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&nclusters, conv_umma_kernel, &cfg) == cudaSuccess && nclusters >= 4) g_max_cluster = 16;
+  } else if (want >= 1 && want < 8) {
+    g_max_cluster = want;
+  }
+  (void)cudaGetLastError();
+  return cudaSuccess;
 }
+int conv_umma_max_cluster() { return g_max_cluster; }
 
-cudaError_t launch_conv_umma(const ConvParams& p, const UmmaPlan& pl, const void* w0, const void* w1, float* ws,
-                             int* counters, bool out_f32, bool pdl, cudaStream_t stream, long long* timeline) {
+cudaError_t launch_conv_umma(const ConvParams& p, const UmmaPlan& pl, const void* w0, const void* w1, bool out_f32,
+                             bool pdl, cudaStream_t stream, long long* timeline) {
   UmmaArgs a;
   a.p = p;
   a.pl = pl;
   a.w0 = (const bf16*)w0;
   a.w1 = (const bf16*)w1;
-  a.ws = ws;
-  a.counters = counters;
   a.out_f32 = out_f32 ? 1 : 0;
   a.timeline = timeline;
   cudaLaunchConfig_t cfg;
@@ -913,11 +1042,22 @@ cudaError_t launch_conv_umma(const ConvParams& p, const UmmaPlan& pl, const void
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = pl.smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (pl.splitk > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 1;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = (unsigned)pl.splitk;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
+  cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, conv_umma_kernel, a);
 }
 

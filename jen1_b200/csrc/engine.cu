@@ -37,7 +37,7 @@ Engine::~Engine() {
   if (smp_.exec) cudaGraphExecDestroy(smp_.exec);
   for (void* p : wallocs_) cudaFree(p);
   void* bufs[] = {kv_cond_, ctx_mask_, ctx_rowpart_, tt_t_, tt_tfm_, tt_tft_, tt_m1_, tt_m2_, tt_map_, tt_film_,
-                  tt_tok_, tt_tokrp_, tt_kv_, d_ctl_, arena_, smp_.coef, umma_ws_, umma_counters_};
+                  tt_tok_, tt_tokrp_, tt_kv_, d_ctl_, arena_, smp_.coef};
   for (void* p : bufs)
     if (p) cudaFree(p);
 }
@@ -291,17 +291,14 @@ int Engine::finalize() {
     const char* pdl = getenv("JEN1_PDL");
     use_umma_ = dtype_ == JEN1_DTYPE_BF16 && !(impl && strcmp(impl, "generic") == 0);
     use_pdl_ = !(pdl && strcmp(pdl, "0") == 0);
+    const char* at = getenv("JEN1_ATTN_IMPL");  // "fma" forces the fp32-FMA attention core (A/B testing)
+    use_umma_attn_ = !(at && strcmp(at, "fma") == 0);
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device_) == cudaSuccess) {
       num_sms_ = prop.multiProcessorCount;
       if (prop.major != 10) use_umma_ = false;  // tcgen05 needs sm_100
     }
-    if (use_umma_) {
-      umma_ws_cap_ = (size_t)64 << 20;
-      if (cudaMalloc((void**)&umma_ws_, umma_ws_cap_) != cudaSuccess || cudaMalloc((void**)&umma_counters_, 65536 * 4) != cudaSuccess ||
-          cudaMemset(umma_counters_, 0, 65536 * 4) != cudaSuccess || conv_umma_init() != cudaSuccess)
-        return fail("tcgen05 path initialisation failed");
-    }
+    if (use_umma_ && conv_umma_init() != cudaSuccess) return fail("tcgen05 path initialisation failed");
   }
   try {
     const int nl = d_.num_layers;
@@ -643,7 +640,7 @@ Act Engine::conv_build(const DConv& W, int Bout, const Act& a0, const Act* a1, f
   if (use_umma_ && !a0.f32 && W.wu && (!W2 || W2->wu) && W.u_nphase == o.nphase && W.u_tpp == o.ntaps &&
       (o.nphase == 1 ? (o.wtap0 == 0 && o.wtap_step == 1) : (o.wtap0 == 0 && o.wtap_phase == W.u_wtap_phase && o.wtap_step == W.u_wtap_step))) {
     p.out = (void*)1;  // planning only looks at which of out / out_ncl is set
-    plan = conv_umma_plan(p, o.want_stats, umma_ws_cap_, num_sms_);
+    plan = conv_umma_plan(p, o.want_stats, num_sms_);
     p.out = nullptr;
   }
   if (into) {
@@ -678,7 +675,7 @@ Act Engine::conv_build(const DConv& W, int Bout, const Act& a0, const Act* a1, f
     if (dry_) return out;
     if (!ok_) return out;
     long long* tl = (timeline_ && tl_ops_ < 1024) ? timeline_ + (size_t)(tl_ops_++) * 32 : nullptr;
-    cudaError_t e = launch_conv_umma(p, plan, W.wu, W2 ? W2->wu : nullptr, umma_ws_, umma_counters_, out.f32, use_pdl_, st_, tl);
+    cudaError_t e = launch_conv_umma(p, plan, W.wu, W2 ? W2->wu : nullptr, out.f32, use_pdl_, st_, tl);
     ++launches_;
     ++umma_launches_;
     ck(e, "tcgen05 conv launch");
@@ -756,12 +753,23 @@ Act Engine::attention_core(const Act& q, const Act* kvself, const DAttn* cross, 
   }
   Act out = new_act(q.Bt, q.L, C);
   p.out = out.ptr;
+  if (debug_ && !dry_) {
+    char nm[32];
+    snprintf(nm, sizeof nm, "at%03d", at_index_++);
+    taps_[nm] = out;
+  }
   if (dry_ || !ok_) return out;
   if (C % H != 0 || p.d > 128) {
     fail("attention head dimension must divide channels and be <= 128");
     return out;
   }
-  cudaError_t e = (dtype_ == JEN1_DTYPE_F32) ? launch_attention<float>(p, st_) : launch_attention<bf16>(p, st_);
+  cudaError_t e;
+  if (use_umma_ && use_umma_attn_ && attn_umma_supported(p)) {
+    e = launch_attention_umma(p, use_pdl_, st_);
+    ++umma_attn_launches_;
+  } else {
+    e = (dtype_ == JEN1_DTYPE_F32) ? launch_attention<float>(p, st_) : launch_attention<bf16>(p, st_);
+  }
   ++launches_;
   ck(e, "attention launch");
   return out;
@@ -1136,6 +1144,7 @@ int Engine::forward(const float* x, const float* cc, const int32_t* cond_rows, c
   dry_ = false;
   debug_ = true;
   op_index_ = 0;
+  at_index_ = 0;
   trace_ = getenv("JEN1_TRACE") != nullptr;
   if (getenv("JEN1_TIMELINE") && !timeline_) {
     cudaMalloc((void**)&timeline_, 1024 * 32 * sizeof(long long));
@@ -1184,10 +1193,9 @@ void Engine::dump_timeline(cudaStream_t st) {
     const long long gap = prev_end ? t[11] - prev_end : 0;
     sum_gap += gap;
     sum_body += t[12] - t[11];
-    fprintf(stderr, "[jen1-tl] u%03d gap_ns %lld body_ns %lld | cyc: early %lld st_loads %lld st_bar1 %lld stats %lld raw0 %lld xform0 %lld panel0 %lld panels %lld accfull %lld ticket %lld end %lld | mma first_a %lld issued %lld done %lld\n",
-            i, gap, t[12] - t[11], t[2] - t[0], t[14] ? t[14] - t[2] : 0, t[15] ? t[15] - t[2] : 0, t[3] - t[2],
-            t[16] - t[2], t[17] - t[2], t[4] - t[2], t[5] - t[2], t[6] - t[2],
-            t[7] ? t[7] - t[2] : 0, t[8] - t[2], t[9] - t[2], t[10] - t[2], t[13] - t[2]);
+    fprintf(stderr, "[jen1-tl] u%03d gap_ns %lld body_ns %lld | cyc: early %lld stats %lld coef %lld panels %lld accfull %lld cluster %lld end %lld | mma first_a %lld issued %lld\n",
+            i, gap, t[12] - t[11], t[2] - t[0], t[3] - t[2], t[4] - t[2], t[5] - t[2], t[6] - t[2],
+            t[7] ? t[7] - t[2] : 0, t[8] - t[2], t[9] - t[2], t[10] - t[2]);
     prev_end = t[12];
   }
   fprintf(stderr, "[jen1-tl] total: %d tcgen05 ops, sum gap %.1f us, sum body %.1f us\n", tl_ops_, sum_gap / 1e3, sum_body / 1e3);
@@ -1310,7 +1318,7 @@ int Engine::sample_step(int step, float* x, const float* noise, const uint8_t* d
     }
     if (noise == nullptr) return fail("sample_step: the first graph-captured step needs a noise buffer");
     cudaGraph_t graph = nullptr;
-    const int64_t l0 = launches_, u0 = umma_launches_;
+    const int64_t l0 = launches_, u0 = umma_launches_, a0 = umma_attn_launches_;
     if (!ck(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal), "begin capture")) return 1;
     const bool good = body();
     cudaError_t e = cudaStreamEndCapture(st, &graph);
@@ -1321,6 +1329,8 @@ int Engine::sample_step(int step, float* x, const float* noise, const uint8_t* d
     }
     smp_.launches_per_step = launches_ - l0;
     smp_.umma_per_step = umma_launches_ - u0;
+    smp_.umma_attn_per_step = umma_attn_launches_ - a0;
+    umma_attn_launches_ = a0;
     launches_ = l0;
     umma_launches_ = u0;
     e = cudaGraphInstantiate(&smp_.exec, graph, 0);
@@ -1332,6 +1342,7 @@ int Engine::sample_step(int step, float* x, const float* noise, const uint8_t* d
   if (!ck(cudaGraphLaunch(smp_.exec, st), "graph launch")) return 1;
   launches_ += smp_.launches_per_step;
   umma_launches_ += smp_.umma_per_step;
+  umma_attn_launches_ += smp_.umma_attn_per_step;
   if (timeline_) {
     const char* e = getenv("JEN1_TIMELINE_STEP");
     if (e && atoi(e) == step) dump_timeline(st);

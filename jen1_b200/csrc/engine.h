@@ -106,6 +106,7 @@ class Engine {
   int64_t launch_count() const { return launches_; }
   int64_t weight_bytes() const { return step_weight_bytes_; }
   int64_t umma_launch_count() const { return umma_launches_; }
+  int64_t umma_attn_launch_count() const { return umma_attn_launches_; }
 
  private:
   // ---- errors
@@ -203,11 +204,9 @@ class Engine {
   // control
   CtlBlock* d_ctl_ = nullptr;
   // tcgen05 path
-  bool use_umma_ = false, use_pdl_ = true;
+  bool use_umma_ = false, use_pdl_ = true, use_umma_attn_ = true;
+  int64_t umma_attn_launches_ = 0;
   int num_sms_ = 148;
-  float* umma_ws_ = nullptr;
-  size_t umma_ws_cap_ = 0;
-  int* umma_counters_ = nullptr;
   int64_t umma_launches_ = 0;
   long long* timeline_ = nullptr;
   int tl_ops_ = 0;
@@ -220,7 +219,7 @@ class Engine {
   bool ok_ = true;
   // debug taps
   bool debug_ = false, trace_ = false;
-  int op_index_ = 0;
+  int op_index_ = 0, at_index_ = 0;
   std::map<std::string, Act> taps_;
   // sampler state
   struct Sampler {
@@ -235,7 +234,7 @@ class Engine {
     cudaGraphExec_t exec = nullptr;
     float* g_x = nullptr;
     const float* g_noise = nullptr;
-    int64_t launches_per_step = 0, umma_per_step = 0;
+    int64_t launches_per_step = 0, umma_per_step = 0, umma_attn_per_step = 0;
   } smp_;
 };
 

@@ -19,28 +19,32 @@ int conv_generic_row_tile();
 int conv_generic_col_tile();
 
 // ---- tcgen05 / TMEM implementation for bf16 storage (conv_umma.cu): swap-AB implicit GEMM, weights streamed as
-//      pre-packed 16 KB blobs by bulk async copies, split-K over an L2 workspace, PDL-aware.
+//      pre-packed 16 KB blobs by bulk async copies, split-K reduced over a thread-block cluster's distributed
+//      shared memory, PDL-aware.
 struct UmmaPlan {
   int ok;                 // 0: shape not supported -> generic kernel
   int NT, n_tiles;        // accumulator columns (padded flat positions) per CTA, number of N tiles
   int m_tiles;            // Cout / 128
-  int splitk;
+  int splitk;             // == cluster size (1,1,splitk)
   int Lq, amin, halo;     // padded positions per batch row; tap row-offset range
-  int R, PS, panel_bytes; // panel rows, panel stride (16-byte units), bytes of one panel (all sub-panels)
+  int R, PS, panel_bytes; // panel rows, rows per sub-panel, bytes of one panel (all sub-panels)
   int steps0, steps1;     // 64-channel K blocks of segment 0 / 1
   int stages, tmem_cols;
-  int bsw;                // activation-panel layout: 0 = no swizzle (chunk-major row panels), 1/2 = 128-byte swizzle
-  int E_max;              // GroupNorm partial entries per batch row (per phase) this launch writes
-  size_t smem, ws_bytes;
+  int bsw;                // activation-panel layout: 1 = 128-byte swizzle
+  int E_max;              // GroupNorm partial entries per batch row (per phase) this launch writes (tiles x splitk)
+  int ring_bytes;         // weight ring (also the epilogue scratch / partial tile)
+  int ch_cap;             // seg-0 input channels one CTA may own (coefficient-table stride)
+  int off_rowmeta1, off_colmeta, off_rowstat, off_gb, off_coef;  // shared-memory table offsets
+  size_t smem;
 };
-UmmaPlan conv_umma_plan(const ConvParams& p, bool want_stats, size_t ws_capacity_bytes, int num_sms);
+UmmaPlan conv_umma_plan(const ConvParams& p, bool want_stats, int num_sms);
 size_t conv_umma_packed_elems(int Cin, int Cout, int ntaps);
 void conv_umma_pack(const float* w_tap_cin_cout, int Cin, int Cout, int nphase, int taps_per_phase, int wtap0,
                     int wtap_phase, int wtap_step, uint16_t* out_bf16);
 cudaError_t conv_umma_init();
+int conv_umma_max_cluster();
 cudaError_t launch_conv_umma(const ConvParams& p, const UmmaPlan& plan, const void* w0_packed, const void* w1_packed,
-                             float* ws, int* counters, bool out_f32, bool pdl, cudaStream_t stream,
-                             long long* timeline = nullptr);
+                             bool out_f32, bool pdl, cudaStream_t stream, long long* timeline = nullptr);
 
 // ---- boundary: [Bx][C][L] fp32 (reference layout) -> channels-last T [Bx][L][Cp] (channels C..Cp-1 zero-filled so
 //      rows stay 16-byte aligned for the tcgen05 path) + GroupNorm partials (FG = 1)
@@ -79,6 +83,9 @@ struct AttnParams {
 };
 template <typename T>
 cudaError_t launch_attention(const AttnParams& p, cudaStream_t stream);
+// tcgen05 / TMEM implementation for bf16 storage (attn_umma.cu): head dim in {16, 32, 64, 128}, up to 256 keys
+bool attn_umma_supported(const AttnParams& p);
+cudaError_t launch_attention_umma(const AttnParams& p, bool pdl, cudaStream_t stream);
 
 // ---- classifier-free-guidance combine + std rescale (reference model.py:362-369) fused with the x0/eps
 //      conversion, clamp and DDIM update (reference gdm.py:128-141, 212-222)

@@ -47,8 +47,10 @@ def compare(T=150, B=2, variant="cfg", verbose=True, models=None):
         torch.cuda.synchronize()
         outs.append(y.cpu())
     worst, nbad, i = 0.0, 0, 0
-    while True:
-        name = "op%03d" % i
+    for pref in ("at", "op"):
+      i = 0
+      while True:
+        name = "%s%03d" % (pref, i)
         try:
             a = mg.engine.debug_tensor(name)
             b = mu.engine.debug_tensor(name)
