@@ -114,8 +114,17 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void bar_sync_producers() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// Cluster barrier for shared-memory hand-offs.  `barrier.cluster.arrive.release` compiles to MEMBAR.ALL.GPU (waits for
+// every outstanding global access of the thread: ~1 us in the layer chain); the data exchanged here lives in shared
+// memory only, so a CTA-scope fence (the stores are performed at this SM's shared memory, the one point every remote
+// ld.shared::cluster of them goes through) followed by the relaxed barrier is sufficient.
 __device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  asm volatile("fence.acq_rel.cta;\n\tbarrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float2 ld_cluster_f32x2(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
+  return v;
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -231,6 +240,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
   float* sred = reinterpret_cast<float*>(a_ring);                          // [kMaxSlots][128][2]
   float* rowred = sred + kMaxSlots * 128 * 2;                              // [4][cols_own][2]
   float* part = reinterpret_cast<float*>(a_ring + kSredBytes + 4 * NT * 8);  // [NT][128] fp32 partial tile (SK > 1)
+  float2* gpart = reinterpret_cast<float2*>(a_ring + kSredBytes + 4 * NT * 8 + NT * 512);  // [slots * 32] statistics partials
 
   if (tid == kProducers) {  // warp 4 lane 0
     for (int i = 0; i < pl.stages; ++i) {
@@ -398,8 +408,9 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const int idx = ib * 128 + rr + 16 * u;
+        if (idx >= rows) break;
         raw[u] = make_uint4(0u, 0u, 0u, 0u);
-        if (idx < rows && chan_ok) {
+        if (chan_ok) {
           const int2 m = meta[idx];
           if (m.x >= 0) {
             int b = m.y & 255;
@@ -525,13 +536,14 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
     //      fine-group sums of every (batch row, source, fine group) item from the producer's partial entries (an item
     //      is split over `parts` lanes combined by shuffles in a fixed order), then one thread per group.
     if (has_gn) {
-      const int nitem = nbl * 64;
+      const int two_src = S0.s[1].C > 0 ? 1 : 0;
+      const int nitem = nbl * (32 << two_src);
       int parts = 1;
-      while (parts < 8 && nitem * parts * 2 <= kProducers) parts *= 2;
+      while (parts < 16 && nitem * parts * 2 <= kProducers) parts *= 2;
       for (int base = 0; base < nitem * parts; base += kProducers) {
         const int idx = base + tid;
         const int item = idx / parts, part_i = idx - item * parts;
-        const int bl = item >> 6, fs = (item >> 5) & 1, ffg = item & 31;
+        const int bl = item >> (5 + two_src), fs = two_src ? (item >> 5) & 1 : 0, ffg = item & 31;
         double a = 0.0, q = 0.0;
         if (item < nitem) {
           const ConvSrc& fsr = S0.s[fs];
@@ -565,8 +577,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
         }
         if (item < nitem && part_i == 0) {
           const double sc = (double)S0.s[fs].scale;
-          fine[item * 2] = a * sc;
-          fine[item * 2 + 1] = q * sc * sc;
+          fine[((bl * 2 + fs) * 32 + ffg) * 2] = a * sc;
+          fine[((bl * 2 + fs) * 32 + ffg) * 2 + 1] = q * sc * sc;
         }
       }
       bar_sync_producers();
@@ -666,6 +678,12 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
   const int cb = (SK > 1) ? min(NT, sk * cols_per) : 0;
   const int ce = min(NT, cb + cols_per);
   const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+  const bool want_stats = p.stats_out != nullptr;
+  const bool want_rows = p.rowpart_out != nullptr;
+  const int b_first_e = q0 / Lq;
+  const int nb_out = min(p.B - 1, (q0 + NT - 1) / Lq) - b_first_e + 1;
+  const int gs = want_stats ? p.Cout / p.FGo : 128;  // channels per fine group of the output
+  const int ngl = 128 / gs;                           // fine groups inside this M tile
 
   if (SK > 1) {
     if (warp < 4) {
@@ -686,11 +704,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
   if (warp < 4) {
     const int cl = tid;
     const int nch = mt * 128 + cl;
-    const int b_first = q0 / Lq;
+    const int b_first = b_first_e;
     const float bias = p.bias ? __ldg(p.bias + nch) : 0.0f;
-    const bool want_stats = p.stats_out != nullptr;
-    const bool want_rows = p.rowpart_out != nullptr;
-    const int nb_out = min(p.B - 1, (q0 + NT - 1) / Lq) - b_first + 1;
     if (SK == 1) {
       mbar_wait(acc_full, 0);
       tc_fence_after();
@@ -702,12 +717,6 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
         sred[((size_t)bl * 128 + cl) * 2 + 1] = 0.f;
       }
     }
-    uint32_t part_remote[kMaxCluster];
-    if (SK > 1) {
-      const uint32_t mine = smem_u32(part);
-#pragma unroll
-      for (int s = 0; s < kMaxCluster; ++s) part_remote[s] = s < SK ? map_cluster(mine, (uint32_t)s) : 0u;
-    }
     int sb = -1;  // batch row of the statistics run in progress
     float colS = 0.f, colQ = 0.f;
     auto flush_stats = [&]() {
@@ -718,83 +727,90 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
       colS = 0.f;
       colQ = 0.f;
     };
-    for (int c0 = cb; c0 < ce; c0 += 16) {
-      const int ncol = min(16, ce - c0);
-      // column metadata and residual values of the chunk as one batch of loads
-      int orow[16], ebv[16];
-      float rv[16];
+    // one finished output element: bias / GELU / residual, store, statistics
+    auto finish = [&](float acc, float resv, int orow, int eb, int colrel) {
+      if (eb != sb) {
+        flush_stats();
+        sb = eb;
+      }
+      float x = 0.0f;
+      if (orow >= 0) {
+        x = acc + bias;
+        if (p.epi_act == ACT_GELU) x = gelu_f(x);
+        x += resv;
+        const size_t oi = ((size_t)eb * p.Lout + orow) * p.Cout + nch;
+        if (A.out_f32) {
+          ((float*)p.out)[oi] = x;
+        } else {
+          ((bf16*)p.out)[oi] = __float2bfloat16_rn(x);
+        }
+      }
+      colS += x;
+      colQ += x * x;
+      if (want_rows) {
+        const float rs = warp_sum(x), rq = warp_sum(x * x);
+        if (lane == 0) {
+          rowred[((size_t)warp * cols_per + colrel) * 2] = rs;
+          rowred[((size_t)warp * cols_per + colrel) * 2 + 1] = rq;
+        }
+      }
+    };
+    if (SK == 1) {
+      for (int c0 = 0; c0 < NT; c0 += 16) {
+        // column metadata and residual values of the chunk as one batch of loads
+        int orow[16], ebv[16];
+        float rv[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int2 cm = j < ncol ? colmeta[c0 + j] : make_int2(-1, -1);
-        orow[j] = cm.x;
-        ebv[j] = cm.y;
-        rv[j] = 0.f;
+        for (int j = 0; j < 16; ++j) {
+          const int2 cm = colmeta[c0 + j];
+          orow[j] = cm.x;
+          ebv[j] = cm.y;
+          rv[j] = 0.f;
+          if (p.res && cm.x >= 0) {
+            int rb = cm.y;
+            if (rb >= p.res_bmod) rb -= p.res_bmod;
+            rv[j] = ldf_cg((const bf16*)p.res + ((size_t)rb * p.Lout + cm.x) * p.Cout + nch);
+          }
+        }
+        float v[16];
+        tmem_ld16(trow + (uint32_t)c0, v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) finish(v[j], rv[j], orow[j], ebv[j], c0 + j);
+      }
+    } else {
+      // split-K: this CTA finishes columns [cb, ce) from the partial tiles of all cluster ranks (fixed order)
+      const uint32_t mine = smem_u32(part);
+      uint32_t part_remote[kMaxCluster];
+#pragma unroll
+      for (int s = 0; s < kMaxCluster; ++s) part_remote[s] = s < SK ? map_cluster(mine, (uint32_t)s) : mine;
+#pragma unroll 1
+      for (int c = cb; c < ce; ++c) {
+        const int2 cm = colmeta[c];
+        float resv = 0.f;
         if (p.res && cm.x >= 0) {
           int rb = cm.y;
           if (rb >= p.res_bmod) rb -= p.res_bmod;
-          rv[j] = ldf_cg((const bf16*)p.res + ((size_t)rb * p.Lout + cm.x) * p.Cout + nch);
+          resv = ldf_cg((const bf16*)p.res + ((size_t)rb * p.Lout + cm.x) * p.Cout + nch);
         }
-      }
-      float v[16];
-      if (SK == 1) {
-        tmem_ld16(trow + (uint32_t)c0, v);
-      } else {
+        const uint32_t off = (uint32_t)((c * 128 + cl) * 4);
+        float tv[kMaxCluster];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float acc = 0.f;
-          if (j < ncol) {
-            const uint32_t off = (uint32_t)(((c0 + j) * 128 + cl) * 4);
-            float tv[kMaxCluster];
+        for (int s = 0; s < kMaxCluster; ++s) tv[s] = ld_cluster_f32(part_remote[s] + off);
+        float acc = 0.f;
 #pragma unroll
-            for (int s = 0; s < kMaxCluster; ++s) tv[s] = s < SK ? ld_cluster_f32(part_remote[s] + off) : 0.f;
-#pragma unroll
-            for (int s = 0; s < kMaxCluster; ++s) acc += tv[s];  // fixed order: deterministic
-          }
-          v[j] = acc;
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        if (j < ncol) {
-          if (ebv[j] != sb) {
-            flush_stats();
-            sb = ebv[j];
-          }
-          float x = 0.0f;
-          if (orow[j] >= 0) {
-            x = v[j] + bias;
-            if (p.epi_act == ACT_GELU) x = gelu_f(x);
-            x += rv[j];
-            const size_t oi = ((size_t)ebv[j] * p.Lout + orow[j]) * p.Cout + nch;
-            if (A.out_f32) {
-              ((float*)p.out)[oi] = x;
-            } else {
-              ((bf16*)p.out)[oi] = __float2bfloat16_rn(x);
-            }
-          }
-          colS += x;
-          colQ += x * x;
-          if (want_rows) {
-            const float rs = warp_sum(x), rq = warp_sum(x * x);
-            if (lane == 0) {
-              rowred[((size_t)warp * cols_per + (c0 + j - cb)) * 2] = rs;
-              rowred[((size_t)warp * cols_per + (c0 + j - cb)) * 2 + 1] = rq;
-            }
-          }
-        }
+        for (int s = 0; s < kMaxCluster; ++s) acc += (s < SK) ? tv[s] : 0.f;
+        finish(acc, resv, cm.x, cm.y, c - cb);
       }
     }
     flush_stats();
     if (want_stats || want_rows) bar_sync_producers();
     if (want_stats) {
-      // per (batch row, fine group) partial of this CTA's columns -> entry (tile index within the batch row, split
-      // rank); the last tile of a batch row also zeroes the unused trailing entries so consumers sum a fixed n_ent.
-      const int gs = p.Cout / p.FGo;
-      const int ngl = 128 / gs;
-      const int n_ent = pl.E_max * p.nphase;  // E_max = tiles per batch row (max) * SK
+      // per (batch row, fine group) partial of this CTA's columns.  Without split-K it is the tile's entry; with
+      // split-K it is parked in shared memory for rank 0 to combine (below).  Entry = tile index within the batch
+      // row; the last tile of a batch row also zeroes the unused trailing entries so consumers sum a fixed n_ent.
+      const int n_ent = pl.E_max * p.nphase;
       for (int idx = tid; idx < nb_out * ngl; idx += kProducers) {
         const int bl = idx / ngl, gl = idx - bl * ngl;
-        const int bb = b_first + bl;
         float a = 0.f, q = 0.f;
         if (bl < kMaxSlots) {
           for (int c = gl * gs; c < (gl + 1) * gs; ++c) {
@@ -802,19 +818,24 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
             q += sred[((size_t)bl * 128 + c) * 2 + 1];
           }
         }
-        const int t_first = (bb * Lq) / NT;
-        int t_last = ((bb + 1) * Lq - 1) / NT;
-        if (t_last > pl.n_tiles - 1) t_last = pl.n_tiles - 1;
-        const int e = (nt - t_first) * SK + sk;
-        const int fg = (mt * 128) / gs + gl;
-        float* so = p.stats_out + (((size_t)bb * n_ent + (size_t)e * p.nphase + z) * p.FGo + fg) * 2;
-        so[0] = a;
-        so[1] = q;
-        if (nt == t_last) {
-          for (int e2 = e + SK; e2 < pl.E_max; e2 += SK) {
-            float* s2 = p.stats_out + (((size_t)bb * n_ent + (size_t)e2 * p.nphase + z) * p.FGo + fg) * 2;
-            s2[0] = 0.f;
-            s2[1] = 0.f;
+        if (SK > 1) {
+          gpart[idx] = make_float2(a, q);
+        } else {
+          const int bb = b_first + bl;
+          const int t_first = (bb * Lq) / NT;
+          int t_last = ((bb + 1) * Lq - 1) / NT;
+          if (t_last > pl.n_tiles - 1) t_last = pl.n_tiles - 1;
+          const int e = nt - t_first;
+          const int fg = (mt * 128) / gs + gl;
+          float* so = p.stats_out + (((size_t)bb * n_ent + (size_t)e * p.nphase + z) * p.FGo + fg) * 2;
+          so[0] = a;
+          so[1] = q;
+          if (nt == t_last) {
+            for (int e2 = e + 1; e2 < pl.E_max; ++e2) {
+              float* s2 = p.stats_out + (((size_t)bb * n_ent + (size_t)e2 * p.nphase + z) * p.FGo + fg) * 2;
+              s2[0] = 0.f;
+              s2[1] = 0.f;
+            }
           }
         }
       }
@@ -836,8 +857,44 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
     }
   }
 
+  if (SK > 1) {
+    cluster_sync_all();  // all partial tiles consumed, all statistics partials parked
+    if (want_stats) {
+      if (sk == 0 && warp < 4) {
+        // rank 0 combines the cluster's statistics partials in rank order and writes the tile's entry
+        const int n_ent = pl.E_max * p.nphase;
+        const uint32_t gmine = smem_u32(gpart);
+        for (int idx = tid; idx < nb_out * ngl; idx += kProducers) {
+          const int bl = idx / ngl, gl = idx - bl * ngl;
+          float a = 0.f, q = 0.f;
+          for (int s = 0; s < SK; ++s) {
+            const float2 v2 = ld_cluster_f32x2(map_cluster(gmine, (uint32_t)s) + (uint32_t)idx * 8u);
+            a += v2.x;
+            q += v2.y;
+          }
+          const int bb = b_first_e + bl;
+          const int t_first = (bb * Lq) / NT;
+          int t_last = ((bb + 1) * Lq - 1) / NT;
+          if (t_last > pl.n_tiles - 1) t_last = pl.n_tiles - 1;
+          const int e = nt - t_first;
+          const int fg = (mt * 128) / gs + gl;
+          float* so = p.stats_out + (((size_t)bb * n_ent + (size_t)e * p.nphase + z) * p.FGo + fg) * 2;
+          so[0] = a;
+          so[1] = q;
+          if (nt == t_last) {
+            for (int e2 = e + 1; e2 < pl.E_max; ++e2) {
+              float* s2 = p.stats_out + (((size_t)bb * n_ent + (size_t)e2 * p.nphase + z) * p.FGo + fg) * 2;
+              s2[0] = 0.f;
+              s2[1] = 0.f;
+            }
+          }
+        }
+      }
+      cluster_sync_all();  // nobody leaves while rank 0 may still read its partials
+    }
+  }
+
   if (tid == 0) { TL_MARK(8); TL_GLOBAL(12); }
-  if (SK > 1) cluster_sync_all();  // nobody leaves while its partial tile may still be read remotely
   tc_fence_before();
   __syncthreads();
   if (warp == 5) {
@@ -935,7 +992,7 @@ UmmaPlan conv_umma_plan(const ConvParams& p, bool want_stats, int num_sms) {
     const bool coef_ok = !need_coef || nslot * ch_cap_of(sk) * 8 <= coef_budget;
     pl.splitk = sk;
     pl.ch_cap = ch_cap_of(sk);
-    pl.E_max = ((pl.Lq - 1) / NT + 2) * sk;
+    pl.E_max = (pl.Lq - 1) / NT + 2;
     // tables
     const int rows0 = f * pl.R;
     int off = round_up(rows0 * 8, 16);
@@ -954,7 +1011,7 @@ UmmaPlan conv_umma_plan(const ConvParams& p, bool want_stats, int num_sms) {
     // the epilogue scratch (+ the fp32 partial tile of the cluster reduction) aliases the ring
     const int budget = 110 * 1024;
     int stages = (budget - 2 * pl.panel_bytes - misc) / kABytes;
-    const int scratch = kSredBytes + 4 * NT * 8 + (sk > 1 ? NT * 512 : 0);
+    const int scratch = kSredBytes + 4 * NT * 8 + (sk > 1 ? NT * 512 + kMaxSlots * 32 * 8 : 0);
     if (stages < 2) stages = 2;
     if (stages > 6) stages = 6;
     pl.stages = stages;
