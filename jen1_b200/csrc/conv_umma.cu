@@ -48,7 +48,7 @@ constexpr int kSredBytes = kMaxSlots * 128 * 2 * 4;
 // fixed part of the "misc" shared-memory block (see the carve-up in the kernel)
 constexpr int kMiscBar = 256;
 constexpr int kMiscStat = 2 * kMaxSlots * 32 * 4;            // gmean, grstd
-constexpr int kMiscFine = kMaxSlots * 2 * 32 * 2 * 8;        // fp64 fine-group sums
+constexpr int kMiscFine = kMaxSlots * 2 * 32 * 2 * 4;        // fine-group sums
 constexpr int kMiscFixed = kMiscBar + kMiscStat + kMiscFine + kMaxSlots * 4 + 32 * 8;  // + scrow + tap table
 
 int g_max_cluster = 8;
@@ -225,13 +225,13 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);  // [1]
   float* gmean = reinterpret_cast<float*>(misc + kMiscBar);         // [kMaxSlots][32]
   float* grstd = gmean + kMaxSlots * 32;                            // [kMaxSlots][32]
-  double* fine = reinterpret_cast<double*>(grstd + kMaxSlots * 32); // [kMaxSlots][2 sources][32 fine groups][2]
+  float* fine = grstd + kMaxSlots * 32;                             // [kMaxSlots][2 sources][32 fine groups][2]
   int* scrow = reinterpret_cast<int*>(fine + kMaxSlots * 2 * 32 * 2);  // [kMaxSlots] conditioning-table row per slot
   int2* tapg = reinterpret_cast<int2*>(scrow + kMaxSlots);          // [32] (panel row offset, unused) per tap
   uint8_t* tabs = misc + kMiscFixed;
   int2* rowmeta = reinterpret_cast<int2*>(tabs);                           // [rows0]: (input row | -1, b | panel row << 8)
   int2* rowmeta1 = reinterpret_cast<int2*>(tabs + pl.off_rowmeta1);        // [NT] same for the seg-1 K steps
-  int2* colmeta = reinterpret_cast<int2*>(tabs + pl.off_colmeta);          // [NT]: (output row | -1, batch row)
+  int4* colmeta = reinterpret_cast<int4*>(tabs + pl.off_colmeta);          // [NT]: (out offset | -1, residual offset, slot, batch row)
   float2* rowstat = reinterpret_cast<float2*>(tabs + pl.off_rowstat);      // [rows0] LayerNorm (mean, rstd) per slot
   float2* gb = reinterpret_cast<float2*>(tabs + pl.off_gb);                // [ch_cap] (gamma, beta)
   float2* coef = reinterpret_cast<float2*>(tabs + pl.off_coef);            // [slots][ch_cap] (a, s): y = a*x + s
@@ -267,6 +267,9 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
   // TMEM is held: dependents may now be scheduled next to us without a TMEM-allocation deadlock.
   pdl_launch_dependents();
   if (tid == 0) TL_MARK(1);
+
+  // weight-only / pre-chain values of the epilogue threads (thread == output channel of the M tile)
+  const float bias = (warp < 4 && p.bias) ? __ldg(p.bias + mt * 128 + tid) : 0.0f;
 
   if (warp == 4) {
     // ======================================================================== weight streamer
@@ -315,12 +318,12 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
           mbar_wait(&a_full[s], (uint32_t)(k & 1));
           tc_fence_after();
           if (t == st0 && j == 0) TL_MARK(9);
-          const uint32_t abase = smem_u32(a_ring + (size_t)s * kABytes);
-          const uint32_t bbase = pbase + prow * 128u;
+          // K advances by 32 bytes inside the swizzle atom: +2 in the (address >> 4) field of the descriptor
+          const uint64_t ad = make_desc_sw128(smem_u32(a_ring + (size_t)s * kABytes));
+          const uint64_t bd = make_desc_sw128(pbase + prow * 128u);
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
-            umma_bf16(tmem_base, make_desc_sw128(abase + (uint32_t)kk * 32u), make_desc_sw128(bbase + (uint32_t)kk * 32u),
-                      idesc, acc);
+            umma_bf16(tmem_base, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc, acc);
             acc = 1;
           }
           umma_commit(&a_empty[s]);
@@ -349,12 +352,11 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
     const bool has_film = affine && p.film != nullptr;
     const bool need_coef = (has_gn || has_film) && my_ch > 0;
     const int cpg = has_gn ? Ct / p.G : 1;
-    const int cl = tid;             // channel within the 128-wide M tile (== TMEM lane)
-    const int nch = mt * 128 + cl;  // output channel
     const int zoff = p.out_off0 + z * p.out_off_phase;
 
     // ---- tables that do not depend on earlier kernels (built while the previous layer is still running)
-    const float bias = p.bias ? __ldg(p.bias + nch) : 0.0f;
+    // (the conditioning rows are written before the step's kernel chain starts)
+    if (tid < nbl) scrow[tid] = p.cond_row ? __ldg(p.cond_row + b_first + tid) : 0;
     for (int idx = tid; idx < rows0; idx += kProducers) {
       const int rho = (f0 == 1) ? 0 : idx / pl.R;
       const int r = idx - rho * pl.R;
@@ -380,7 +382,10 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
       const int eml = q - eb * Lq;
       const int o = eml * p.out_stride + zoff;
       const bool valid = (eb < p.B) && (eml < p.Lm) && (o >= 0) && (o < p.Lout);
-      colmeta[c] = make_int2(valid ? o : -1, eb);
+      int rb = eb;
+      if (rb >= p.res_bmod) rb -= p.res_bmod;
+      colmeta[c] = make_int4(valid ? (eb * p.Lout + o) * p.Cout : -1, valid ? (rb * p.Lout + o) * p.Cout : 0,
+                             eb - b_first, eb);
     }
     if (has_gn) {
       for (int c = tid; c < my_ch; c += kProducers) {
@@ -496,7 +501,6 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
     if (tid == 0) { TL_MARK(2); TL_GLOBAL(11); }
 
     // ---- first loads: conditioning row, first panel unit (in flight during the statistics reduction)
-    if (tid < nbl) scrow[tid] = p.cond_row ? __ldcg(p.cond_row + b_first + tid) : 0;
     uint4 rA[8], rB[8];
     uint32_t mA = 0, mB = 0;
     issue(0, 0, rA, mA);
@@ -544,7 +548,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
         const int idx = base + tid;
         const int item = idx / parts, part_i = idx - item * parts;
         const int bl = item >> (5 + two_src), fs = two_src ? (item >> 5) & 1 : 0, ffg = item & 31;
-        double a = 0.0, q = 0.0;
+        float a = 0.f, q = 0.f;
         if (item < nitem) {
           const ConvSrc& fsr = S0.s[fs];
           if (fsr.C > 0 && ffg < fsr.FG) {
@@ -558,13 +562,13 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
                 const int e = e0 + u * parts;
                 buf[u] = e < fsr.n_ent ? __ldcg(st + (size_t)e * fsr.FG) : make_float2(0.f, 0.f);
               }
-              double a0 = 0.0, a1 = 0.0, q0s = 0.0, q1s = 0.0;
+              float a0 = 0.f, a1 = 0.f, q0s = 0.f, q1s = 0.f;
 #pragma unroll
               for (int u = 0; u < 16; u += 2) {
-                a0 += (double)buf[u].x;
-                q0s += (double)buf[u].y;
-                a1 += (double)buf[u + 1].x;
-                q1s += (double)buf[u + 1].y;
+                a0 += buf[u].x;
+                q0s += buf[u].y;
+                a1 += buf[u + 1].x;
+                q1s += buf[u + 1].y;
               }
               a += a0 + a1;
               q += q0s + q1s;
@@ -576,7 +580,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
           q += __shfl_xor_sync(0xffffffffu, q, o);
         }
         if (item < nitem && part_i == 0) {
-          const double sc = (double)S0.s[fs].scale;
+          const float sc = S0.s[fs].scale;
           fine[((bl * 2 + fs) * 32 + ffg) * 2] = a * sc;
           fine[((bl * 2 + fs) * 32 + ffg) * 2 + 1] = q * sc * sc;
         }
@@ -586,7 +590,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
       for (int idx = tid; idx < nbl * p.G; idx += kProducers) {
         const int bl = idx / p.G, g = idx - bl * p.G;
         const int lo = g * cpg, hi = lo + cpg;
-        double ga = 0.0, gq = 0.0;
+        float ga = 0.f, gq = 0.f;
         int off = 0;
         for (int s = 0; s < 2; ++s) {
           const ConvSrc& sr = S0.s[s];
@@ -602,15 +606,16 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
           }
           off += sr.C;
         }
-        const double n = (double)(p.gn_real_c > 0 ? p.gn_real_c / p.G : cpg) * (double)S0.L;
-        const double mean = ga / n;
-        double var = gq / n - mean * mean;
-        if (var < 0.0) var = 0.0;
-        gmean[bl * 32 + g] = (float)mean;
-        grstd[bl * 32 + g] = rsqrtf((float)var + p.eps);
+        // fp32 is ample here: this kernel only serves bf16 storage (the strict fp32 mode runs the generic kernel)
+        const float inv_n = 1.0f / ((float)(p.gn_real_c > 0 ? p.gn_real_c / p.G : cpg) * (float)S0.L);
+        const float mean = ga * inv_n;
+        float var = fmaf(-mean, mean, gq * inv_n);
+        if (var < 0.0f) var = 0.0f;
+        gmean[bl * 32 + g] = mean;
+        grstd[bl * 32 + g] = rsqrtf(var + p.eps);
       }
     }
-    bar_sync_producers();  // scrow, gmean / grstd, rowstat
+    bar_sync_producers();  // gmean / grstd, rowstat
     if (tid == 0) TL_MARK(3);
 
     // ---- per-(batch row, channel) affine coefficients of this CTA's channel slice:
@@ -685,8 +690,20 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
   const int gs = want_stats ? p.Cout / p.FGo : 128;  // channels per fine group of the output
   const int ngl = 128 / gs;                           // fine groups inside this M tile
 
+  const int nch = mt * 128 + (tid & 127);  // output channel of an epilogue thread
+  // split-K: residual values of this CTA's first columns are fetched before the accumulators are even ready
+  float res_pre[4] = {0.f, 0.f, 0.f, 0.f};
   if (SK > 1) {
     if (warp < 4) {
+      if (p.res) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (cb + j < ce) {
+            const int4 cm = colmeta[cb + j];
+            if (cm.x >= 0) res_pre[j] = ldf_cg((const bf16*)p.res + (size_t)(uint32_t)cm.y + nch);
+          }
+        }
+      }
       mbar_wait(acc_full, 0);
       tc_fence_after();
       if (tid == 0) TL_MARK(6);
@@ -703,10 +720,9 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
 
   if (warp < 4) {
     const int cl = tid;
-    const int nch = mt * 128 + cl;
     const int b_first = b_first_e;
-    const float bias = p.bias ? __ldg(p.bias + nch) : 0.0f;
-    if (SK == 1) {
+    const bool multi = nb_out > 1;  // the tile spans several batch rows: statistics are kept per slot
+    if (SK == 1) {  // the scratch below aliases the weight ring: every MMA must have completed first
       mbar_wait(acc_full, 0);
       tc_fence_after();
       if (tid == 0) TL_MARK(6);
@@ -717,36 +733,38 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
         sred[((size_t)bl * 128 + cl) * 2 + 1] = 0.f;
       }
     }
-    int sb = -1;  // batch row of the statistics run in progress
+    int sb = 0;  // slot of the statistics run in progress
     float colS = 0.f, colQ = 0.f;
     auto flush_stats = [&]() {
-      if (want_stats && sb >= b_first && sb < p.B && sb - b_first < kMaxSlots) {
-        sred[((size_t)(sb - b_first) * 128 + cl) * 2] = colS;
-        sred[((size_t)(sb - b_first) * 128 + cl) * 2 + 1] = colQ;
+      if (want_stats && sb >= 0 && sb < nb_out && sb < kMaxSlots) {
+        sred[((size_t)sb * 128 + cl) * 2] += colS;
+        sred[((size_t)sb * 128 + cl) * 2 + 1] += colQ;
       }
       colS = 0.f;
       colQ = 0.f;
     };
     // one finished output element: bias / GELU / residual, store, statistics
-    auto finish = [&](float acc, float resv, int orow, int eb, int colrel) {
-      if (eb != sb) {
-        flush_stats();
-        sb = eb;
+    auto finish = [&](float acc, float resv, int ooff, int col, int colrel) {
+      if (multi) {
+        const int slot = colmeta[col].z;
+        if (slot != sb) {
+          flush_stats();
+          sb = slot;
+        }
       }
       float x = 0.0f;
-      if (orow >= 0) {
+      if (ooff >= 0) {
         x = acc + bias;
         if (p.epi_act == ACT_GELU) x = gelu_f(x);
         x += resv;
-        const size_t oi = ((size_t)eb * p.Lout + orow) * p.Cout + nch;
         if (A.out_f32) {
-          ((float*)p.out)[oi] = x;
+          ((float*)p.out)[(size_t)(uint32_t)ooff + nch] = x;
         } else {
-          ((bf16*)p.out)[oi] = __float2bfloat16_rn(x);
+          ((bf16*)p.out)[(size_t)(uint32_t)ooff + nch] = __float2bfloat16_rn(x);
         }
       }
       colS += x;
-      colQ += x * x;
+      colQ = fmaf(x, x, colQ);
       if (want_rows) {
         const float rs = warp_sum(x), rq = warp_sum(x * x);
         if (lane == 0) {
@@ -756,26 +774,30 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
       }
     };
     if (SK == 1) {
-      for (int c0 = 0; c0 < NT; c0 += 16) {
-        // column metadata and residual values of the chunk as one batch of loads
-        int orow[16], ebv[16];
-        float rv[16];
+      // chunks of 16 columns; the metadata + residual loads of chunk k+1 are in flight while chunk k is finished
+      int ooA[16], ooB[16];
+      float rvA[16], rvB[16];
+      auto fetch = [&](int c0, int (&oo)[16], float (&rv)[16]) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const int2 cm = colmeta[c0 + j];
-          orow[j] = cm.x;
-          ebv[j] = cm.y;
-          rv[j] = 0.f;
-          if (p.res && cm.x >= 0) {
-            int rb = cm.y;
-            if (rb >= p.res_bmod) rb -= p.res_bmod;
-            rv[j] = ldf_cg((const bf16*)p.res + ((size_t)rb * p.Lout + cm.x) * p.Cout + nch);
-          }
+          const int4 cm = colmeta[c0 + j];
+          oo[j] = cm.x;
+          rv[j] = (p.res && cm.x >= 0) ? ldf_cg((const bf16*)p.res + (size_t)(uint32_t)cm.y + nch) : 0.f;
         }
+      };
+      auto process = [&](int c0, const int (&oo)[16], const float (&rv)[16]) {
         float v[16];
         tmem_ld16(trow + (uint32_t)c0, v);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) finish(v[j], rv[j], orow[j], ebv[j], c0 + j);
+        for (int j = 0; j < 16; ++j) finish(v[j], rv[j], oo[j], c0 + j, c0 + j);
+      };
+      fetch(0, ooA, rvA);
+      for (int c0 = 0; c0 < NT; c0 += 32) {
+        if (c0 + 16 < NT) fetch(c0 + 16, ooB, rvB);
+        process(c0, ooA, rvA);
+        if (c0 + 16 >= NT) break;
+        if (c0 + 32 < NT) fetch(c0 + 32, ooA, rvA);
+        process(c0 + 16, ooB, rvB);
       }
     } else {
       // split-K: this CTA finishes columns [cb, ce) from the partial tiles of all cluster ranks (fixed order)
@@ -785,13 +807,10 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
       for (int s = 0; s < kMaxCluster; ++s) part_remote[s] = s < SK ? map_cluster(mine, (uint32_t)s) : mine;
 #pragma unroll 1
       for (int c = cb; c < ce; ++c) {
-        const int2 cm = colmeta[c];
-        float resv = 0.f;
-        if (p.res && cm.x >= 0) {
-          int rb = cm.y;
-          if (rb >= p.res_bmod) rb -= p.res_bmod;
-          resv = ldf_cg((const bf16*)p.res + ((size_t)rb * p.Lout + cm.x) * p.Cout + nch);
-        }
+        const int4 cm = colmeta[c];
+        const int jr = c - cb;
+        float resv = jr == 0 ? res_pre[0] : (jr == 1 ? res_pre[1] : (jr == 2 ? res_pre[2] : res_pre[3]));
+        if (jr >= 4 && p.res && cm.x >= 0) resv = ldf_cg((const bf16*)p.res + (size_t)(uint32_t)cm.y + nch);
         const uint32_t off = (uint32_t)((c * 128 + cl) * 4);
         float tv[kMaxCluster];
 #pragma unroll
@@ -799,7 +818,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
         float acc = 0.f;
 #pragma unroll
         for (int s = 0; s < kMaxCluster; ++s) acc += (s < SK) ? tv[s] : 0.f;
-        finish(acc, resv, cm.x, cm.y, c - cb);
+        finish(acc, resv, cm.x, c, jr);
       }
     }
     flush_stats();
@@ -842,14 +861,14 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
     }
     if (want_rows) {
       for (int col = cb + tid; col < ce; col += kProducers) {
-        const int2 cm = colmeta[col];
+        const int4 cm = colmeta[col];
         if (cm.x >= 0) {
           float a = 0.f, qq = 0.f;
           for (int w = 0; w < 4; ++w) {
             a += rowred[((size_t)w * cols_per + (col - cb)) * 2];
             qq += rowred[((size_t)w * cols_per + (col - cb)) * 2 + 1];
           }
-          float* ro = p.rowpart_out + (((size_t)cm.y * p.Lout + cm.x) * pl.m_tiles + mt) * 2;
+          float* ro = p.rowpart_out + ((size_t)(cm.x / p.Cout) * pl.m_tiles + mt) * 2;
           ro[0] = a;
           ro[1] = qq;
         }
@@ -866,11 +885,15 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
         const uint32_t gmine = smem_u32(gpart);
         for (int idx = tid; idx < nb_out * ngl; idx += kProducers) {
           const int bl = idx / ngl, gl = idx - bl * ngl;
+          float2 v2[kMaxCluster];
+#pragma unroll
+          for (int s = 0; s < kMaxCluster; ++s)
+            v2[s] = ld_cluster_f32x2(map_cluster(gmine, (uint32_t)(s < SK ? s : 0)) + (uint32_t)idx * 8u);
           float a = 0.f, q = 0.f;
-          for (int s = 0; s < SK; ++s) {
-            const float2 v2 = ld_cluster_f32x2(map_cluster(gmine, (uint32_t)s) + (uint32_t)idx * 8u);
-            a += v2.x;
-            q += v2.y;
+#pragma unroll
+          for (int s = 0; s < kMaxCluster; ++s) {
+            a += s < SK ? v2[s].x : 0.f;
+            q += s < SK ? v2[s].y : 0.f;
           }
           const int bb = b_first_e + bl;
           const int t_first = (bb * Lq) / NT;
@@ -913,6 +936,7 @@ UmmaPlan conv_umma_plan(const ConvParams& p, bool want_stats, int num_sms) {
   const ConvSeg& S0 = p.seg[0];
   if (p.out == nullptr && p.out_ncl != nullptr) return pl;  // [B][C][L] output is a boundary format: generic path
   if (p.Cout % 128 != 0 || p.B < 1 || p.B > 256) return pl;
+  if ((long long)p.B * p.Lout * p.Cout >= (1ll << 31)) return pl;  // 32-bit element offsets in the column table
   for (int sg = 0; sg < p.nseg; ++sg)
     for (int k = 0; k < 2; ++k) {
       const ConvSrc& sr = p.seg[sg].s[k];
@@ -999,7 +1023,7 @@ UmmaPlan conv_umma_plan(const ConvParams& p, bool want_stats, int num_sms) {
     pl.off_rowmeta1 = off;
     off += p.nseg > 1 ? NT * 8 : 0;
     pl.off_colmeta = off;
-    off += NT * 8;
+    off += NT * 16;
     pl.off_rowstat = off;
     off += p.mode == PRO_ROWNORM ? round_up(rows0 * 8, 16) : 0;
     pl.off_gb = off;
