@@ -49,7 +49,7 @@ constexpr int kSredBytes = kMaxSlots * 128 * 2 * 4;
 constexpr int kMiscBar = 256;
 constexpr int kMiscStat = 2 * kMaxSlots * 32 * 4;            // gmean, grstd
 constexpr int kMiscFine = kMaxSlots * 2 * 32 * 2 * 4;        // fine-group sums
-constexpr int kMiscFixed = kMiscBar + kMiscStat + kMiscFine + kMaxSlots * 4 + 32 * 8;  // + scrow + tap table
+constexpr int kMiscFixed = kMiscBar + kMiscStat + kMiscFine + kMaxSlots * 4 + 32 * 8 + 64 * 8;  // + scrow + taps + group ranges
 
 int g_max_cluster = 8;
 
@@ -228,12 +228,12 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
   float* fine = grstd + kMaxSlots * 32;                             // [kMaxSlots][2 sources][32 fine groups][2]
   int* scrow = reinterpret_cast<int*>(fine + kMaxSlots * 2 * 32 * 2);  // [kMaxSlots] conditioning-table row per slot
   int2* tapg = reinterpret_cast<int2*>(scrow + kMaxSlots);          // [32] (panel row offset, unused) per tap
+  int2* grange = tapg + 32;                                         // [32 groups][2 sources] fine-group range
   uint8_t* tabs = misc + kMiscFixed;
   int2* rowmeta = reinterpret_cast<int2*>(tabs);                           // [rows0]: (input row | -1, b | panel row << 8)
   int2* rowmeta1 = reinterpret_cast<int2*>(tabs + pl.off_rowmeta1);        // [NT] same for the seg-1 K steps
   int4* colmeta = reinterpret_cast<int4*>(tabs + pl.off_colmeta);          // [NT]: (out offset | -1, residual offset, slot, batch row)
   float2* rowstat = reinterpret_cast<float2*>(tabs + pl.off_rowstat);      // [rows0] LayerNorm (mean, rstd) per slot
-  float2* gb = reinterpret_cast<float2*>(tabs + pl.off_gb);                // [ch_cap] (gamma, beta)
   float2* coef = reinterpret_cast<float2*>(tabs + pl.off_coef);            // [slots][ch_cap] (a, s): y = a*x + s
   const int ch_cap = pl.ch_cap;
   // epilogue scratch aliases the weight ring (all MMAs have completed by then)
@@ -356,7 +356,6 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
 
     // ---- tables that do not depend on earlier kernels (built while the previous layer is still running)
     // (the conditioning rows are written before the step's kernel chain starts)
-    if (tid < nbl) scrow[tid] = p.cond_row ? __ldg(p.cond_row + b_first + tid) : 0;
     for (int idx = tid; idx < rows0; idx += kProducers) {
       const int rho = (f0 == 1) ? 0 : idx / pl.R;
       const int r = idx - rho * pl.R;
@@ -387,12 +386,48 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
       colmeta[c] = make_int4(valid ? (eb * p.Lout + o) * p.Cout : -1, valid ? (rb * p.Lout + o) * p.Cout : 0,
                              eb - b_first, eb);
     }
-    if (has_gn) {
-      for (int c = tid; c < my_ch; c += kProducers) {
-        const int ch = ch_base + c;
-        gb[c] = ch < Ct ? make_float2(__ldg(p.gamma + ch), __ldg(p.beta + ch)) : make_float2(0.f, 0.f);
+    // weight-only halves of the affine coefficients: P = gamma*(1+film_scale), Q = beta*(1+film_scale) + film_shift
+    // (the FiLM table and the conditioning rows are written before the step's kernel chain starts)
+    if (need_coef) {
+      for (int bl = 0; bl < nbl; ++bl) {
+        const int crow = p.cond_row ? __ldg(p.cond_row + b_first + bl) : 0;
+        const float* fp = has_film ? p.film + (size_t)crow * p.film_stride : nullptr;
+        for (int c = tid; c < my_ch; c += kProducers) {
+          const int ch = ch_base + c;
+          float P = 0.f, Q = 0.f;
+          if (ch < Ct) {
+            P = has_gn ? __ldg(p.gamma + ch) : 1.0f;
+            Q = has_gn ? __ldg(p.beta + ch) : 0.0f;
+            if (has_film) {
+              const float f1 = __ldg(fp + ch) + 1.0f;
+              P *= f1;
+              Q = fmaf(Q, f1, __ldg(fp + Ct + ch));
+            }
+            if (!has_gn) P *= (ch >= S0.s[0].C ? S0.s[1] : S0.s[0]).scale;  // final: no statistics to wait for
+          }
+          coef[(size_t)bl * ch_cap + c] = make_float2(P, Q);
+        }
       }
     }
+    if (has_gn && tid < p.G) {  // fine-group range of GroupNorm group `tid` in each source
+      const int lo = tid * cpg, hi = lo + cpg;
+      int off = 0;
+      for (int sI = 0; sI < 2; ++sI) {
+        const ConvSrc& sr = S0.s[sI];
+        int2 rg = make_int2(0, 0);
+        if (sr.C > 0) {
+          const int olo = max(lo, off), ohi = min(hi, off + sr.C);
+          if (ohi > olo) {
+            const int gsz = sr.C / sr.FG;
+            rg = make_int2((olo - off) / gsz, (ohi - off) / gsz);
+          }
+        }
+        grange[tid * 2 + sI] = rg;
+        off += sr.C;
+      }
+    }
+    const float inv_n = has_gn ? 1.0f / ((float)(p.gn_real_c > 0 ? p.gn_real_c / p.G : cpg) * (float)S0.L) : 0.f;
+    const int cpg_shift = (has_gn && (cpg & (cpg - 1)) == 0) ? __ffs(cpg) - 1 : -1;
     bar_sync_producers();
 
     // ---- panel unit helpers.  A unit = up to 128 panel slots (rows) of one K step; a thread owns the 16-byte
@@ -589,25 +624,16 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
       // pass 2: one thread per (batch row, group)
       for (int idx = tid; idx < nbl * p.G; idx += kProducers) {
         const int bl = idx / p.G, g = idx - bl * p.G;
-        const int lo = g * cpg, hi = lo + cpg;
         float ga = 0.f, gq = 0.f;
-        int off = 0;
-        for (int s = 0; s < 2; ++s) {
-          const ConvSrc& sr = S0.s[s];
-          if (sr.C > 0) {
-            const int olo = max(lo, off), ohi = min(hi, off + sr.C);
-            if (ohi > olo) {
-              const int gs = sr.C / sr.FG;
-              for (int fg = (olo - off) / gs; fg < (ohi - off) / gs; ++fg) {
-                ga += fine[((bl * 2 + s) * 32 + fg) * 2];
-                gq += fine[((bl * 2 + s) * 32 + fg) * 2 + 1];
-              }
-            }
+#pragma unroll
+        for (int sI = 0; sI < 2; ++sI) {
+          const int2 rg = grange[g * 2 + sI];
+          for (int fg = rg.x; fg < rg.y; ++fg) {
+            ga += fine[((bl * 2 + sI) * 32 + fg) * 2];
+            gq += fine[((bl * 2 + sI) * 32 + fg) * 2 + 1];
           }
-          off += sr.C;
         }
         // fp32 is ample here: this kernel only serves bf16 storage (the strict fp32 mode runs the generic kernel)
-        const float inv_n = 1.0f / ((float)(p.gn_real_c > 0 ? p.gn_real_c / p.G : cpg) * (float)S0.L);
         const float mean = ga * inv_n;
         float var = fmaf(-mean, mean, gq * inv_n);
         if (var < 0.0f) var = 0.0f;
@@ -618,36 +644,17 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
     bar_sync_producers();  // gmean / grstd, rowstat
     if (tid == 0) TL_MARK(3);
 
-    // ---- per-(batch row, channel) affine coefficients of this CTA's channel slice:
-    //      y = a*x + s,  a = scale*gamma*rstd*(1+film_scale),  s = (beta - mean*gamma*rstd)*(1+film_scale) + film_shift
-    if (need_coef) {
+    // ---- per-(batch row, channel) affine coefficients of this CTA's channel slice, finished in place:
+    //      y = a*x + s,  a = scale*rstd*P,  s = Q - mean*rstd*P   (P, Q tabulated before the wait)
+    if (need_coef && has_gn) {
       for (int bl = 0; bl < nbl; ++bl) {
-        const float* fp = has_film ? p.film + (size_t)scrow[bl] * p.film_stride : nullptr;
         for (int c = tid; c < my_ch; c += kProducers) {
           const int ch = ch_base + c;
-          float a = 0.f, sft = 0.f;
-          if (ch < Ct) {
-            float fs = 0.f, fh = 0.f;
-            if (has_film) {
-              fs = __ldcg(fp + ch);
-              fh = __ldcg(fp + Ct + ch);
-            }
-            const float scale = (ch >= S0.s[0].C ? S0.s[1] : S0.s[0]).scale;
-            a = scale;
-            if (has_gn) {
-              const int g = ch / cpg;
-              const float2 gbv = gb[c];
-              const float ga = gbv.x * grstd[bl * 32 + g];
-              a = ga * scale;
-              sft = gbv.y - gmean[bl * 32 + g] * ga;
-            }
-            if (has_film) {
-              const float fs1 = fs + 1.0f;
-              a *= fs1;
-              sft = sft * fs1 + fh;
-            }
-          }
-          coef[(size_t)bl * ch_cap + c] = make_float2(a, sft);
+          const int g = cpg_shift >= 0 ? ch >> cpg_shift : ch / cpg;
+          const float2 pq = coef[(size_t)bl * ch_cap + c];
+          const float rp = (ch < Ct) ? grstd[bl * 32 + g] * pq.x : 0.f;
+          const float scale = (ch >= S0.s[0].C ? S0.s[1] : S0.s[0]).scale;
+          coef[(size_t)bl * ch_cap + c] = make_float2(rp * scale, (ch < Ct) ? fmaf(-gmean[bl * 32 + g], rp, pq.y) : 0.f);
         }
       }
       bar_sync_producers();
@@ -692,7 +699,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
 
   const int nch = mt * 128 + (tid & 127);  // output channel of an epilogue thread
   // split-K: residual values of this CTA's first columns are fetched before the accumulators are even ready
-  float res_pre[4] = {0.f, 0.f, 0.f, 0.f};
+  unsigned short res_pre[4] = {0, 0, 0, 0};
   if (SK > 1) {
     if (warp < 4) {
       if (p.res) {
@@ -700,7 +707,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
         for (int j = 0; j < 4; ++j) {
           if (cb + j < ce) {
             const int4 cm = colmeta[cb + j];
-            if (cm.x >= 0) res_pre[j] = ldf_cg((const bf16*)p.res + (size_t)(uint32_t)cm.y + nch);
+            if (cm.x >= 0) res_pre[j] = __ldcg(reinterpret_cast<const unsigned short*>(p.res) + (size_t)(uint32_t)cm.y + nch);
           }
         }
       }
@@ -775,21 +782,23 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
     };
     if (SK == 1) {
       // chunks of 16 columns; the metadata + residual loads of chunk k+1 are in flight while chunk k is finished
+      // (the residual is kept as raw bf16 bits until it is used, so that issuing the loads never waits on them)
       int ooA[16], ooB[16];
-      float rvA[16], rvB[16];
-      auto fetch = [&](int c0, int (&oo)[16], float (&rv)[16]) {
+      unsigned short rvA[16], rvB[16];
+      auto fetch = [&](int c0, int (&oo)[16], unsigned short (&rv)[16]) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int4 cm = colmeta[c0 + j];
           oo[j] = cm.x;
-          rv[j] = (p.res && cm.x >= 0) ? ldf_cg((const bf16*)p.res + (size_t)(uint32_t)cm.y + nch) : 0.f;
+          rv[j] = (p.res && cm.x >= 0) ? __ldcg(reinterpret_cast<const unsigned short*>(p.res) + (size_t)(uint32_t)cm.y + nch)
+                                       : (unsigned short)0;
         }
       };
-      auto process = [&](int c0, const int (&oo)[16], const float (&rv)[16]) {
+      auto process = [&](int c0, const int (&oo)[16], const unsigned short (&rv)[16]) {
         float v[16];
         tmem_ld16(trow + (uint32_t)c0, v);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) finish(v[j], rv[j], oo[j], c0 + j, c0 + j);
+        for (int j = 0; j < 16; ++j) finish(v[j], __uint_as_float((uint32_t)rv[j] << 16), oo[j], c0 + j, c0 + j);
       };
       fetch(0, ooA, rvA);
       for (int c0 = 0; c0 < NT; c0 += 32) {
@@ -809,8 +818,9 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
       for (int c = cb; c < ce; ++c) {
         const int4 cm = colmeta[c];
         const int jr = c - cb;
-        float resv = jr == 0 ? res_pre[0] : (jr == 1 ? res_pre[1] : (jr == 2 ? res_pre[2] : res_pre[3]));
-        if (jr >= 4 && p.res && cm.x >= 0) resv = ldf_cg((const bf16*)p.res + (size_t)(uint32_t)cm.y + nch);
+        const unsigned short rraw = jr == 0 ? res_pre[0] : (jr == 1 ? res_pre[1] : (jr == 2 ? res_pre[2] : res_pre[3]));
+        float resv = __uint_as_float((uint32_t)rraw << 16);
+        if (jr >= 4) resv = (p.res && cm.x >= 0) ? ldf_cg((const bf16*)p.res + (size_t)(uint32_t)cm.y + nch) : 0.f;
         const uint32_t off = (uint32_t)((c * 128 + cl) * 4);
         float tv[kMaxCluster];
 #pragma unroll
@@ -1027,7 +1037,6 @@ UmmaPlan conv_umma_plan(const ConvParams& p, bool want_stats, int num_sms) {
     pl.off_rowstat = off;
     off += p.mode == PRO_ROWNORM ? round_up(rows0 * 8, 16) : 0;
     pl.off_gb = off;
-    off += (p.mode == PRO_AFFINE && p.G > 0) ? pl.ch_cap * 8 : 0;
     pl.off_coef = off;
     off += need_coef ? nslot * pl.ch_cap * 8 : 0;
     const int misc = kMiscFixed + off;
