@@ -535,151 +535,149 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
     pdl_wait();  // everything below reads what the previous kernels wrote
     if (tid == 0) { TL_MARK(2); TL_GLOBAL(11); }
 
-    // ---- first loads: conditioning row, first panel unit (in flight during the statistics reduction)
+    // ---- panel pipeline.  One call site each for the loads (`issue`) and the transform (`consume`) keeps the kernel's
+    //      instruction footprint small; the loads of unit k+1 are in flight while unit k is transformed, and the
+    //      loads of unit 0 are in flight during the statistics reduction of the first pass.
     uint4 rA[8], rB[8];
     uint32_t mA = 0, mB = 0;
-    issue(0, 0, rA, mA);
+    int cn = 0, cib = 0;  // unit being consumed
+    int in_ = 0, iib = 0; // next unit to load
+    bool primed = false;
+    for (;;) {
+      const bool can_issue = in_ < my_steps;
+      if (can_issue) issue(in_, iib, rB, mB);
+      if (primed) {
+        consume(cn, cib, rA, mA);
+      } else {
+      if (!affine) {
+        // LayerNorm statistics of every panel row from the producer's per-tile partials (once per CTA)
+        const ConvSrc& sr = S0.s[0];
+        const float inv = 1.0f / (float)sr.C;
+        for (int idx = tid; idx < rows0; idx += kProducers) {
+          const int2 m = rowmeta[idx];
+          float2 ms = make_float2(0.f, 1.f);
+          if (m.x >= 0) {
+            int b = m.y & 255;
+            if (b >= sr.bmod) b -= sr.bmod;
+            const float2* rp = reinterpret_cast<const float2*>(p.rowpart) + ((size_t)b * S0.L + m.x) * p.rp_nct;
+            float a = 0.f, qq = 0.f;
+            for (int j0 = 0; j0 < p.rp_nct; j0 += 8) {
+              float2 v2[8];
+  #pragma unroll
+              for (int jj = 0; jj < 8; ++jj) v2[jj] = (j0 + jj < p.rp_nct) ? __ldcg(rp + j0 + jj) : make_float2(0.f, 0.f);
+  #pragma unroll
+              for (int jj = 0; jj < 8; ++jj) {
+                a += v2[jj].x;
+                qq += v2[jj].y;
+              }
+            }
+            const float m1 = a * inv;
+            float var = qq * inv - m1 * m1;
+            if (var < 0.0f) var = 0.0f;
+            ms = make_float2(m1, 1.0f / sqrtf(var + p.ln_eps));
+          }
+          rowstat[idx] = ms;
+        }
+      }
 
-    if (!affine) {
-      // LayerNorm statistics of every panel row from the producer's per-tile partials (once per CTA)
-      const ConvSrc& sr = S0.s[0];
-      const float inv = 1.0f / (float)sr.C;
-      for (int idx = tid; idx < rows0; idx += kProducers) {
-        const int2 m = rowmeta[idx];
-        float2 ms = make_float2(0.f, 1.f);
-        if (m.x >= 0) {
-          int b = m.y & 255;
-          if (b >= sr.bmod) b -= sr.bmod;
-          const float2* rp = reinterpret_cast<const float2*>(p.rowpart) + ((size_t)b * S0.L + m.x) * p.rp_nct;
-          float a = 0.f, qq = 0.f;
-          for (int j0 = 0; j0 < p.rp_nct; j0 += 8) {
-            float2 v2[8];
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj) v2[jj] = (j0 + jj < p.rp_nct) ? __ldcg(rp + j0 + jj) : make_float2(0.f, 0.f);
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj) {
-              a += v2[jj].x;
-              qq += v2[jj].y;
+      // ---- GroupNorm statistics of the input for the batch rows this tile touches.  Deterministic two-level reduce:
+      //      fine-group sums of every (batch row, source, fine group) item from the producer's partial entries (an item
+      //      is split over `parts` lanes combined by shuffles in a fixed order), then one thread per group.
+      if (has_gn) {
+        const int two_src = S0.s[1].C > 0 ? 1 : 0;
+        const int nitem = nbl * (32 << two_src);
+        int parts = 1;
+        while (parts < 16 && nitem * parts * 2 <= kProducers) parts *= 2;
+        for (int base = 0; base < nitem * parts; base += kProducers) {
+          const int idx = base + tid;
+          const int item = idx / parts, part_i = idx - item * parts;
+          const int bl = item >> (5 + two_src), fs = two_src ? (item >> 5) & 1 : 0, ffg = item & 31;
+          float a = 0.f, q = 0.f;
+          if (item < nitem) {
+            const ConvSrc& fsr = S0.s[fs];
+            if (fsr.C > 0 && ffg < fsr.FG) {
+              int b = b_first + bl;
+              if (b >= fsr.bmod) b -= fsr.bmod;
+              const float2* st = reinterpret_cast<const float2*>(fsr.stats) + (size_t)b * fsr.n_ent * fsr.FG + ffg;
+              for (int e0 = part_i; e0 < fsr.n_ent; e0 += parts * 16) {  // 16 independent L2 loads in flight
+                float2 buf[16];
+  #pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                  const int e = e0 + u * parts;
+                  buf[u] = e < fsr.n_ent ? __ldcg(st + (size_t)e * fsr.FG) : make_float2(0.f, 0.f);
+                }
+                float a0 = 0.f, a1 = 0.f, q0s = 0.f, q1s = 0.f;
+  #pragma unroll
+                for (int u = 0; u < 16; u += 2) {
+                  a0 += buf[u].x;
+                  q0s += buf[u].y;
+                  a1 += buf[u + 1].x;
+                  q1s += buf[u + 1].y;
+                }
+                a += a0 + a1;
+                q += q0s + q1s;
+              }
             }
           }
-          const float m1 = a * inv;
-          float var = qq * inv - m1 * m1;
+          for (int o = 1; o < parts; o <<= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            q += __shfl_xor_sync(0xffffffffu, q, o);
+          }
+          if (item < nitem && part_i == 0) {
+            const float sc = S0.s[fs].scale;
+            fine[((bl * 2 + fs) * 32 + ffg) * 2] = a * sc;
+            fine[((bl * 2 + fs) * 32 + ffg) * 2 + 1] = q * sc * sc;
+          }
+        }
+        bar_sync_producers();
+        // pass 2: one thread per (batch row, group)
+        for (int idx = tid; idx < nbl * p.G; idx += kProducers) {
+          const int bl = idx / p.G, g = idx - bl * p.G;
+          float ga = 0.f, gq = 0.f;
+  #pragma unroll
+          for (int sI = 0; sI < 2; ++sI) {
+            const int2 rg = grange[g * 2 + sI];
+            for (int fg = rg.x; fg < rg.y; ++fg) {
+              ga += fine[((bl * 2 + sI) * 32 + fg) * 2];
+              gq += fine[((bl * 2 + sI) * 32 + fg) * 2 + 1];
+            }
+          }
+          // fp32 is ample here: this kernel only serves bf16 storage (the strict fp32 mode runs the generic kernel)
+          const float mean = ga * inv_n;
+          float var = fmaf(-mean, mean, gq * inv_n);
           if (var < 0.0f) var = 0.0f;
-          ms = make_float2(m1, 1.0f / sqrtf(var + p.ln_eps));
+          gmean[bl * 32 + g] = mean;
+          grstd[bl * 32 + g] = rsqrtf(var + p.eps);
         }
-        rowstat[idx] = ms;
       }
-    }
+      bar_sync_producers();  // gmean / grstd, rowstat
+      if (tid == 0) TL_MARK(3);
 
-    // ---- GroupNorm statistics of the input for the batch rows this tile touches.  Deterministic two-level reduce:
-    //      fine-group sums of every (batch row, source, fine group) item from the producer's partial entries (an item
-    //      is split over `parts` lanes combined by shuffles in a fixed order), then one thread per group.
-    if (has_gn) {
-      const int two_src = S0.s[1].C > 0 ? 1 : 0;
-      const int nitem = nbl * (32 << two_src);
-      int parts = 1;
-      while (parts < 16 && nitem * parts * 2 <= kProducers) parts *= 2;
-      for (int base = 0; base < nitem * parts; base += kProducers) {
-        const int idx = base + tid;
-        const int item = idx / parts, part_i = idx - item * parts;
-        const int bl = item >> (5 + two_src), fs = two_src ? (item >> 5) & 1 : 0, ffg = item & 31;
-        float a = 0.f, q = 0.f;
-        if (item < nitem) {
-          const ConvSrc& fsr = S0.s[fs];
-          if (fsr.C > 0 && ffg < fsr.FG) {
-            int b = b_first + bl;
-            if (b >= fsr.bmod) b -= fsr.bmod;
-            const float2* st = reinterpret_cast<const float2*>(fsr.stats) + (size_t)b * fsr.n_ent * fsr.FG + ffg;
-            for (int e0 = part_i; e0 < fsr.n_ent; e0 += parts * 16) {  // 16 independent L2 loads in flight
-              float2 buf[16];
-#pragma unroll
-              for (int u = 0; u < 16; ++u) {
-                const int e = e0 + u * parts;
-                buf[u] = e < fsr.n_ent ? __ldcg(st + (size_t)e * fsr.FG) : make_float2(0.f, 0.f);
-              }
-              float a0 = 0.f, a1 = 0.f, q0s = 0.f, q1s = 0.f;
-#pragma unroll
-              for (int u = 0; u < 16; u += 2) {
-                a0 += buf[u].x;
-                q0s += buf[u].y;
-                a1 += buf[u + 1].x;
-                q1s += buf[u + 1].y;
-              }
-              a += a0 + a1;
-              q += q0s + q1s;
-            }
+      // ---- per-(batch row, channel) affine coefficients of this CTA's channel slice, finished in place:
+      //      y = a*x + s,  a = scale*rstd*P,  s = Q - mean*rstd*P   (P, Q tabulated before the wait)
+      if (need_coef && has_gn) {
+        for (int bl = 0; bl < nbl; ++bl) {
+          for (int c = tid; c < my_ch; c += kProducers) {
+            const int ch = ch_base + c;
+            const int g = cpg_shift >= 0 ? ch >> cpg_shift : ch / cpg;
+            const float2 pq = coef[(size_t)bl * ch_cap + c];
+            const float rp = (ch < Ct) ? grstd[bl * 32 + g] * pq.x : 0.f;
+            const float scale = (ch >= S0.s[0].C ? S0.s[1] : S0.s[0]).scale;
+            coef[(size_t)bl * ch_cap + c] = make_float2(rp * scale, (ch < Ct) ? fmaf(-gmean[bl * 32 + g], rp, pq.y) : 0.f);
           }
         }
-        for (int o = 1; o < parts; o <<= 1) {
-          a += __shfl_xor_sync(0xffffffffu, a, o);
-          q += __shfl_xor_sync(0xffffffffu, q, o);
-        }
-        if (item < nitem && part_i == 0) {
-          const float sc = S0.s[fs].scale;
-          fine[((bl * 2 + fs) * 32 + ffg) * 2] = a * sc;
-          fine[((bl * 2 + fs) * 32 + ffg) * 2 + 1] = q * sc * sc;
-        }
+        bar_sync_producers();
       }
-      bar_sync_producers();
-      // pass 2: one thread per (batch row, group)
-      for (int idx = tid; idx < nbl * p.G; idx += kProducers) {
-        const int bl = idx / p.G, g = idx - bl * p.G;
-        float ga = 0.f, gq = 0.f;
+      if (tid == 0) TL_MARK(4);
+      }
+      if (!can_issue) break;
 #pragma unroll
-        for (int sI = 0; sI < 2; ++sI) {
-          const int2 rg = grange[g * 2 + sI];
-          for (int fg = rg.x; fg < rg.y; ++fg) {
-            ga += fine[((bl * 2 + sI) * 32 + fg) * 2];
-            gq += fine[((bl * 2 + sI) * 32 + fg) * 2 + 1];
-          }
-        }
-        // fp32 is ample here: this kernel only serves bf16 storage (the strict fp32 mode runs the generic kernel)
-        const float mean = ga * inv_n;
-        float var = fmaf(-mean, mean, gq * inv_n);
-        if (var < 0.0f) var = 0.0f;
-        gmean[bl * 32 + g] = mean;
-        grstd[bl * 32 + g] = rsqrtf(var + p.eps);
-      }
-    }
-    bar_sync_producers();  // gmean / grstd, rowstat
-    if (tid == 0) TL_MARK(3);
-
-    // ---- per-(batch row, channel) affine coefficients of this CTA's channel slice, finished in place:
-    //      y = a*x + s,  a = scale*rstd*P,  s = Q - mean*rstd*P   (P, Q tabulated before the wait)
-    if (need_coef && has_gn) {
-      for (int bl = 0; bl < nbl; ++bl) {
-        for (int c = tid; c < my_ch; c += kProducers) {
-          const int ch = ch_base + c;
-          const int g = cpg_shift >= 0 ? ch >> cpg_shift : ch / cpg;
-          const float2 pq = coef[(size_t)bl * ch_cap + c];
-          const float rp = (ch < Ct) ? grstd[bl * 32 + g] * pq.x : 0.f;
-          const float scale = (ch >= S0.s[0].C ? S0.s[1] : S0.s[0]).scale;
-          coef[(size_t)bl * ch_cap + c] = make_float2(rp * scale, (ch < Ct) ? fmaf(-gmean[bl * 32 + g], rp, pq.y) : 0.f);
-        }
-      }
-      bar_sync_producers();
-    }
-    if (tid == 0) TL_MARK(4);
-
-    // ---- panels: loads of unit k+1 are in flight while unit k is transformed
-    {
-      int n = 0, ib = 0;
-      while (true) {
-        int n1 = n, ib1 = ib;
-        advance(n1, ib1);
-        const bool more1 = n1 < my_steps;
-        if (more1) issue(n1, ib1, rB, mB);
-        consume(n, ib, rA, mA);
-        if (!more1) break;
-        int n2 = n1, ib2 = ib1;
-        advance(n2, ib2);
-        const bool more2 = n2 < my_steps;
-        if (more2) issue(n2, ib2, rA, mA);
-        consume(n1, ib1, rB, mB);
-        if (!more2) break;
-        n = n2;
-        ib = ib2;
-      }
+      for (int u = 0; u < 8; ++u) rA[u] = rB[u];
+      mA = mB;
+      cn = in_;
+      cib = iib;
+      advance(in_, iib);
+      primed = true;
     }
     if (tid == 0) TL_MARK(5);
   }
@@ -781,32 +779,63 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
       }
     };
     if (SK == 1) {
-      // chunks of 16 columns; the metadata + residual loads of chunk k+1 are in flight while chunk k is finished
-      // (the residual is kept as raw bf16 bits until it is used, so that issuing the loads never waits on them)
-      int ooA[16], ooB[16];
-      unsigned short rvA[16], rvB[16];
-      auto fetch = [&](int c0, int (&oo)[16], unsigned short (&rv)[16]) {
+      const bool lean = !multi && !want_rows && p.epi_act == ACT_NONE && !A.out_f32;
+      if (lean) {
+        // The common case (conv + bias + optional residual, bf16 out, one batch row per tile) with a minimal body per
+        // column: the fully unrolled general path is ~2 KB of code per column and would stream the whole loop from
+        // the instruction cache hierarchy on every chunk.  Chunks of 16 columns; the metadata + residual loads of
+        // chunk k+1 are in flight while chunk k is finished (the residual is kept as raw bf16 bits until it is
+        // used, so that issuing the loads never waits on them).
+        const unsigned short* resp = reinterpret_cast<const unsigned short*>(p.res);
+        bf16* outp = (bf16*)p.out + nch;
+        int ooA[16], ooB[16];
+        unsigned short rvA[16], rvB[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const int4 cm = colmeta[c0 + j];
-          oo[j] = cm.x;
-          rv[j] = (p.res && cm.x >= 0) ? __ldcg(reinterpret_cast<const unsigned short*>(p.res) + (size_t)(uint32_t)cm.y + nch)
-                                       : (unsigned short)0;
+          const int4 cm = colmeta[j];
+          ooA[j] = cm.x;
+          rvA[j] = (resp && cm.x >= 0) ? __ldcg(resp + (size_t)(uint32_t)cm.y + nch) : (unsigned short)0;
         }
-      };
-      auto process = [&](int c0, const int (&oo)[16], const unsigned short (&rv)[16]) {
-        float v[16];
-        tmem_ld16(trow + (uint32_t)c0, v);
+        for (int c0 = 0; c0 < NT; c0 += 16) {
+          if (c0 + 16 < NT) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) finish(v[j], __uint_as_float((uint32_t)rv[j] << 16), oo[j], c0 + j, c0 + j);
-      };
-      fetch(0, ooA, rvA);
-      for (int c0 = 0; c0 < NT; c0 += 32) {
-        if (c0 + 16 < NT) fetch(c0 + 16, ooB, rvB);
-        process(c0, ooA, rvA);
-        if (c0 + 16 >= NT) break;
-        if (c0 + 32 < NT) fetch(c0 + 32, ooA, rvA);
-        process(c0 + 16, ooB, rvB);
+            for (int j = 0; j < 16; ++j) {
+              const int4 cm = colmeta[c0 + 16 + j];
+              ooB[j] = cm.x;
+              rvB[j] = (resp && cm.x >= 0) ? __ldcg(resp + (size_t)(uint32_t)cm.y + nch) : (unsigned short)0;
+            }
+          }
+          float v[16];
+          tmem_ld16(trow + (uint32_t)c0, v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float x = 0.f;
+            if (ooA[j] >= 0) {
+              x = (v[j] + bias) + __uint_as_float((uint32_t)rvA[j] << 16);
+              outp[(size_t)(uint32_t)ooA[j]] = __float2bfloat16_rn(x);
+            }
+            colS += x;
+            colQ = fmaf(x, x, colQ);
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            ooA[j] = ooB[j];
+            rvA[j] = rvB[j];
+          }
+        }
+      } else {
+        // general path (GELU / fp32 out / per-row LayerNorm partials / several batch rows per tile): rolled over the
+        // columns of a chunk to keep it compact (these launches have few columns)
+        for (int c0 = 0; c0 < NT; c0 += 16) {
+          float v[16];
+          tmem_ld16(trow + (uint32_t)c0, v);
+#pragma unroll 1
+          for (int j = 0; j < 16; ++j) {
+            const int4 cm = colmeta[c0 + j];
+            const float resv = (p.res && cm.x >= 0) ? ldf_cg((const bf16*)p.res + (size_t)(uint32_t)cm.y + nch) : 0.f;
+            finish(v[j], resv, cm.x, c0 + j, c0 + j);
+          }
+        }
       }
     } else {
       // split-K: this CTA finishes columns [cb, ce) from the partial tiles of all cluster ranks (fixed order)
