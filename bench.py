@@ -107,6 +107,17 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def _profile_facts(workload):
+    """DRAM traffic per step and kernel shares from the committed ncu launch list of the same command (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "step_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(workload, {})
+        except ValueError:
+            pass
+    return {}
+
+
 def _make_problem(desc, B, T, seed):
     import torch
     g = torch.Generator().manual_seed(seed)
@@ -303,31 +314,38 @@ def run_ours(args, wl):
         out_h.copy_(lat, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
 
-    e2e_call()  # warm (graph capture for this shape, allocator)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize(dev)
-    t0 = time.perf_counter()
-    e2e_call()
-    torch.cuda.synchronize(dev)
-    e_ms = (time.perf_counter() - t0) * 1e3
-    t_e = torch.tensor([e_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-    e_ms_step = t_e.item() / Se
-    h2d = (emb_p.numel() * 4 + mask_p.numel() + cc_p.numel() * 4)
-    d2h = out_h.numel() * 4
-    e2e = {"value": world * B * T / (e_ms_step / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d / Se,
-           "d2h_bytes_per_step": d2h / Se, "steps_per_call": Se, "ms_per_step": e_ms_step,
-           "api": "GaussianDiffusion.sample(UNetCFG1d, shape, conditioning) with pinned-host conditioning in, host latent out"}
+    e2e = None
+    if not args.no_e2e:
+        e2e_call()  # warm (graph capture for this shape, allocator)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        e2e_call()
+        torch.cuda.synchronize(dev)
+        e_ms = (time.perf_counter() - t0) * 1e3
+        t_e = torch.tensor([e_ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+        e_ms_step = t_e.item() / Se
+        h2d = (emb_p.numel() * 4 + mask_p.numel() + cc_p.numel() * 4)
+        d2h = out_h.numel() * 4
+        e2e = {"value": world * B * T / (e_ms_step / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d / Se,
+               "d2h_bytes_per_step": d2h / Se, "steps_per_call": Se, "ms_per_step": e_ms_step,
+               "api": "GaussianDiffusion.sample(UNetCFG1d, shape, conditioning): pinned-host conditioning in, host latent out; "
+                      "includes the per-call context K/V hoist and timestep tables"}
 
     if rank == 0:
         pk = _peaks()
         sb = step_bytes(desc, B, T, cfg=True, elem_bytes=2 if args.dtype == "bf16" else 4)
         alg = sb["total_bytes"]
         ach = alg / (ms_per_step / 1e3) / 1e9
+        prof = _profile_facts(args.workload)
         roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
-                "traffic": None, "kernel": "whole sampler step (one CUDA-graph launch = %d kernels)" % launches_per_step,
+                "traffic": prof.get("dram_bytes_per_step"),
+                "kernel": "one sampler step = one CUDA-graph launch of %d kernels; conv_umma_kernel (tcgen05 tap-GEMM) is "
+                          "%s of its device time" % (launches_per_step, prof.get("conv_umma_share", "the dominant share")),
+                "traffic_source": prof.get("source"),
                 "algorithmic_bytes": alg, "weight_bytes": sb["weight_bytes"], "act_bytes_per_row": sb["act_bytes_per_row"],
                 "rows": sb["rows"], "peak_source": pk["source"], "flops_per_step": sb["flops"],
                 "tensor_frac": sb["flops"] / (ms_per_step / 1e3) / 1e12 / pk["tensor"]}
@@ -355,6 +373,7 @@ def main():
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs under ncu)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     wl = WORKLOADS[args.workload]

@@ -356,29 +356,40 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
 
     // ---- tables that do not depend on earlier kernels (built while the previous layer is still running)
     // (the conditioning rows are written before the step's kernel chain starts)
+    // (q / Lq by a short subtract loop from the tile's first batch row: a tile touches <= kMaxSlots rows, and integer
+    //  division is ~40 instructions of pure latency on this path)
+    const int ml_first = q0 - b_first * Lq;
+    auto split_q = [&](int r, int& b, int& ml) {  // q0 + r = b * Lq + ml
+      b = b_first;
+      ml = ml_first + r;
+      while (ml >= Lq) {
+        ml -= Lq;
+        ++b;
+      }
+    };
     for (int idx = tid; idx < rows0; idx += kProducers) {
-      const int rho = (f0 == 1) ? 0 : idx / pl.R;
-      const int r = idx - rho * pl.R;
-      const int q = q0 + r;
-      const int b = q / Lq;
-      const int ml = q - b * Lq;
+      int rho = 0, r = idx;
+      while (r >= pl.R) {  // idx = rho * R + r, rho < in_stride
+        r -= pl.R;
+        ++rho;
+      }
+      int b, ml;
+      split_q(r, b, ml);
       const int irow = (ml + pl.amin) * f0 + rho;
       const bool ok = b < p.B && irow >= 0 && irow < S0.L;
       rowmeta[idx] = make_int2(ok ? irow : -1, (b & 255) | ((rho * pl.PS + r) << 8));
     }
     if (p.nseg > 1) {
       for (int r = tid; r < NT; r += kProducers) {
-        const int q = q0 + r;
-        const int b = q / Lq;
-        const int ml = q - b * Lq;
+        int b, ml;
+        split_q(r, b, ml);
         const bool ok = b < p.B && ml < p.seg[1].L;
         rowmeta1[r] = make_int2(ok ? ml : -1, (b & 255) | (r << 8));
       }
     }
     for (int c = tid; c < NT; c += kProducers) {
-      const int q = q0 + c;
-      const int eb = q / Lq;
-      const int eml = q - eb * Lq;
+      int eb, eml;
+      split_q(c, eb, eml);
       const int o = eml * p.out_stride + zoff;
       const bool valid = (eb < p.B) && (eml < p.Lm) && (o >= 0) && (o < p.Lout);
       int rb = eb;

@@ -26,7 +26,7 @@ def make(desc, sd, impl):
     return m
 
 
-def compare(T=150, B=2, variant="cfg", verbose=True, models=None):
+def compare(T=150, B=2, variant="cfg", verbose=True, models=None, masked_tail=0):
     desc = UNetDesc()
     if models is None:
         sd = random_state_dict(desc, 0)
@@ -36,7 +36,11 @@ def compare(T=150, B=2, variant="cfg", verbose=True, models=None):
     x = torch.randn(B, 128, T, generator=g).cuda()
     t = torch.randint(0, 1000, (B,), generator=g).cuda()
     emb = torch.randn(B, 128, 1024, generator=g).cuda()
-    mask = torch.ones(B, 128, dtype=torch.bool).cuda()
+    mask = torch.ones(B, 128, dtype=torch.bool)
+    if masked_tail:  # what T5Conditioner produces for short prompts: padded rows masked out and zeroed
+        mask[:, 128 - masked_tail:] = False
+        emb = emb * mask[:, :, None].cuda()
+    mask = mask.cuda()
     cc = torch.randn(B, 129, T, generator=g).cuda()
     kw = {"plain": dict(embedding_scale=1.0),
           "cfg": dict(embedding_scale=0.8, batch_cfg=True, scale_cfg=True),
