@@ -148,14 +148,14 @@ __global__ void __launch_bounds__(kAtThreads, 1) attn_umma_kernel(const __grid_c
   const int trow_time = p.cross ? p.cond_row[r] : 0;
   const int cpr = 1 << g.cpr_shift;
 
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-
-  // ---- stage Q, K, V: items = 16-byte chunks; [0, nq) Q chunks, then K chunks, then V chunks
-  {
-    const int nq = 128 << g.cpr_shift;
-    const int nk = g.KR << g.cpr_shift;
-    const int total = nq + 2 * nk;
-    for (int base = 0; base < total; base += kAtThreads * 8) {
+  // ---- stage Q, K, V: items = 16-byte chunks; [0, nq) Q chunks, then K chunks, then V chunks.  Cross-attention
+  //      keys / values come from per-step constant caches, so they are staged BEFORE the PDL wait (while the
+  //      producer of Q is still running); only what the previous kernel wrote is loaded after it.
+  const int nq = 128 << g.cpr_shift;
+  const int nk = g.KR << g.cpr_shift;
+  const int total = nq + 2 * nk;
+  auto stage = [&](int lo, int hi) {
+    for (int base = lo; base < hi; base += kAtThreads * 8) {
       uint4 val[8];
       float mk[8];
       uint32_t dst[8];
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(kAtThreads, 1) attn_umma_kernel(const __grid_c
         val[u] = make_uint4(0u, 0u, 0u, 0u);
         mk[u] = 1.0f;
         dst[u] = 0xffffffffu;
-        if (it < total) {
+        if (it < hi) {
           int kind, idx;
           if (it < nq) {
             kind = 0;
@@ -221,30 +221,33 @@ __global__ void __launch_bounds__(kAtThreads, 1) attn_umma_kernel(const __grid_c
         }
       }
     }
-    // chunks beyond the head dim inside the last 64-channel block must read as zero (d = 16 / 32)
-    if (cpr < 8) {
-      const int rows_all = 128 + 2 * g.KR;
-      const int zc = 8 - cpr;
-      for (int it = tid; it < rows_all * zc; it += kAtThreads) {
-        const int row_all = it / zc, ch = cpr + (it - row_all * zc);
-        uint32_t tile;
-        int row;
-        if (row_all < 128) {
-          tile = 0u;
-          row = row_all;
-        } else if (row_all < 128 + g.KR) {
-          tile = g.off_k;
-          row = row_all - 128;
-        } else {
-          tile = g.off_v;
-          row = row_all - 128 - g.KR;
-        }
-        *reinterpret_cast<uint4*>(smem + tile + (uint32_t)row * 128u + (uint32_t)((ch ^ (row & 7)) * 16)) = make_uint4(0u, 0u, 0u, 0u);
+  };
+  // chunks beyond the head dim inside the last 64-channel block must read as zero (d = 16 / 32)
+  if (cpr < 8) {
+    const int rows_all = 128 + 2 * g.KR;
+    const int zc = 8 - cpr;
+    for (int it = tid; it < rows_all * zc; it += kAtThreads) {
+      const int row_all = it / zc, ch = cpr + (it - row_all * zc);
+      uint32_t tile;
+      int row;
+      if (row_all < 128) {
+        tile = 0u;
+        row = row_all;
+      } else if (row_all < 128 + g.KR) {
+        tile = g.off_k;
+        row = row_all - 128;
+      } else {
+        tile = g.off_v;
+        row = row_all - 128 - g.KR;
       }
+      *reinterpret_cast<uint4*>(smem + tile + (uint32_t)row * 128u + (uint32_t)((ch ^ (row & 7)) * 16)) = make_uint4(0u, 0u, 0u, 0u);
     }
-    fence_async_smem();
-    mbar_arrive(&bars[0]);
   }
+  if (p.cross) stage(nq, total);
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  stage(0, p.cross ? nq : total);
+  fence_async_smem();
+  mbar_arrive(&bars[0]);
 
   if (warp == 4 && lane == 0) {
     // ======================================================================== MMA issuer

@@ -240,7 +240,6 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
   float* sred = reinterpret_cast<float*>(a_ring);                          // [kMaxSlots][128][2]
   float* rowred = sred + kMaxSlots * 128 * 2;                              // [4][cols_own][2]
   float* part = reinterpret_cast<float*>(a_ring + kSredBytes + 4 * NT * 8);  // [NT][128] fp32 partial tile (SK > 1)
-  float2* gpart = reinterpret_cast<float2*>(a_ring + kSredBytes + 4 * NT * 8 + NT * 512);  // [slots * 32] statistics partials
 
   if (tid == kProducers) {  // warp 4 lane 0
     for (int i = 0; i < pl.stages; ++i) {
@@ -595,49 +594,66 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
       //      fine-group sums of every (batch row, source, fine group) item from the producer's partial entries (an item
       //      is split over `parts` lanes combined by shuffles in a fixed order), then one thread per group.
       if (has_gn) {
+        // items = (batch row, source, PAIR of fine groups): one 16-byte load brings both (sum, sumsq) pairs of an entry
         const int two_src = S0.s[1].C > 0 ? 1 : 0;
-        const int nitem = nbl * (32 << two_src);
+        const int nitem = nbl * (16 << two_src);
         int parts = 1;
         while (parts < 16 && nitem * parts * 2 <= kProducers) parts *= 2;
         for (int base = 0; base < nitem * parts; base += kProducers) {
           const int idx = base + tid;
           const int item = idx / parts, part_i = idx - item * parts;
-          const int bl = item >> (5 + two_src), fs = two_src ? (item >> 5) & 1 : 0, ffg = item & 31;
-          float a = 0.f, q = 0.f;
+          const int bl = item >> (4 + two_src), fs = two_src ? (item >> 4) & 1 : 0, pi = item & 15;
+          float a0 = 0.f, q0s = 0.f, a1 = 0.f, q1s = 0.f;
           if (item < nitem) {
             const ConvSrc& fsr = S0.s[fs];
-            if (fsr.C > 0 && ffg < fsr.FG) {
+            if (fsr.C > 0 && 2 * pi < fsr.FG) {
               int b = b_first + bl;
               if (b >= fsr.bmod) b -= fsr.bmod;
-              const float2* st = reinterpret_cast<const float2*>(fsr.stats) + (size_t)b * fsr.n_ent * fsr.FG + ffg;
-              for (int e0 = part_i; e0 < fsr.n_ent; e0 += parts * 16) {  // 16 independent L2 loads in flight
-                float2 buf[16];
-  #pragma unroll
-                for (int u = 0; u < 16; ++u) {
-                  const int e = e0 + u * parts;
-                  buf[u] = e < fsr.n_ent ? __ldcg(st + (size_t)e * fsr.FG) : make_float2(0.f, 0.f);
+              const float* st = fsr.stats + ((size_t)b * fsr.n_ent * fsr.FG + 2 * pi) * 2;
+              if (fsr.FG >= 2) {
+                for (int e0 = part_i; e0 < fsr.n_ent; e0 += parts * 12) {  // 12 independent 16-byte L2 loads in flight
+                  float4 buf[12];
+#pragma unroll
+                  for (int u = 0; u < 12; ++u) {
+                    const int e = e0 + u * parts;
+                    buf[u] = e < fsr.n_ent ? __ldcg(reinterpret_cast<const float4*>(st + (size_t)e * fsr.FG * 2))
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+                  }
+#pragma unroll
+                  for (int u = 0; u < 12; ++u) {
+                    a0 += buf[u].x;
+                    q0s += buf[u].y;
+                    a1 += buf[u].z;
+                    q1s += buf[u].w;
+                  }
                 }
-                float a0 = 0.f, a1 = 0.f, q0s = 0.f, q1s = 0.f;
-  #pragma unroll
-                for (int u = 0; u < 16; u += 2) {
-                  a0 += buf[u].x;
-                  q0s += buf[u].y;
-                  a1 += buf[u + 1].x;
-                  q1s += buf[u + 1].y;
+              } else {  // a single whole-tensor group (boundary tensors)
+                for (int e0 = part_i; e0 < fsr.n_ent; e0 += parts * 12) {
+                  float2 buf[12];
+#pragma unroll
+                  for (int u = 0; u < 12; ++u) {
+                    const int e = e0 + u * parts;
+                    buf[u] = e < fsr.n_ent ? __ldcg(reinterpret_cast<const float2*>(st + (size_t)e * fsr.FG * 2)) : make_float2(0.f, 0.f);
+                  }
+#pragma unroll
+                  for (int u = 0; u < 12; ++u) {
+                    a0 += buf[u].x;
+                    q0s += buf[u].y;
+                  }
                 }
-                a += a0 + a1;
-                q += q0s + q1s;
               }
             }
           }
           for (int o = 1; o < parts; o <<= 1) {
-            a += __shfl_xor_sync(0xffffffffu, a, o);
-            q += __shfl_xor_sync(0xffffffffu, q, o);
+            a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+            q0s += __shfl_xor_sync(0xffffffffu, q0s, o);
+            a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+            q1s += __shfl_xor_sync(0xffffffffu, q1s, o);
           }
           if (item < nitem && part_i == 0) {
             const float sc = S0.s[fs].scale;
-            fine[((bl * 2 + fs) * 32 + ffg) * 2] = a * sc;
-            fine[((bl * 2 + fs) * 32 + ffg) * 2 + 1] = q * sc * sc;
+            float4* fo = reinterpret_cast<float4*>(fine + ((bl * 2 + fs) * 32 + 2 * pi) * 2);
+            *fo = make_float4(a0 * sc, q0s * sc * sc, a1 * sc, q1s * sc * sc);
           }
         }
         bar_sync_producers();
@@ -874,10 +890,9 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
     flush_stats();
     if (want_stats || want_rows) bar_sync_producers();
     if (want_stats) {
-      // per (batch row, fine group) partial of this CTA's columns.  Without split-K it is the tile's entry; with
-      // split-K it is parked in shared memory for rank 0 to combine (below).  Entry = tile index within the batch
-      // row; the last tile of a batch row also zeroes the unused trailing entries so consumers sum a fixed n_ent.
-      const int n_ent = pl.E_max * p.nphase;
+      // per (batch row, fine group) partial of this CTA's columns -> entry (tile index within the batch row, split
+      // rank); the last tile of a batch row also zeroes the unused trailing entries so consumers sum a fixed n_ent.
+      const int n_ent = pl.E_max * p.nphase;  // E_max = tiles per batch row (max) * SK
       for (int idx = tid; idx < nb_out * ngl; idx += kProducers) {
         const int bl = idx / ngl, gl = idx - bl * ngl;
         float a = 0.f, q = 0.f;
@@ -887,24 +902,20 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
             q += sred[((size_t)bl * 128 + c) * 2 + 1];
           }
         }
-        if (SK > 1) {
-          gpart[idx] = make_float2(a, q);
-        } else {
-          const int bb = b_first + bl;
-          const int t_first = (bb * Lq) / NT;
-          int t_last = ((bb + 1) * Lq - 1) / NT;
-          if (t_last > pl.n_tiles - 1) t_last = pl.n_tiles - 1;
-          const int e = nt - t_first;
-          const int fg = (mt * 128) / gs + gl;
-          float* so = p.stats_out + (((size_t)bb * n_ent + (size_t)e * p.nphase + z) * p.FGo + fg) * 2;
-          so[0] = a;
-          so[1] = q;
-          if (nt == t_last) {
-            for (int e2 = e + 1; e2 < pl.E_max; ++e2) {
-              float* s2 = p.stats_out + (((size_t)bb * n_ent + (size_t)e2 * p.nphase + z) * p.FGo + fg) * 2;
-              s2[0] = 0.f;
-              s2[1] = 0.f;
-            }
+        const int bb = b_first + bl;
+        const int t_first = (bb * Lq) / NT;
+        int t_last = ((bb + 1) * Lq - 1) / NT;
+        if (t_last > pl.n_tiles - 1) t_last = pl.n_tiles - 1;
+        const int e = (nt - t_first) * SK + sk;
+        const int fg = (mt * 128) / gs + gl;
+        float* so = p.stats_out + (((size_t)bb * n_ent + (size_t)e * p.nphase + z) * p.FGo + fg) * 2;
+        so[0] = a;
+        so[1] = q;
+        if (nt == t_last) {
+          for (int e2 = e + SK; e2 < pl.E_max; e2 += SK) {
+            float* s2 = p.stats_out + (((size_t)bb * n_ent + (size_t)e2 * p.nphase + z) * p.FGo + fg) * 2;
+            s2[0] = 0.f;
+            s2[1] = 0.f;
           }
         }
       }
@@ -926,46 +937,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
     }
   }
 
-  if (SK > 1) {
-    cluster_sync_all();  // all partial tiles consumed, all statistics partials parked
-    if (want_stats) {
-      if (sk == 0 && warp < 4) {
-        // rank 0 combines the cluster's statistics partials in rank order and writes the tile's entry
-        const int n_ent = pl.E_max * p.nphase;
-        const uint32_t gmine = smem_u32(gpart);
-        for (int idx = tid; idx < nb_out * ngl; idx += kProducers) {
-          const int bl = idx / ngl, gl = idx - bl * ngl;
-          float2 v2[kMaxCluster];
-#pragma unroll
-          for (int s = 0; s < kMaxCluster; ++s)
-            v2[s] = ld_cluster_f32x2(map_cluster(gmine, (uint32_t)(s < SK ? s : 0)) + (uint32_t)idx * 8u);
-          float a = 0.f, q = 0.f;
-#pragma unroll
-          for (int s = 0; s < kMaxCluster; ++s) {
-            a += s < SK ? v2[s].x : 0.f;
-            q += s < SK ? v2[s].y : 0.f;
-          }
-          const int bb = b_first_e + bl;
-          const int t_first = (bb * Lq) / NT;
-          int t_last = ((bb + 1) * Lq - 1) / NT;
-          if (t_last > pl.n_tiles - 1) t_last = pl.n_tiles - 1;
-          const int e = nt - t_first;
-          const int fg = (mt * 128) / gs + gl;
-          float* so = p.stats_out + (((size_t)bb * n_ent + (size_t)e * p.nphase + z) * p.FGo + fg) * 2;
-          so[0] = a;
-          so[1] = q;
-          if (nt == t_last) {
-            for (int e2 = e + 1; e2 < pl.E_max; ++e2) {
-              float* s2 = p.stats_out + (((size_t)bb * n_ent + (size_t)e2 * p.nphase + z) * p.FGo + fg) * 2;
-              s2[0] = 0.f;
-              s2[1] = 0.f;
-            }
-          }
-        }
-      }
-      cluster_sync_all();  // nobody leaves while rank 0 may still read its partials
-    }
-  }
+  if (SK > 1) cluster_sync_all();  // nobody leaves while its partial tile may still be read remotely
 
   if (tid == 0) { TL_MARK(8); TL_GLOBAL(12); }
   tc_fence_before();
@@ -1066,7 +1038,7 @@ UmmaPlan conv_umma_plan(const ConvParams& p, bool want_stats, int num_sms) {
     const bool coef_ok = !need_coef || nslot * ch_cap_of(sk) * 8 <= coef_budget;
     pl.splitk = sk;
     pl.ch_cap = ch_cap_of(sk);
-    pl.E_max = (pl.Lq - 1) / NT + 2;
+    pl.E_max = ((pl.Lq - 1) / NT + 2) * sk;
     // tables
     const int rows0 = f * pl.R;
     int off = round_up(rows0 * 8, 16);
@@ -1084,7 +1056,7 @@ UmmaPlan conv_umma_plan(const ConvParams& p, bool want_stats, int num_sms) {
     // the epilogue scratch (+ the fp32 partial tile of the cluster reduction) aliases the ring
     const int budget = 110 * 1024;
     int stages = (budget - 2 * pl.panel_bytes - misc) / kABytes;
-    const int scratch = kSredBytes + 4 * NT * 8 + (sk > 1 ? NT * 512 + kMaxSlots * 32 * 8 : 0);
+    const int scratch = kSredBytes + 4 * NT * 8 + (sk > 1 ? NT * 512 : 0);
     if (stages < 2) stages = 2;
     if (stages > 6) stages = 6;
     pl.stages = stages;

@@ -82,3 +82,27 @@ def test_full_unet_bf16_matches_reference_golden(ab_models, golden_dir):
                    channels_list=[cc.cuda()], **dict(VARIANTS[v])).cpu()
             err = ((y - ref).norm() / ref.norm()).item()
             assert err < 2e-2, "full bf16 %s %s rel-L2 %.3e" % (name, v, err)
+
+
+def test_full_size_batch_independence(ab_models):
+    """BASELINE config 3 shape (30 s latent T=4545, 4 samples -> 8 CFG rows): samples are independent units, so
+    permuting the batch permutes the outputs.  Only the way tiles / split-K fold the batch rows changes (fp32
+    summation order of bf16 products), hence the tolerance; the same holds for running one sample alone."""
+    _, _, (_, mu) = ab_models
+    B, T = 4, 4545
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(B, 128, T, generator=g).cuda()
+    t = torch.full((B,), 500, dtype=torch.long).cuda()
+    emb = torch.randn(B, 128, 1024, generator=g).cuda()
+    mask = torch.ones(B, 128, dtype=torch.bool).cuda()
+    cc = torch.zeros(B, 129, T).cuda()
+    kw = dict(features=None, embedding_scale=0.8, batch_cfg=True, scale_cfg=True)
+    y = mu(x, t, embedding=emb, embedding_mask=mask, channels_list=[cc], **kw).clone()
+    perm = torch.tensor([2, 0, 3, 1]).cuda()
+    yp = mu(x[perm].contiguous(), t, embedding=emb[perm].contiguous(), embedding_mask=mask, channels_list=[cc], **kw).clone()
+    y1 = mu(x[1:2].contiguous(), t[:1], embedding=emb[1:2].contiguous(), embedding_mask=mask[:1], channels_list=[cc[:1]], **kw)
+    torch.cuda.synchronize()
+    assert torch.isfinite(y).all()
+    e_perm = ((yp - y[perm]).norm() / y.norm()).item()
+    e_one = ((y1 - y[1:2]).norm() / y[1:2].norm()).item()
+    assert e_perm < 1e-2 and e_one < 1e-2, (e_perm, e_one)
