@@ -806,7 +806,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
       }
     };
     if (SK == 1) {
-      const bool lean = !multi && !want_rows && p.epi_act == ACT_NONE && !A.out_f32;
+      const bool lean = !want_rows && p.epi_act == ACT_NONE && !A.out_f32;
       if (lean) {
         // The common case (conv + bias + optional residual, bf16 out, one batch row per tile) with a minimal body per
         // column: the fully unrolled general path is ~2 KB of code per column and would stream the whole loop from
@@ -817,6 +817,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
         bf16* outp = (bf16*)p.out + nch;
         int ooA[16], ooB[16];
         unsigned short rvA[16], rvB[16];
+        int nextb = (b_first + 1) * Lq - q0;  // first column of the next batch row (slot 1)
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int4 cm = colmeta[j];
@@ -834,15 +835,33 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
           }
           float v[16];
           tmem_ld16(trow + (uint32_t)c0, v);
+          if (nextb >= c0 + 16) {  // no batch-row boundary inside this chunk (CTA-uniform)
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float x = 0.f;
-            if (ooA[j] >= 0) {
-              x = (v[j] + bias) + __uint_as_float((uint32_t)rvA[j] << 16);
-              outp[(size_t)(uint32_t)ooA[j]] = __float2bfloat16_rn(x);
+            for (int j = 0; j < 16; ++j) {
+              float x = 0.f;
+              if (ooA[j] >= 0) {
+                x = (v[j] + bias) + __uint_as_float((uint32_t)rvA[j] << 16);
+                outp[(size_t)(uint32_t)ooA[j]] = __float2bfloat16_rn(x);
+              }
+              colS += x;
+              colQ = fmaf(x, x, colQ);
             }
-            colS += x;
-            colQ = fmaf(x, x, colQ);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (c0 + j == nextb) {  // the statistics of the next batch row start here
+                flush_stats();
+                ++sb;
+                nextb += Lq;
+              }
+              float x = 0.f;
+              if (ooA[j] >= 0) {
+                x = (v[j] + bias) + __uint_as_float((uint32_t)rvA[j] << 16);
+                outp[(size_t)(uint32_t)ooA[j]] = __float2bfloat16_rn(x);
+              }
+              colS += x;
+              colQ = fmaf(x, x, colQ);
+            }
           }
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -990,82 +1009,111 @@ UmmaPlan conv_umma_plan(const ConvParams& p, bool want_stats, int num_sms) {
   pl.steps1 = p.nseg > 1 ? (p.seg[1].Cin + 63) / 64 : 0;
   pl.m_tiles = p.Cout / 128;
   const long long nq = (long long)p.B * pl.Lq;
-  // N tile: aim at >= one CTA per SM, bounded by the panel size (strided convs keep `f` sub-panels)
+  // ---- tile / split-K selection.  The layer chain is latency bound, so the plan minimises the critical path of ONE
+  //      CTA instead of maximising the CTA count: K steps per CTA (each costs a load -> transform -> MMA round),
+  //      weight bytes a CTA must stream beyond what the ring prefetches under PDL, panel rows and epilogue columns.
+  //      Split-K (<= cluster size) is preferred over narrow N tiles: it divides both the K loop and the weight stream,
+  //      whereas every extra N tile re-streams the whole weight slice from L2.
   int nt_cap = 256 / f;
   if (nt_cap < 16) nt_cap = 16;
-  long long want = (nq * pl.m_tiles * p.nphase + num_sms - 1) / num_sms;
-  int NT = round_up((int)(want < 16 ? 16 : want), 16);
-  if (NT > nt_cap) NT = nt_cap;
-  if (NT > 128 && NT < 256) NT = round_up(NT, 32);
-  if ((long long)NT > round_up((int)nq, 16)) NT = round_up((int)nq, 16);
-  if (NT < 16) NT = 16;
-  // distinct batch rows per tile must fit the per-slot tables
-  auto slots = [&](int nt) {
-    const int s = (nt + pl.halo + pl.Lq - 1) / pl.Lq + 1;
-    return s < p.B ? s : p.B;
+  if ((long long)nt_cap > round_up((int)(nq < 16 ? 16 : nq), 16)) nt_cap = round_up((int)(nq < 16 ? 16 : nq), 16);
+  auto slots = [&](int nt) {  // distinct batch rows per tile must fit the per-slot tables
+    const int sl = (nt + pl.halo + pl.Lq - 1) / pl.Lq + 1;
+    return sl < p.B ? sl : p.B;
   };
-  while (NT > 16 && slots(NT) > kMaxSlots) NT -= 16;
-  if (slots(NT) > kMaxSlots) return pl;
   const int nsteps = pl.steps0 + pl.steps1;
   const bool need_coef = p.mode == PRO_AFFINE && (p.G > 0 || p.film != nullptr);
-  for (;; NT -= 16) {
-    pl.NT = NT;
-    pl.n_tiles = (int)((nq + NT - 1) / NT);
-    pl.R = NT + pl.halo;
-    pl.bsw = 1;
-    pl.PS = round_up(pl.R, 8);  // rows per sub-panel (128-byte rows, 128-byte swizzle, 1024-byte aligned)
-    pl.panel_bytes = f * pl.PS * 128;
-    if (pl.panel_bytes < NT * 128) pl.panel_bytes = round_up(NT * 128, 1024);
+  const int ntaps = S0.ntaps;
+  auto configure = [&](int NT, UmmaPlan& c) -> bool {
+    c = pl;
+    if (slots(NT) > kMaxSlots) return false;
+    c.NT = NT;
+    c.n_tiles = (int)((nq + NT - 1) / NT);
+    c.R = NT + c.halo;
+    c.bsw = 1;
+    c.PS = round_up(c.R, 8);  // rows per sub-panel (128-byte rows, 128-byte swizzle, 1024-byte aligned)
+    c.panel_bytes = f * c.PS * 128;
+    if (c.panel_bytes < NT * 128) c.panel_bytes = round_up(NT * 128, 1024);
     int tc = 32;
     while (tc < NT) tc <<= 1;
-    pl.tmem_cols = tc;
+    c.tmem_cols = tc;
+    const long long tiles = (long long)c.n_tiles * c.m_tiles * p.nphase;
+    if (tiles > 65535) return false;
     // split-K over a cluster: spread weight streaming over the GPU when the output tiles alone do not fill it
-    const long long tiles = (long long)pl.n_tiles * pl.m_tiles * p.nphase;
-    if (tiles > 65535) return pl;
     int sk = (int)(num_sms / tiles);
     if (sk < 1) sk = 1;
     if (sk > nsteps) sk = nsteps;
     if (sk > g_max_cluster) sk = g_max_cluster;
     // the per-slot coefficient table of a CTA's channel slice must stay small: split K further if needed
     const int nslot = slots(NT);
-    auto ch_cap_of = [&](int s) {
-      int ms = (nsteps + s - 1) / s;
-      if (ms > pl.steps0) ms = pl.steps0;
+    auto ch_cap_of = [&](int sp) {
+      int ms = (nsteps + sp - 1) / sp;
+      if (ms > c.steps0) ms = c.steps0;
       return ms * 64;
     };
     const int coef_budget = 24 * 1024;
     while (need_coef && nslot * ch_cap_of(sk) * 8 > coef_budget && sk < nsteps && sk < g_max_cluster) ++sk;
-    const bool coef_ok = !need_coef || nslot * ch_cap_of(sk) * 8 <= coef_budget;
-    pl.splitk = sk;
-    pl.ch_cap = ch_cap_of(sk);
-    pl.E_max = ((pl.Lq - 1) / NT + 2) * sk;
+    if (need_coef && nslot * ch_cap_of(sk) * 8 > coef_budget) return false;
+    c.splitk = sk;
+    c.ch_cap = ch_cap_of(sk);
+    c.E_max = ((c.Lq - 1) / NT + 2) * sk;
     // tables
-    const int rows0 = f * pl.R;
+    const int rows0 = f * c.R;
     int off = round_up(rows0 * 8, 16);
-    pl.off_rowmeta1 = off;
+    c.off_rowmeta1 = off;
     off += p.nseg > 1 ? NT * 8 : 0;
-    pl.off_colmeta = off;
+    c.off_colmeta = off;
     off += NT * 16;
-    pl.off_rowstat = off;
+    c.off_rowstat = off;
     off += p.mode == PRO_ROWNORM ? round_up(rows0 * 8, 16) : 0;
-    pl.off_gb = off;
-    pl.off_coef = off;
-    off += need_coef ? nslot * pl.ch_cap * 8 : 0;
+    c.off_gb = off;
+    c.off_coef = off;
+    off += need_coef ? nslot * c.ch_cap * 8 : 0;
     const int misc = kMiscFixed + off;
     // shared memory: two panels + as many 16 KB weight stages as fit in ~half an SM (two CTAs co-reside under PDL);
     // the epilogue scratch (+ the fp32 partial tile of the cluster reduction) aliases the ring
     const int budget = 110 * 1024;
-    int stages = (budget - 2 * pl.panel_bytes - misc) / kABytes;
+    int stages = (budget - 2 * c.panel_bytes - misc) / kABytes;
     const int scratch = kSredBytes + 4 * NT * 8 + (sk > 1 ? NT * 512 : 0);
     if (stages < 2) stages = 2;
     if (stages > 6) stages = 6;
-    pl.stages = stages;
-    pl.ring_bytes = stages * kABytes;
-    if (pl.ring_bytes < scratch) pl.ring_bytes = round_up(scratch, 1024);
-    pl.smem = (size_t)pl.ring_bytes + 2 * (size_t)pl.panel_bytes + misc + 1024;
-    if (coef_ok && pl.smem <= (size_t)(sk > 1 ? 113 : 227) * 1024) break;
-    if (NT <= 16) return pl;
+    c.stages = stages;
+    c.ring_bytes = stages * kABytes;
+    if (c.ring_bytes < scratch) c.ring_bytes = round_up(scratch, 1024);
+    c.smem = (size_t)c.ring_bytes + 2 * (size_t)c.panel_bytes + misc + 1024;
+    return c.smem <= (size_t)(sk > 1 ? 113 : 227) * 1024;
+  };
+  auto cost_us = [&](const UmmaPlan& c) {
+    const long long tiles = (long long)c.n_tiles * c.m_tiles * p.nphase;
+    const double waves = (double)((tiles * c.splitk + num_sms - 1) / num_sms);
+    const int steps = (nsteps + c.splitk - 1) / c.splitk;
+    const double rows = (double)(c.R * f);
+    const double wkb = (double)steps * ntaps * 16.0;
+    const double prefetch = c.stages * 16.0;
+    const double cols = c.splitk > 1 ? (double)((c.NT + c.splitk - 1) / c.splitk) : (double)c.NT;
+    double t = steps * (0.6 + 0.15 * rows / 16.0);      // K loop: fixed round trip + panel rows
+    t += (wkb > prefetch ? (wkb - prefetch) / 60.0 : 0.0);  // weight bytes beyond the PDL prefetch at ~60 GB/s per SM
+    t += 0.03 * cols + (c.splitk > 1 ? 0.6 : 0.0);      // epilogue columns, cluster exchange
+    t += 0.01 * (double)c.E_max;                        // statistics entries the consumer must reduce
+    return t * waves;
+  };
+  static const int cand[] = {16, 32, 48, 64, 96, 128, 192, 256};
+  bool found = false;
+  double best = 0.0;
+  UmmaPlan bestp = pl;
+  for (int NT : cand) {
+    if (NT > nt_cap) break;
+    UmmaPlan c;
+    if (!configure(NT, c)) continue;
+    const double t = cost_us(c);
+    if (!found || t < best - 1e-9) {
+      found = true;
+      best = t;
+      bestp = c;
+    }
   }
+  if (!found) return pl;
+  pl = bestp;
   pl.ok = 1;
   return pl;
 }
