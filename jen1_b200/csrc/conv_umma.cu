@@ -889,21 +889,72 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
       uint32_t part_remote[kMaxCluster];
 #pragma unroll
       for (int s = 0; s < kMaxCluster; ++s) part_remote[s] = s < SK ? map_cluster(mine, (uint32_t)s) : mine;
+      const bool lean = !want_rows && p.epi_act == ACT_NONE && !A.out_f32;
+      if (lean) {
+        // four columns per round: 64 DSMEM loads in flight, minimal per-column code
+        bf16* outp = (bf16*)p.out + nch;
+        const unsigned short* resp = reinterpret_cast<const unsigned short*>(p.res);
 #pragma unroll 1
-      for (int c = cb; c < ce; ++c) {
-        const int4 cm = colmeta[c];
-        const int jr = c - cb;
-        const unsigned short rraw = jr == 0 ? res_pre[0] : (jr == 1 ? res_pre[1] : (jr == 2 ? res_pre[2] : res_pre[3]));
-        float resv = __uint_as_float((uint32_t)rraw << 16);
-        if (jr >= 4) resv = (p.res && cm.x >= 0) ? ldf_cg((const bf16*)p.res + (size_t)(uint32_t)cm.y + nch) : 0.f;
-        const uint32_t off = (uint32_t)((c * 128 + cl) * 4);
-        float tv[kMaxCluster];
+        for (int c = cb; c < ce; c += 4) {
+          int oo[4], sl[4];
+          unsigned short rr[4];
+          float tv[4][kMaxCluster];
 #pragma unroll
-        for (int s = 0; s < kMaxCluster; ++s) tv[s] = ld_cluster_f32(part_remote[s] + off);
-        float acc = 0.f;
+          for (int j = 0; j < 4; ++j) {
+            oo[j] = -1;
+            sl[j] = sb;
+            rr[j] = 0;
+            if (c + j < ce) {
+              const int4 cm = colmeta[c + j];
+              oo[j] = cm.x;
+              sl[j] = cm.z;
+              if (c == cb) {
+                rr[j] = res_pre[j];
+              } else if (resp && cm.x >= 0) {
+                rr[j] = __ldcg(resp + (size_t)(uint32_t)cm.y + nch);
+              }
+              const uint32_t off = (uint32_t)(((c + j) * 128 + cl) * 4);
 #pragma unroll
-        for (int s = 0; s < kMaxCluster; ++s) acc += (s < SK) ? tv[s] : 0.f;
-        finish(acc, resv, cm.x, c, jr);
+              for (int s2 = 0; s2 < kMaxCluster; ++s2) tv[j][s2] = ld_cluster_f32(part_remote[s2] + off);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (c + j < ce) {
+              float acc = 0.f;
+#pragma unroll
+              for (int s2 = 0; s2 < kMaxCluster; ++s2) acc += (s2 < SK) ? tv[j][s2] : 0.f;  // rank order: deterministic
+              if (multi && sl[j] != sb) {
+                flush_stats();
+                sb = sl[j];
+              }
+              float x = 0.f;
+              if (oo[j] >= 0) {
+                x = (acc + bias) + __uint_as_float((uint32_t)rr[j] << 16);
+                outp[(size_t)(uint32_t)oo[j]] = __float2bfloat16_rn(x);
+              }
+              colS += x;
+              colQ = fmaf(x, x, colQ);
+            }
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int c = cb; c < ce; ++c) {
+          const int4 cm = colmeta[c];
+          const int jr = c - cb;
+          const unsigned short rraw = jr == 0 ? res_pre[0] : (jr == 1 ? res_pre[1] : (jr == 2 ? res_pre[2] : res_pre[3]));
+          float resv = __uint_as_float((uint32_t)rraw << 16);
+          if (jr >= 4) resv = (p.res && cm.x >= 0) ? ldf_cg((const bf16*)p.res + (size_t)(uint32_t)cm.y + nch) : 0.f;
+          const uint32_t off = (uint32_t)((c * 128 + cl) * 4);
+          float tv[kMaxCluster];
+#pragma unroll
+          for (int s = 0; s < kMaxCluster; ++s) tv[s] = ld_cluster_f32(part_remote[s] + off);
+          float acc = 0.f;
+#pragma unroll
+          for (int s = 0; s < kMaxCluster; ++s) acc += (s < SK) ? tv[s] : 0.f;
+          finish(acc, resv, cm.x, c, jr);
+        }
       }
     }
     flush_stats();
@@ -1093,7 +1144,7 @@ UmmaPlan conv_umma_plan(const ConvParams& p, bool want_stats, int num_sms) {
     const double cols = c.splitk > 1 ? (double)((c.NT + c.splitk - 1) / c.splitk) : (double)c.NT;
     double t = steps * (0.6 + 0.15 * rows / 16.0);      // K loop: fixed round trip + panel rows
     t += (wkb > prefetch ? (wkb - prefetch) / 60.0 : 0.0);  // weight bytes beyond the PDL prefetch at ~60 GB/s per SM
-    t += 0.03 * cols + (c.splitk > 1 ? 0.6 : 0.0);      // epilogue columns, cluster exchange
+    t += (c.splitk > 1 ? 0.12 * cols + 0.6 : 0.04 * cols);  // epilogue columns (DSMEM reduction vs TMEM), cluster exchange
     t += 0.01 * (double)c.E_max;                        // statistics entries the consumer must reduce
     return t * waves;
   };

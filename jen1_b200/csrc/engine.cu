@@ -1219,10 +1219,6 @@ int Engine::sample_begin(const float* coef_host, int S, const float* cc, int B, 
   const size_t need = workspace_bytes(B, T);
   if (need == 0) return fail("sample_begin: unsupported shape: " + err_);
   if (!ensure_arena(need)) return 1;
-  if (smp_.exec) {
-    cudaGraphExecDestroy(smp_.exec);
-    smp_.exec = nullptr;
-  }
   if ((size_t)S * 8 * 4 > smp_.coef_cap) {
     cudaDeviceSynchronize();
     if (smp_.coef) cudaFree(smp_.coef);
@@ -1231,6 +1227,19 @@ int Engine::sample_begin(const float* coef_host, int S, const float* cc, int B, 
     smp_.coef_cap = (size_t)S * 8 * 4;
   }
   if (!ck(cudaMemcpyAsync(smp_.coef, coef_host, (size_t)S * 8 * 4, cudaMemcpyHostToDevice, st), "memcpy coef")) return 1;
+  // A captured step graph stays valid across sample() calls as long as everything baked into it is unchanged:
+  // shapes and mode flags (they select kernels / plans) and the buffers the nodes point at (arena, tables, caches
+  // -- their owners destroy the graph when they reallocate).  Re-capturing 263 nodes costs ~10 ms per call.
+  Sampler::Sig sig;
+  memset(&sig, 0, sizeof(sig));
+  sig.B = B; sig.T = T; sig.causal = causal; sig.scale_cfg = scale_cfg; sig.objective = objective; sig.use_graph = use_graph;
+  sig.emb_scale = emb_scale; sig.phi = phi; sig.ctx_B = ctx_B_; sig.ctx_S = ctx_S_; sig.ctx_has_mask = ctx_has_mask_ ? 1 : 0;
+  sig.arena = arena_; sig.coef = smp_.coef; sig.tt_film = tt_film_; sig.kv_cond = kv_cond_;
+  if (smp_.exec && memcmp(&sig, &smp_.sig, sizeof(sig)) != 0) {
+    cudaGraphExecDestroy(smp_.exec);
+    smp_.exec = nullptr;
+  }
+  smp_.sig = sig;
   smp_.S = S;
   smp_.B = B;
   smp_.T = T;
@@ -1256,8 +1265,10 @@ int Engine::sample_begin(const float* coef_host, int S, const float* cc, int B, 
   if (!ck(e, "pack(cc)")) return 1;
   smp_.arena_base = arena_off_;
   smp_.active = true;
-  smp_.g_x = nullptr;
-  smp_.g_noise = nullptr;
+  if (!smp_.exec) {
+    smp_.g_x = nullptr;
+    smp_.g_noise = nullptr;
+  }
   return 0;
 }
 

@@ -235,6 +235,11 @@ class Engine {
     float* g_x = nullptr;
     const float* g_noise = nullptr;
     int64_t launches_per_step = 0, umma_per_step = 0, umma_attn_per_step = 0;
+    struct Sig {  // everything a captured step graph depends on
+      int B, T, causal, scale_cfg, objective, use_graph, ctx_B, ctx_S, ctx_has_mask;
+      float emb_scale, phi;
+      const void *arena, *coef, *tt_film, *kv_cond;
+    } sig = {};
   } smp_;
 };
 

@@ -232,8 +232,16 @@ class GaussianDiffusion:
             audio = self._randn(tuple(shape), device)
             if init_data is not None:
                 audio = audio + init_data.to(device)
-            x = audio.to(torch.float32).contiguous()
-            noise = torch.empty_like(x)
+            # persistent state / noise buffers per shape: the engine's captured step graph points at them, so a
+            # second sample() call of the same shape replays the graph instead of re-capturing it
+            bufs = model.__dict__.setdefault("_sampler_buffers", {})
+            key = (tuple(shape), str(device))
+            if key not in bufs:
+                bufs.clear()
+                bufs[key] = (torch.empty(tuple(shape), device=device, dtype=torch.float32),
+                             torch.empty(tuple(shape), device=device, dtype=torch.float32))
+            x, noise = bufs[key]
+            x.copy_(audio)
             audios = [x.clone()] if return_all_timesteps else None
             for i, (time, time_next) in enumerate(pairs):
                 drop = None
@@ -248,7 +256,7 @@ class GaussianDiffusion:
                     else:
                         noise.normal_()
                 eng.sample_step(i, x, noise, drop)
-            out = x if not return_all_timesteps else torch.stack(audios, dim=1)
+            out = x.clone() if not return_all_timesteps else torch.stack(audios, dim=1)
         cur.wait_stream(side)
         out.record_stream(cur)
         return out
