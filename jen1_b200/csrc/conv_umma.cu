@@ -177,8 +177,15 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
 }
-// SiLU whose result is rounded to bf16 right away: the fast exp / divide (rel. error ~1e-6) are invisible
-__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+// SiLU whose result is rounded to bf16 right away: x*sigmoid(x) = h + h*tanh(h), h = x/2, with the single-instruction
+// hardware tanh (MUFU.TANH, rel. error ~2^-11 -- below bf16's 2^-9 rounding step); 3 instructions instead of ~7 and one
+// MUFU op instead of two on the producers' critical path
+__device__ __forceinline__ float silu_fast(float x) {
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
 
 inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
