@@ -813,7 +813,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
       }
     };
     if (SK == 1) {
-      const bool lean = !want_rows && p.epi_act == ACT_NONE && !A.out_f32;
+      const bool lean = !want_rows && p.epi_act == ACT_NONE;
       if (lean) {
         // The common case (conv + bias + optional residual, bf16 out, one batch row per tile) with a minimal body per
         // column: the fully unrolled general path is ~2 KB of code per column and would stream the whole loop from
@@ -822,6 +822,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
         // used, so that issuing the loads never waits on them).
         const unsigned short* resp = reinterpret_cast<const unsigned short*>(p.res);
         bf16* outp = (bf16*)p.out + nch;
+        float* outf = (float*)p.out + nch;
         int ooA[16], ooB[16];
         unsigned short rvA[16], rvB[16];
         int nextb = (b_first + 1) * Lq - q0;  // first column of the next batch row (slot 1)
@@ -848,7 +849,11 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
               float x = 0.f;
               if (ooA[j] >= 0) {
                 x = (v[j] + bias) + __uint_as_float((uint32_t)rvA[j] << 16);
-                outp[(size_t)(uint32_t)ooA[j]] = __float2bfloat16_rn(x);
+                if (A.out_f32) {
+                  outf[(size_t)(uint32_t)ooA[j]] = x;
+                } else {
+                  outp[(size_t)(uint32_t)ooA[j]] = __float2bfloat16_rn(x);
+                }
               }
               colS += x;
               colQ = fmaf(x, x, colQ);
@@ -864,7 +869,11 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
               float x = 0.f;
               if (ooA[j] >= 0) {
                 x = (v[j] + bias) + __uint_as_float((uint32_t)rvA[j] << 16);
-                outp[(size_t)(uint32_t)ooA[j]] = __float2bfloat16_rn(x);
+                if (A.out_f32) {
+                  outf[(size_t)(uint32_t)ooA[j]] = x;
+                } else {
+                  outp[(size_t)(uint32_t)ooA[j]] = __float2bfloat16_rn(x);
+                }
               }
               colS += x;
               colQ = fmaf(x, x, colQ);
@@ -896,10 +905,11 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
       uint32_t part_remote[kMaxCluster];
 #pragma unroll
       for (int s = 0; s < kMaxCluster; ++s) part_remote[s] = s < SK ? map_cluster(mine, (uint32_t)s) : mine;
-      const bool lean = !want_rows && p.epi_act == ACT_NONE && !A.out_f32;
+      const bool lean = !want_rows && p.epi_act == ACT_NONE;
       if (lean) {
         // four columns per round: 64 DSMEM loads in flight, minimal per-column code
         bf16* outp = (bf16*)p.out + nch;
+        float* outf = (float*)p.out + nch;
         const unsigned short* resp = reinterpret_cast<const unsigned short*>(p.res);
 #pragma unroll 1
         for (int c = cb; c < ce; c += 4) {
@@ -938,7 +948,11 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
               float x = 0.f;
               if (oo[j] >= 0) {
                 x = (acc + bias) + __uint_as_float((uint32_t)rr[j] << 16);
-                outp[(size_t)(uint32_t)oo[j]] = __float2bfloat16_rn(x);
+                if (A.out_f32) {
+                  outf[(size_t)(uint32_t)oo[j]] = x;
+                } else {
+                  outp[(size_t)(uint32_t)oo[j]] = __float2bfloat16_rn(x);
+                }
               }
               colS += x;
               colQ = fmaf(x, x, colQ);
@@ -1143,7 +1157,25 @@ UmmaPlan conv_umma_plan(const ConvParams& p, bool want_stats, int num_sms) {
   };
   auto cost_us = [&](const UmmaPlan& c) {
     const long long tiles = (long long)c.n_tiles * c.m_tiles * p.nphase;
-    const double waves = (double)((tiles * c.splitk + num_sms - 1) / num_sms);
+    // Two CTAs fit an SM (<= 113 KB each).  The panel / epilogue phases are bound by per-warp instruction latency
+    // (one warp per scheduler), so two RUNNING CTAs per SM nearly double the throughput of those phases; the price is
+    // that the next layer's CTAs can no longer sit next to this layer's (exposed prologue, no weight prefetch).
+    static int oversub = -1;
+    if (oversub < 0) {
+      const char* e = getenv("JEN1_OVERSUB");
+      oversub = e ? atoi(e) : 1;
+    }
+    static double o_mul = -1.0, o_add = -1.0;
+    if (o_mul < 0.0) {
+      const char* e1 = getenv("JEN1_OVERSUB_MUL");
+      const char* e2 = getenv("JEN1_OVERSUB_ADD");
+      o_mul = e1 ? atof(e1) : 0.85;
+      o_add = e2 ? atof(e2) : 0.0;
+    }
+    const long long ctas = tiles * c.splitk;
+    const double conc = (oversub && c.smem <= (size_t)113 * 1024) ? 2.0 : 1.0;
+    const double waves = (double)((ctas + (long long)(conc * num_sms) - 1) / (long long)(conc * num_sms));
+    const double over_mul = (conc > 1.0 && ctas > num_sms) ? o_mul : 1.0, over_add = (conc > 1.0 && ctas > num_sms) ? o_add : 0.0;
     const int steps = (nsteps + c.splitk - 1) / c.splitk;
     const double rows = (double)(c.R * f);
     const double wkb = (double)steps * ntaps * 16.0;
@@ -1153,7 +1185,7 @@ UmmaPlan conv_umma_plan(const ConvParams& p, bool want_stats, int num_sms) {
     t += (wkb > prefetch ? (wkb - prefetch) / 60.0 : 0.0);  // weight bytes beyond the PDL prefetch at ~60 GB/s per SM
     t += (c.splitk > 1 ? 0.12 * cols + 0.6 : 0.04 * cols);  // epilogue columns (DSMEM reduction vs TMEM), cluster exchange
     t += 0.01 * (double)c.E_max;                        // statistics entries the consumer must reduce
-    return t * waves;
+    return t * waves * over_mul + over_add;
   };
   static const int cand[] = {16, 32, 48, 64, 96, 128, 192, 256};
   bool found = false;
