@@ -340,7 +340,7 @@ def run_ours(args, wl):
         sb = step_bytes(desc, B, T, cfg=True, elem_bytes=2 if args.dtype == "bf16" else 4)
         alg = sb["total_bytes"]
         ach = alg / (ms_per_step / 1e3) / 1e9
-        prof = _profile_facts(args.workload)
+        prof = _profile_facts(args.workload) if args.batch in (0, WORKLOADS[args.workload]["B"]) else {}
         roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
                 "traffic": prof.get("dram_bytes_per_step"),
                 "kernel": "one sampler step = one CUDA-graph launch of %d kernels; conv_umma_kernel (tcgen05 tap-GEMM) is "
@@ -374,9 +374,15 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs under ncu)")
+    ap.add_argument("--batch", type=int, default=0, help="exploratory: override the per-GPU batch of the workload "
+                    "(NOT a BASELINE config; the line says so in config.workload)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
-    wl = WORKLOADS[args.workload]
+    wl = dict(WORKLOADS[args.workload])
+    if args.batch > 0 and args.batch != wl["B"]:
+        wl["name"] = wl["name"].replace("batch %d per GPU" % wl["B"], "batch %d per GPU (exploratory override of %s)" % (args.batch, args.workload))
+        wl["name"] = wl["name"].replace("(%d UNet rows)" % (2 * wl["B"]), "(%d UNet rows)" % (2 * args.batch))
+        wl["B"] = args.batch
     if args.impl == "reference":
         run_reference(args, wl)
     else:

@@ -151,7 +151,9 @@ __global__ void __launch_bounds__(kAtThreads, 1) attn_umma_kernel(const __grid_c
   // ---- stage Q, K, V: items = 16-byte chunks; [0, nq) Q chunks, then K chunks, then V chunks.  Cross-attention
   //      keys / values come from per-step constant caches, so they are staged BEFORE the PDL wait (while the
   //      producer of Q is still running); only what the previous kernel wrote is loaded after it.
-  const int nq = 128 << g.cpr_shift;
+  // query rows beyond N are never stored: their tile rows are left as they are (an MMA row only feeds its own
+  // output row), so only the real rows are staged
+  const int nq = min(128, p.N - i0) << g.cpr_shift;
   const int nk = g.KR << g.cpr_shift;
   const int total = nq + 2 * nk;
   auto stage = [&](int lo, int hi) {

@@ -49,7 +49,7 @@ constexpr int kSredBytes = kMaxSlots * 128 * 2 * 4;
 constexpr int kMiscBar = 256;
 constexpr int kMiscStat = 2 * kMaxSlots * 32 * 4;            // gmean, grstd
 constexpr int kMiscFine = kMaxSlots * 2 * 32 * 2 * 4;        // fine-group sums
-constexpr int kMiscFixed = kMiscBar + kMiscStat + kMiscFine + kMaxSlots * 4 + 32 * 8 + 64 * 8;  // + scrow + taps + group ranges
+constexpr int kMiscFixed = kMiscBar + kMiscStat + kMiscFine + 32 * 8 + 64 * 8;  // + tap table + group ranges
 
 int g_max_cluster = 8;
 
@@ -120,11 +120,6 @@ __device__ __forceinline__ void bar_sync_producers() { asm volatile("bar.sync 1,
 // ld.shared::cluster of them goes through) followed by the relaxed barrier is sufficient.
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("fence.acq_rel.cta;\n\tbarrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
-}
-__device__ __forceinline__ float2 ld_cluster_f32x2(uint32_t addr) {
-  float2 v;
-  asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr) : "memory");
-  return v;
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -233,8 +228,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
   float* gmean = reinterpret_cast<float*>(misc + kMiscBar);         // [kMaxSlots][32]
   float* grstd = gmean + kMaxSlots * 32;                            // [kMaxSlots][32]
   float* fine = grstd + kMaxSlots * 32;                             // [kMaxSlots][2 sources][32 fine groups][2]
-  int* scrow = reinterpret_cast<int*>(fine + kMaxSlots * 2 * 32 * 2);  // [kMaxSlots] conditioning-table row per slot
-  int2* tapg = reinterpret_cast<int2*>(scrow + kMaxSlots);          // [32] (panel row offset, unused) per tap
+  int2* tapg = reinterpret_cast<int2*>(fine + kMaxSlots * 2 * 32 * 2);  // [32] (panel row offset, unused) per tap
   int2* grange = tapg + 32;                                         // [32 groups][2 sources] fine-group range
   uint8_t* tabs = misc + kMiscFixed;
   int2* rowmeta = reinterpret_cast<int2*>(tabs);                           // [rows0]: (input row | -1, b | panel row << 8)
@@ -1102,7 +1096,6 @@ UmmaPlan conv_umma_plan(const ConvParams& p, bool want_stats, int num_sms) {
     c.NT = NT;
     c.n_tiles = (int)((nq + NT - 1) / NT);
     c.R = NT + c.halo;
-    c.bsw = 1;
     c.PS = round_up(c.R, 8);  // rows per sub-panel (128-byte rows, 128-byte swizzle, 1024-byte aligned)
     c.panel_bytes = f * c.PS * 128;
     if (c.panel_bytes < NT * 128) c.panel_bytes = round_up(NT * 128, 1024);
@@ -1138,7 +1131,6 @@ UmmaPlan conv_umma_plan(const ConvParams& p, bool want_stats, int num_sms) {
     off += NT * 16;
     c.off_rowstat = off;
     off += p.mode == PRO_ROWNORM ? round_up(rows0 * 8, 16) : 0;
-    c.off_gb = off;
     c.off_coef = off;
     off += need_coef ? nslot * c.ch_cap * 8 : 0;
     const int misc = kMiscFixed + off;

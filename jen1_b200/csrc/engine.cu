@@ -178,17 +178,6 @@ DNorm Engine::pack_norm(const std::string& prefix, int pad_to) {
   return n;
 }
 
-namespace {
-struct FilmAcc {
-  std::vector<float> w, b;  // concatenated [sum 2C][Fm], [sum 2C]
-};
-struct KvcAcc {
-  std::vector<float> w, b;  // concatenated folded to_kv [sum 2C][E], [sum 2C]
-};
-FilmAcc* g_film = nullptr;  // set during finalize (single-threaded per handle)
-KvcAcc* g_kvc = nullptr;
-}  // namespace
-
 DRes Engine::pack_res(const std::string& p, int cin, int cout, int cin_pad) {
   DRes r;
   r.cout = cout;
@@ -200,9 +189,9 @@ DRes Engine::pack_res(const std::string& p, int cin, int cout, int cin_pad) {
   r.gn2 = pack_norm(p + ".block2.groupnorm");
   const HostTensor& fw = ht(p + ".to_scale_shift.to_scale_shift.1.weight");
   const HostTensor& fb = ht(p + ".to_scale_shift.to_scale_shift.1.bias");
-  r.film_off = (int64_t)g_film->b.size();
-  g_film->w.insert(g_film->w.end(), fw.data.begin(), fw.data.end());
-  g_film->b.insert(g_film->b.end(), fb.data.begin(), fb.data.end());
+  r.film_off = (int64_t)film_acc_b_.size();
+  film_acc_w_.insert(film_acc_w_.end(), fw.data.begin(), fw.data.end());
+  film_acc_b_.insert(film_acc_b_.end(), fb.data.begin(), fb.data.end());
   r.has_out = host_.count(p + ".to_out.conv.weight") > 0;
   if (r.has_out != (cin != cout)) throw EngineError("to_out presence mismatch at " + p);
   if (r.has_out) {
@@ -252,9 +241,9 @@ DAttn Engine::pack_attention(const std::string& p, int C, bool cross) {
     a.qkv = pack_linear_raw(w, &b, 3 * C, C, false);
   } else {
     a.qkv = pack_linear_raw(q2, &qb, C, C, false);
-    a.kvc_off = (int64_t)g_kvc->b.size();
-    g_kvc->w.insert(g_kvc->w.end(), kv2.begin(), kv2.end());
-    g_kvc->b.insert(g_kvc->b.end(), kvb.begin(), kvb.end());
+    a.kvc_off = (int64_t)kvc_acc_b_.size();
+    kvc_acc_w_.insert(kvc_acc_w_.end(), kv2.begin(), kv2.end());
+    kvc_acc_b_.insert(kvc_acc_b_.end(), kvb.begin(), kvb.end());
   }
   a.out = pack_linear_raw(ht(p + ".attention.to_out.weight").data, &ht(p + ".attention.to_out.bias").data, C, C, false);
   return a;
@@ -282,10 +271,10 @@ int Engine::finalize() {
   ok_ = true;
   if (finalized_) return fail("finalize called twice");
   if (cudaSetDevice(device_) != cudaSuccess) return fail("cudaSetDevice failed (no CUDA device? there is no CPU fallback)");
-  FilmAcc film;
-  KvcAcc kvc;
-  g_film = &film;
-  g_kvc = &kvc;
+  film_acc_w_.clear();
+  film_acc_b_.clear();
+  kvc_acc_w_.clear();
+  kvc_acc_b_.clear();
   {
     const char* impl = getenv("JEN1_CONV_IMPL");  // "generic" forces the fp32-FMA kernel everywhere (A/B testing)
     const char* pdl = getenv("JEN1_PDL");
@@ -357,11 +346,11 @@ int Engine::finalize() {
     to_out_ = pack_res("to_out.block", lc(0), d_.out_channels);
 
     // FiLM: all MappingToScaleShift linears (reference blocks.py:148-165) as one [Fm -> sum 2C] fp32 GEMM
-    film_total_ = (int64_t)film.b.size();
-    film_lin_ = pack_linear_raw(film.w, &film.b, (int)film_total_, Fm_, true, false);
+    film_total_ = (int64_t)film_acc_b_.size();
+    film_lin_ = pack_linear_raw(film_acc_w_, &film_acc_b_, (int)film_total_, Fm_, true, false);
     // cross-attention K/V projections of the context, all layers as one [E -> sum 2C] GEMM
-    kvc_total_ = (int64_t)kvc.b.size();
-    if (kvc_total_ > 0) kvc_lin_ = pack_linear_raw(kvc.w, &kvc.b, (int)kvc_total_, E_, false, false);
+    kvc_total_ = (int64_t)kvc_acc_b_.size();
+    if (kvc_total_ > 0) kvc_lin_ = pack_linear_raw(kvc_acc_w_, &kvc_acc_b_, (int)kvc_total_, E_, false, false);
 
     // control block + weight-only cache: K/V of the learned null embedding (reference utils/module.py:20-33)
     if (cudaMalloc(&d_ctl_, sizeof(CtlBlock)) != cudaSuccess) throw EngineError("cudaMalloc ctl");
@@ -393,12 +382,12 @@ int Engine::finalize() {
       if (cudaDeviceSynchronize() != cudaSuccess) throw EngineError("kernel failure while building the fixed-embedding K/V cache");
     }
   } catch (const std::exception& e) {
-    g_film = nullptr;
-    g_kvc = nullptr;
     return fail(e.what());
   }
-  g_film = nullptr;
-  g_kvc = nullptr;
+  film_acc_w_ = std::vector<float>();
+  film_acc_b_ = std::vector<float>();
+  kvc_acc_w_ = std::vector<float>();
+  kvc_acc_b_ = std::vector<float>();
   host_.clear();
   finalized_ = true;
   return 0;

@@ -168,6 +168,8 @@ class Engine {
   std::string err_;
   bool finalized_ = false;
   std::map<std::string, HostTensor> host_;
+  // finalize() scratch: all MappingToScaleShift linears / all cross-attention to_kv, concatenated
+  std::vector<float> film_acc_w_, film_acc_b_, kvc_acc_w_, kvc_acc_b_;
   std::vector<void*> wallocs_;
   int64_t weight_total_bytes_ = 0, step_weight_bytes_ = 0;
   int64_t launches_ = 0;

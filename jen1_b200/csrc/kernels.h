@@ -30,11 +30,10 @@ struct UmmaPlan {
   int R, PS, panel_bytes; // panel rows, rows per sub-panel, bytes of one panel (all sub-panels)
   int steps0, steps1;     // 64-channel K blocks of segment 0 / 1
   int stages, tmem_cols;
-  int bsw;                // activation-panel layout: 1 = 128-byte swizzle
   int E_max;              // GroupNorm partial entries per batch row (per phase) this launch writes (N tiles x splitk)
   int ring_bytes;         // weight ring (also the epilogue scratch / partial tile)
   int ch_cap;             // seg-0 input channels one CTA may own (coefficient-table stride)
-  int off_rowmeta1, off_colmeta, off_rowstat, off_gb, off_coef;  // shared-memory table offsets
+  int off_rowmeta1, off_colmeta, off_rowstat, off_coef;  // shared-memory table offsets
   size_t smem;
 };
 UmmaPlan conv_umma_plan(const ConvParams& p, bool want_stats, int num_sms);
