@@ -144,3 +144,24 @@ def test_ddim_trajectory_matches_oracle(tiny_models):
         got = d.sample(models["fp32"], (B, desc.in_channels, T), cond_d, return_all_timesteps=True).cpu()
         assert got.shape == ref.shape
         assert rel_l2(got, ref) < 2e-3, "graph=%s rel-L2 %.3e" % (graph, rel_l2(got, ref))
+
+
+@pytest.mark.parametrize("objective", ["x0", "v"])
+def test_ddim_other_objectives_match_oracle(tiny_models, objective):
+    """The fused sampler kernel's x0 / v conversions (reference gdm.py:95-105, 132-141) against the oracle."""
+    from jen1_b200.diffusion import create_gaussian_diffusion
+    from oracle.gdm_oracle import OracleDiffusion
+    from oracle.unet_oracle import OracleUNet
+    desc, sd, models = tiny_models
+    B, T, S = 2, 33, 20
+    x, t, emb, mask, cc = make_inputs(desc, B, T, 23, 2)
+    cond = dict(cross_attn_cond=emb, cross_attn_masks=mask, global_cond=None, input_concat_cond=cc)
+    torch.manual_seed(17)
+    ref = OracleDiffusion(sampling_timesteps=S, objective=objective).sample(OracleUNet(desc, sd), (B, desc.in_channels, T), cond)
+    cond_d = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in cond.items()}
+    d = create_gaussian_diffusion(steps=1000, noise_schedule="linear", objective=objective, device=DEV,
+                                  cfg_dropout_proba=0.2, embedding_scale=0.8, batch_cfg=True, scale_cfg=True,
+                                  sampling_steps=S, rng_device="cpu")
+    torch.manual_seed(17)
+    got = d.sample(models["fp32"], (B, desc.in_channels, T), cond_d).cpu()
+    assert rel_l2(got, ref) < 2e-3, rel_l2(got, ref)

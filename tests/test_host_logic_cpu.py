@@ -1,0 +1,94 @@
+"""Host-side logic of the PRODUCT package against the reference goldens, on CPU (no engine involved):
+schedule tables and DDIM index arithmetic bit-exact, per-step DDIM scalars, q_sample / training loss, and the generic
+sampling loop (`GaussianDiffusion.sample` driving an arbitrary callable -- here the oracle denoiser) against the
+reference trajectories."""
+import os
+
+import torch
+
+from jen1_b200.config import UNetDesc, latent_frames, tiny_desc
+from jen1_b200.diffusion import create_gaussian_diffusion, extract, get_beta_schedule
+from jen1_b200.weights import random_state_dict
+from oracle.make_golden import make_inputs
+from oracle.unet_oracle import OracleUNet
+
+
+def _dif(S=100, objective="noise", **kw):
+    return create_gaussian_diffusion(steps=1000, noise_schedule="linear", objective=objective, device="cpu",
+                                     cfg_dropout_proba=0.2, embedding_scale=0.8, batch_cfg=True, scale_cfg=True,
+                                     sampling_steps=S, **kw)
+
+
+def test_product_schedule_tables_bit_exact(golden_dir):
+    fx = torch.load(os.path.join(golden_dir, "gdm.pt"))
+    d = _dif(100)
+    for k, ref in fx["tables"].items():
+        assert torch.equal(getattr(d, k), ref), k
+    assert torch.equal(get_beta_schedule("cosine", 1000)[0].to(torch.float32), fx["betas_cosine"])
+    for S, pairs in fx["pairs"].items():
+        assert _dif(int(S)).time_pairs() == [tuple(p) for p in pairs]
+
+
+def test_ddim_coefficients_follow_reference_formulas():
+    d = _dif(100)
+    coef = d.ddim_coefficients()
+    pairs = d.time_pairs()
+    assert coef.shape == (100, 8) and pairs[0][0] == 999 and pairs[-1] == (9, -1)
+    ac = d.alphas_cumprod
+    for i in (0, 1, 50, 98):
+        t, tn = pairs[i]
+        a, an = ac[t], ac[tn]
+        sigma = 1.0 * ((1 - a / an) * (1 - an) / (1 - a)).sqrt()  # reference gdm.py:214
+        c = (1 - an - sigma ** 2).sqrt()
+        assert torch.equal(coef[i, 0], d.sqrt_recip_alphas_cumprod[t]) and torch.equal(coef[i, 1], d.sqrt_recipm1_alphas_cumprod[t])
+        assert torch.equal(coef[i, 4], an.sqrt()) and torch.equal(coef[i, 5], c) and torch.equal(coef[i, 6], sigma)
+        assert coef[i, 7] == 0
+    assert coef[99, 7] == 1 and torch.all(coef[99, 4:7] == 0)  # last step returns x0 (gdm.py:208-210)
+
+
+def test_extract_gathers_per_sample():
+    a = torch.arange(10.0)
+    out = extract(a, torch.tensor([3, 7]), (2, 4, 5))
+    assert out.shape == (2, 1, 1) and out.flatten().tolist() == [3.0, 7.0]
+
+
+def test_product_q_sample_and_loss_match_reference(golden_dir):
+    fx = torch.load(os.path.join(golden_dir, "gdm.pt"))
+    desc = tiny_desc()
+    model = OracleUNet(desc, random_state_dict(desc, 7))
+    d = _dif(100)
+    x, t, emb, mask, cc = make_inputs(desc, 3, 50, 31, 0)
+    assert torch.equal(d.q_sample(x, t, fx["q_sample"]["noise"]), fx["q_sample"]["x_t"])
+    cond = dict(cross_attn_cond=emb, cross_attn_masks=mask, global_cond=None, input_concat_cond=cc)
+    torch.manual_seed(fx["train_loss"]["rng_seed"])
+    loss = float(d.training_loosses(model, x, t, cond))
+    assert abs(loss - fx["train_loss"]["loss"]) < 1e-5
+
+
+def test_product_generic_loop_matches_reference_trajectories(golden_dir):
+    fx = torch.load(os.path.join(golden_dir, "gdm.pt"))
+    desc = tiny_desc()
+    model = OracleUNet(desc, random_state_dict(desc, 7))
+    tag, rec = next(iter(fx["traj"].items()))
+    x, t, emb, mask, cc = make_inputs(desc, rec["B"], rec["T"], rec["seed"], 4)
+    cond = dict(cross_attn_cond=emb, cross_attn_masks=mask, global_cond=None, input_concat_cond=cc)
+    init = 0.5 * x if rec["use_init"] else None
+    torch.manual_seed(rec["seed"])
+    y = _dif(rec["S"]).sample(model, (rec["B"], desc.in_channels, rec["T"]), cond, return_all_timesteps=True,
+                              causal=rec["causal"], init_data=init)
+    assert y.shape == rec["all_steps"].shape
+    assert (y - rec["all_steps"]).abs().max().item() < 5e-4, tag
+    for obj in ("x0", "v"):
+        xx, tt, emb, mask, cc = make_inputs(desc, 1, 20, 41, 0)
+        cond = dict(cross_attn_cond=emb, cross_attn_masks=mask, global_cond=None, input_concat_cond=cc)
+        torch.manual_seed(5)
+        y = _dif(25, objective=obj).sample(model, (1, desc.in_channels, 20), cond)
+        assert (y - fx["traj_" + obj]).abs().max().item() < 5e-4, obj
+
+
+def test_latent_frame_algebra_and_level_lengths():
+    assert latent_frames(10) == 1515 and latent_frames(30) == 4545
+    d = UNetDesc()
+    assert d.level_lengths(4545) == [4545, 4545, 1137, 285, 72, 36, 18, 9, 5, 3]
+    assert d.level_lengths(1515) == [1515, 1515, 379, 95, 24, 12, 6, 3, 2, 1]
+    assert d.num_params() == 296543106
