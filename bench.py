@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the JEN-1 denoiser hot path (BASELINE.json metric: denoiser latent-frames/sec/step).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload config2|config3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload config2|config3|config5]
 
 One "step" = one DDIM sampler step of the hot path over one batch: pack x -> UNetCFG1d on the doubled CFG batch
 -> CFG combine + std rescale -> x0/eps conversion + clamp -> DDIM update (reference gdm.py:202-222), plus the
@@ -41,6 +41,9 @@ WORKLOADS = {
     "config2": dict(B=1, seconds=10, T=1515, name="100-step DDIM, 10 s (T=1515) latent, batch 1 per GPU, CFG 0.8 (2 UNet rows)"),
     # BASELINE.json configs[2]: 30 s, batch 32 over 8 GPUs = 4 samples per GPU
     "config3": dict(B=4, seconds=30, T=4545, name="100-step DDIM, 30 s (T=4545) latent, batch 4 per GPU, CFG 0.8 (8 UNet rows)"),
+    # BASELINE.json configs[4]: continuation (masked latent, causal convs + causal self-attention), 30 s, batch 16 over 4 GPUs
+    "config5": dict(B=4, seconds=30, T=4545, causal=True,
+                    name="100-step DDIM continuation (causal), 30 s (T=4545) masked latent, batch 4 per GPU, CFG 0.8 (8 UNet rows)"),
 }
 METRIC = "denoiser latent-frames/sec/step"
 UNIT = "latent-frames/s"
@@ -118,12 +121,17 @@ def _profile_facts(workload):
     return {}
 
 
-def _make_problem(desc, B, T, seed):
+def _make_problem(desc, B, T, seed, continuation=False):
     import torch
     g = torch.Generator().manual_seed(seed)
     emb = torch.randn(B, desc.context_embedding_max_length, desc.context_embedding_features, generator=g)
     mask = torch.ones(B, desc.context_embedding_max_length, dtype=torch.bool)
     cc = torch.zeros(B, desc.context_channels[0], T)  # text-guided: zero masked latent + zero mask
+    if continuation:  # keep the first half of a stand-in latent, generate the rest
+        lat = torch.randn(B, desc.in_channels, T, generator=g) * 0.5
+        keep = torch.zeros(B, 1, T)
+        keep[:, :, : T // 2] = 1.0
+        cc = torch.cat([lat * keep, keep], dim=1)
     return emb, mask, cc
 
 
@@ -145,7 +153,8 @@ def run_reference(args, wl):
     sd = random_state_dict(desc, 0)
     model = OracleUNet(desc, sd)
     dif = OracleDiffusion(sampling_timesteps=100)
-    emb, mask, cc = _make_problem(desc, B, T, 1)
+    causal = bool(wl.get("causal", False))
+    emb, mask, cc = _make_problem(desc, B, T, 1, causal)
     cond = dict(cross_attn_cond=emb, cross_attn_masks=mask, global_cond=None, input_concat_cond=cc)
     pairs = dif.time_pairs()
     torch.manual_seed(0)
@@ -154,7 +163,7 @@ def run_reference(args, wl):
     def step(i, x):
         time_, time_next = pairs[i % (len(pairs) - 1)]
         tc = torch.full((B,), time_, dtype=torch.long)
-        eps, x0 = dif.model_predictions(x, tc, model, cond, clip=True)
+        eps, x0 = dif.model_predictions(x, tc, model, cond, clip=True, causal=causal)
         a, an = dif.alphas_cumprod[time_], dif.alphas_cumprod[time_next]
         sigma = dif.eta * ((1 - a / an) * (1 - an) / (1 - a)).sqrt()
         c = (1 - an - sigma ** 2).sqrt()
@@ -189,7 +198,8 @@ def cpu_baseline(desc, sd, wl, budget_s=20.0):
     B, T = wl["B"], wl["T"]
     model = OracleUNet(desc, sd)
     dif = OracleDiffusion(sampling_timesteps=100)
-    emb, mask, cc = _make_problem(desc, B, T, 1)
+    causal = bool(wl.get("causal", False))
+    emb, mask, cc = _make_problem(desc, B, T, 1, causal)
     cond = dict(cross_attn_cond=emb, cross_attn_masks=mask, global_cond=None, input_concat_cond=cc)
     pairs = dif.time_pairs()
     torch.manual_seed(0)
@@ -202,7 +212,7 @@ def cpu_baseline(desc, sd, wl, budget_s=20.0):
             time_, _ = pairs[i % len(pairs)]
             tc = torch.full((B,), time_, dtype=torch.long)
             t0 = time.perf_counter()
-            eps, x0 = dif.model_predictions(x, tc, model, cond, clip=True)
+            eps, x0 = dif.model_predictions(x, tc, model, cond, clip=True, causal=causal)
             x = x0 * 0.99 + 0.1 * eps + 0.05 * torch.randn_like(x)
             times.append(time.perf_counter() - t0)
             i += 1
@@ -249,7 +259,7 @@ def run_ours(args, wl):
                                     cfg_dropout_proba=0.2, embedding_scale=0.8, batch_cfg=True, scale_cfg=True,
                                     sampling_steps=S)
     # each rank owns its own shard of the global batch (distinct prompts): seed by rank
-    emb_h, mask_h, cc_h = _make_problem(desc, B, T, 1 + rank)
+    emb_h, mask_h, cc_h = _make_problem(desc, B, T, 1 + rank, bool(wl.get("causal", False)))
     emb_p, mask_p, cc_p = emb_h.pin_memory(), mask_h.pin_memory(), cc_h.pin_memory()
 
     # ---------------- device-resident timing: K sampler steps, CUDA events on the launching stream
@@ -261,7 +271,7 @@ def run_ours(args, wl):
         coef = dif.ddim_coefficients()
         coef[:, 7] = 0.0  # no "last step" shortcut inside the timed window: every step does the full update
         coef[:, 4:7] = torch.nan_to_num(coef[:, 4:7])
-        eng.sample_begin(coef, cc, B, T, False, 0.8, True, 0.7, "noise", True)
+        eng.sample_begin(coef, cc, B, T, bool(wl.get("causal", False)), 0.8, True, 0.7, "noise", True)
         torch.manual_seed(1234 + rank)
         x = torch.randn(B, desc.in_channels, T, device=dev)
         noise = torch.empty_like(x)
@@ -310,7 +320,7 @@ def run_ours(args, wl):
     def e2e_call():
         cond = dict(cross_attn_cond=emb_p.to(dev, non_blocking=True), cross_attn_masks=mask_p.to(dev, non_blocking=True),
                     global_cond=None, input_concat_cond=cc_p.to(dev, non_blocking=True))
-        lat = dif_e.sample(model, (B, desc.in_channels, T), cond)
+        lat = dif_e.sample(model, (B, desc.in_channels, T), cond, causal=bool(wl.get("causal", False)))
         out_h.copy_(lat, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
 

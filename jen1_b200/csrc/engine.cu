@@ -37,7 +37,7 @@ Engine::~Engine() {
   if (smp_.exec) cudaGraphExecDestroy(smp_.exec);
   for (void* p : wallocs_) cudaFree(p);
   void* bufs[] = {kv_cond_, ctx_mask_, ctx_rowpart_, tt_t_, tt_tfm_, tt_tft_, tt_m1_, tt_m2_, tt_map_, tt_film_,
-                  tt_tok_, tt_tokrp_, tt_kv_, d_ctl_, arena_, smp_.coef};
+                  tt_tok_, tt_tokrp_, tt_kv_, d_ctl_, arena_, smp_.coef, timeline_};
   for (void* p : bufs)
     if (p) cudaFree(p);
 }
