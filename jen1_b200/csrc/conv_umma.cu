@@ -231,8 +231,9 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
   int2* tapg = reinterpret_cast<int2*>(fine + kMaxSlots * 2 * 32 * 2);  // [32] (panel row offset, unused) per tap
   int2* grange = tapg + 32;                                         // [32 groups][2 sources] fine-group range
   uint8_t* tabs = misc + kMiscFixed;
-  int2* rowmeta = reinterpret_cast<int2*>(tabs);                           // [rows0]: (input row | -1, b | panel row << 8)
-  int2* rowmeta1 = reinterpret_cast<int2*>(tabs + pl.off_rowmeta1);        // [NT] same for the seg-1 K steps
+  // [rows0]: (element offset of the input row in source 0 | -1, ... in source 1, b | panel row << 8, row index in source 0)
+  int4* rowmeta = reinterpret_cast<int4*>(tabs);
+  int4* rowmeta1 = reinterpret_cast<int4*>(tabs + pl.off_rowmeta1);        // [NT] same for the seg-1 K steps
   int4* colmeta = reinterpret_cast<int4*>(tabs + pl.off_colmeta);          // [NT]: (out offset | -1, residual offset, slot, batch row)
   float2* rowstat = reinterpret_cast<float2*>(tabs + pl.off_rowstat);      // [rows0] LayerNorm (mean, rstd) per slot
   float2* coef = reinterpret_cast<float2*>(tabs + pl.off_coef);            // [slots][ch_cap] (a, s): y = a*x + s
@@ -377,14 +378,23 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
       split_q(r, b, ml);
       const int irow = (ml + pl.amin) * f0 + rho;
       const bool ok = b < p.B && irow >= 0 && irow < S0.L;
-      rowmeta[idx] = make_int2(ok ? irow : -1, (b & 255) | ((rho * pl.PS + r) << 8));
+      int b0 = b, b1 = b;
+      if (b0 >= S0.s[0].bmod) b0 -= S0.s[0].bmod;
+      if (b1 >= S0.s[1].bmod) b1 -= S0.s[1].bmod;
+      rowmeta[idx] = make_int4(ok ? (b0 * S0.L + irow) * S0.s[0].C : -1, ok ? (b1 * S0.L + irow) * S0.s[1].C : 0,
+                               (b & 255) | ((rho * pl.PS + r) << 8), ok ? b0 * S0.L + irow : 0);
     }
     if (p.nseg > 1) {
       for (int r = tid; r < NT; r += kProducers) {
         int b, ml;
         split_q(r, b, ml);
         const bool ok = b < p.B && ml < p.seg[1].L;
-        rowmeta1[r] = make_int2(ok ? ml : -1, (b & 255) | (r << 8));
+        const ConvSeg& S1 = p.seg[1];
+        int b0 = b, b1 = b;
+        if (b0 >= S1.s[0].bmod) b0 -= S1.s[0].bmod;
+        if (b1 >= S1.s[1].bmod) b1 -= S1.s[1].bmod;
+        rowmeta1[r] = make_int4(ok ? (b0 * S1.L + ml) * S1.s[0].C : -1, ok ? (b1 * S1.L + ml) * S1.s[1].C : 0,
+                                (b & 255) | (r << 8), 0);
       }
     }
     for (int c = tid; c < NT; c += kProducers) {
@@ -453,8 +463,9 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
       const ConvSrc& sr = second ? S.s[1] : S.s[0];
       const int cc = second ? c0 - S.s[0].C : c0;
       const bool chan_ok = cc < sr.C;
-      const int2* meta = s1 ? rowmeta1 : rowmeta;
+      const int4* meta = s1 ? rowmeta1 : rowmeta;
       const int rows = s1 ? NT : rows0;
+      const bf16* base = (const bf16*)sr.ptr + cc;
       okm = 0;
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
@@ -462,11 +473,9 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
         if (idx >= rows) break;
         raw[u] = make_uint4(0u, 0u, 0u, 0u);
         if (chan_ok) {
-          const int2 m = meta[idx];
+          const int4 m = meta[idx];
           if (m.x >= 0) {
-            int b = m.y & 255;
-            if (b >= sr.bmod) b -= sr.bmod;
-            raw[u] = __ldcg(reinterpret_cast<const uint4*>((const bf16*)sr.ptr + ((size_t)b * S.L + m.x) * sr.C + cc));
+            raw[u] = __ldcg(reinterpret_cast<const uint4*>(base + (size_t)(uint32_t)(second ? m.y : m.x)));
             okm |= 1u << u;
           }
         }
@@ -479,7 +488,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
       const int c0 = (s1 ? t - pl.steps0 : t) * 64 + kc * 8;
       const bool second = c0 >= S.s[0].C;
       const float sscale = (second ? S.s[1] : S.s[0]).scale;
-      const int2* meta = s1 ? rowmeta1 : rowmeta;
+      const int4* meta = s1 ? rowmeta1 : rowmeta;
       const int rows = s1 ? NT : rows0;
       if (ib == 0 && n >= 2) mbar_wait(&p_empty[pb], (uint32_t)(((n >> 1) - 1) & 1));
       uint8_t* pan = panels + (size_t)pb * panel_bytes;
@@ -487,8 +496,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
       for (int u = 0; u < 8; ++u) {
         const int idx = ib * 128 + rr + 16 * u;
         if (idx >= rows) break;
-        const int2 m = meta[idx];
-        const int prow = m.y >> 8;
+        const int mz = meta[idx].z;
+        const int prow = mz >> 8;
         uint4 o = make_uint4(0u, 0u, 0u, 0u);
         if ((okm >> u) & 1u) {
           float v[8];
@@ -503,7 +512,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
             for (int e = 0; e < 8; ++e) v[e] *= sscale;
           } else if (affine) {
             if (need_coef) {
-              const float4* cf = reinterpret_cast<const float4*>(coef + (size_t)((m.y & 255) - b_first) * ch_cap + (c0 - ch_base));
+              const float4* cf = reinterpret_cast<const float4*>(coef + (size_t)((mz & 255) - b_first) * ch_cap + (c0 - ch_base));
               const float4 k0 = cf[0], k1 = cf[1], k2 = cf[2], k3 = cf[3];
               v[0] = fmaf(k0.x, v[0], k0.y); v[1] = fmaf(k0.z, v[1], k0.w);
               v[2] = fmaf(k1.x, v[2], k1.y); v[3] = fmaf(k1.z, v[3], k1.w);
@@ -565,12 +574,10 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
         const ConvSrc& sr = S0.s[0];
         const float inv = 1.0f / (float)sr.C;
         for (int idx = tid; idx < rows0; idx += kProducers) {
-          const int2 m = rowmeta[idx];
+          const int4 m = rowmeta[idx];
           float2 ms = make_float2(0.f, 1.f);
           if (m.x >= 0) {
-            int b = m.y & 255;
-            if (b >= sr.bmod) b -= sr.bmod;
-            const float2* rp = reinterpret_cast<const float2*>(p.rowpart) + ((size_t)b * S0.L + m.x) * p.rp_nct;
+            const float2* rp = reinterpret_cast<const float2*>(p.rowpart) + (size_t)m.w * p.rp_nct;
             float a = 0.f, qq = 0.f;
             for (int j0 = 0; j0 < p.rp_nct; j0 += 8) {
               float2 v2[8];
@@ -598,11 +605,14 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
         // items = (batch row, source, PAIR of fine groups): one 16-byte load brings both (sum, sumsq) pairs of an entry
         const int two_src = S0.s[1].C > 0 ? 1 : 0;
         const int nitem = nbl * (16 << two_src);
-        int parts = 1;
-        while (parts < 16 && nitem * parts * 2 <= kProducers) parts *= 2;
+        int parts = 1, lparts = 0;
+        while (parts < 16 && nitem * parts * 2 <= kProducers) {
+          parts *= 2;
+          ++lparts;
+        }
         for (int base = 0; base < nitem * parts; base += kProducers) {
           const int idx = base + tid;
-          const int item = idx / parts, part_i = idx - item * parts;
+          const int item = idx >> lparts, part_i = idx & (parts - 1);
           const int bl = item >> (4 + two_src), fs = two_src ? (item >> 4) & 1 : 0, pi = item & 15;
           float a0 = 0.f, q0s = 0.f, a1 = 0.f, q1s = 0.f;
           if (item < nitem) {
@@ -1049,6 +1059,7 @@ UmmaPlan conv_umma_plan(const ConvParams& p, bool want_stats, int num_sms) {
       const ConvSrc& sr = p.seg[sg].s[k];
       if (sr.C > 0 && (sr.C % 8 != 0)) return pl;
       if (sr.C > 0 && (sr.bmod < 1 || p.B > 2 * sr.bmod)) return pl;  // `b % bmod` is one conditional subtract
+      if (sr.C > 0 && (long long)sr.bmod * p.seg[sg].L * sr.C >= (1ll << 31)) return pl;  // 32-bit offsets in the row table
     }
   if (p.res && (p.res_bmod < 1 || p.B > 2 * p.res_bmod)) return pl;
   if (S0.s[0].C <= 0) return pl;
@@ -1124,9 +1135,9 @@ UmmaPlan conv_umma_plan(const ConvParams& p, bool want_stats, int num_sms) {
     c.E_max = ((c.Lq - 1) / NT + 2) * sk;
     // tables
     const int rows0 = f * c.R;
-    int off = round_up(rows0 * 8, 16);
+    int off = rows0 * 16;
     c.off_rowmeta1 = off;
-    off += p.nseg > 1 ? NT * 8 : 0;
+    off += p.nseg > 1 ? NT * 16 : 0;
     c.off_colmeta = off;
     off += NT * 16;
     c.off_rowstat = off;
