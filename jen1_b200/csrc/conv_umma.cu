@@ -569,144 +569,144 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
       if (primed) {
         consume(cn, cib, rA, mA);
       } else {
-      if (!affine) {
-        // LayerNorm statistics of every panel row from the producer's per-tile partials (once per CTA)
-        const ConvSrc& sr = S0.s[0];
-        const float inv = 1.0f / (float)sr.C;
-        for (int idx = tid; idx < rows0; idx += kProducers) {
-          const int4 m = rowmeta[idx];
-          float2 ms = make_float2(0.f, 1.f);
-          if (m.x >= 0) {
-            const float2* rp = reinterpret_cast<const float2*>(p.rowpart) + (size_t)m.w * p.rp_nct;
-            float a = 0.f, qq = 0.f;
-            for (int j0 = 0; j0 < p.rp_nct; j0 += 8) {
-              float2 v2[8];
-  #pragma unroll
-              for (int jj = 0; jj < 8; ++jj) v2[jj] = (j0 + jj < p.rp_nct) ? __ldcg(rp + j0 + jj) : make_float2(0.f, 0.f);
-  #pragma unroll
-              for (int jj = 0; jj < 8; ++jj) {
-                a += v2[jj].x;
-                qq += v2[jj].y;
+        if (!affine) {
+          // LayerNorm statistics of every panel row from the producer's per-tile partials (once per CTA)
+          const ConvSrc& sr = S0.s[0];
+          const float inv = 1.0f / (float)sr.C;
+          for (int idx = tid; idx < rows0; idx += kProducers) {
+            const int4 m = rowmeta[idx];
+            float2 ms = make_float2(0.f, 1.f);
+            if (m.x >= 0) {
+              const float2* rp = reinterpret_cast<const float2*>(p.rowpart) + (size_t)m.w * p.rp_nct;
+              float a = 0.f, qq = 0.f;
+              for (int j0 = 0; j0 < p.rp_nct; j0 += 8) {
+                float2 v2[8];
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) v2[jj] = (j0 + jj < p.rp_nct) ? __ldcg(rp + j0 + jj) : make_float2(0.f, 0.f);
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                  a += v2[jj].x;
+                  qq += v2[jj].y;
+                }
+              }
+              const float m1 = a * inv;
+              float var = qq * inv - m1 * m1;
+              if (var < 0.0f) var = 0.0f;
+              ms = make_float2(m1, 1.0f / sqrtf(var + p.ln_eps));
+            }
+            rowstat[idx] = ms;
+          }
+        }
+
+        // ---- GroupNorm statistics of the input for the batch rows this tile touches.  Deterministic two-level reduce:
+        //      fine-group sums of every (batch row, source, fine group) item from the producer's partial entries (an item
+        //      is split over `parts` lanes combined by shuffles in a fixed order), then one thread per group.
+        if (has_gn) {
+          // items = (batch row, source, PAIR of fine groups): one 16-byte load brings both (sum, sumsq) pairs of an entry
+          const int two_src = S0.s[1].C > 0 ? 1 : 0;
+          const int nitem = nbl * (16 << two_src);
+          int parts = 1, lparts = 0;
+          while (parts < 16 && nitem * parts * 2 <= kProducers) {
+            parts *= 2;
+            ++lparts;
+          }
+          for (int base = 0; base < nitem * parts; base += kProducers) {
+            const int idx = base + tid;
+            const int item = idx >> lparts, part_i = idx & (parts - 1);
+            const int bl = item >> (4 + two_src), fs = two_src ? (item >> 4) & 1 : 0, pi = item & 15;
+            float a0 = 0.f, q0s = 0.f, a1 = 0.f, q1s = 0.f;
+            if (item < nitem) {
+              const ConvSrc& fsr = S0.s[fs];
+              if (fsr.C > 0 && 2 * pi < fsr.FG) {
+                int b = b_first + bl;
+                if (b >= fsr.bmod) b -= fsr.bmod;
+                const float* st = fsr.stats + ((size_t)b * fsr.n_ent * fsr.FG + 2 * pi) * 2;
+                if (fsr.FG >= 2) {
+                  for (int e0 = part_i; e0 < fsr.n_ent; e0 += parts * 12) {  // 12 independent 16-byte L2 loads in flight
+                    float4 buf[12];
+#pragma unroll
+                    for (int u = 0; u < 12; ++u) {
+                      const int e = e0 + u * parts;
+                      buf[u] = e < fsr.n_ent ? __ldcg(reinterpret_cast<const float4*>(st + (size_t)e * fsr.FG * 2))
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 12; ++u) {
+                      a0 += buf[u].x;
+                      q0s += buf[u].y;
+                      a1 += buf[u].z;
+                      q1s += buf[u].w;
+                    }
+                  }
+                } else {  // a single whole-tensor group (boundary tensors)
+                  for (int e0 = part_i; e0 < fsr.n_ent; e0 += parts * 12) {
+                    float2 buf[12];
+#pragma unroll
+                    for (int u = 0; u < 12; ++u) {
+                      const int e = e0 + u * parts;
+                      buf[u] = e < fsr.n_ent ? __ldcg(reinterpret_cast<const float2*>(st + (size_t)e * fsr.FG * 2)) : make_float2(0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 12; ++u) {
+                      a0 += buf[u].x;
+                      q0s += buf[u].y;
+                    }
+                  }
+                }
               }
             }
-            const float m1 = a * inv;
-            float var = qq * inv - m1 * m1;
+            for (int o = 1; o < parts; o <<= 1) {
+              a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+              q0s += __shfl_xor_sync(0xffffffffu, q0s, o);
+              a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+              q1s += __shfl_xor_sync(0xffffffffu, q1s, o);
+            }
+            if (item < nitem && part_i == 0) {
+              const float sc = S0.s[fs].scale;
+              float4* fo = reinterpret_cast<float4*>(fine + ((bl * 2 + fs) * 32 + 2 * pi) * 2);
+              *fo = make_float4(a0 * sc, q0s * sc * sc, a1 * sc, q1s * sc * sc);
+            }
+          }
+          bar_sync_producers();
+          // pass 2: one thread per (batch row, group)
+          for (int idx = tid; idx < nbl * p.G; idx += kProducers) {
+            const int bl = idx / p.G, g = idx - bl * p.G;
+            float ga = 0.f, gq = 0.f;
+#pragma unroll
+            for (int sI = 0; sI < 2; ++sI) {
+              const int2 rg = grange[g * 2 + sI];
+              for (int fg = rg.x; fg < rg.y; ++fg) {
+                ga += fine[((bl * 2 + sI) * 32 + fg) * 2];
+                gq += fine[((bl * 2 + sI) * 32 + fg) * 2 + 1];
+              }
+            }
+            // fp32 is ample here: this kernel only serves bf16 storage (the strict fp32 mode runs the generic kernel)
+            const float mean = ga * inv_n;
+            float var = fmaf(-mean, mean, gq * inv_n);
             if (var < 0.0f) var = 0.0f;
-            ms = make_float2(m1, 1.0f / sqrtf(var + p.ln_eps));
+            gmean[bl * 32 + g] = mean;
+            grstd[bl * 32 + g] = rsqrtf(var + p.eps);
           }
-          rowstat[idx] = ms;
         }
-      }
+        bar_sync_producers();  // gmean / grstd, rowstat
+        if (tid == 0) TL_MARK(3);
 
-      // ---- GroupNorm statistics of the input for the batch rows this tile touches.  Deterministic two-level reduce:
-      //      fine-group sums of every (batch row, source, fine group) item from the producer's partial entries (an item
-      //      is split over `parts` lanes combined by shuffles in a fixed order), then one thread per group.
-      if (has_gn) {
-        // items = (batch row, source, PAIR of fine groups): one 16-byte load brings both (sum, sumsq) pairs of an entry
-        const int two_src = S0.s[1].C > 0 ? 1 : 0;
-        const int nitem = nbl * (16 << two_src);
-        int parts = 1, lparts = 0;
-        while (parts < 16 && nitem * parts * 2 <= kProducers) {
-          parts *= 2;
-          ++lparts;
-        }
-        for (int base = 0; base < nitem * parts; base += kProducers) {
-          const int idx = base + tid;
-          const int item = idx >> lparts, part_i = idx & (parts - 1);
-          const int bl = item >> (4 + two_src), fs = two_src ? (item >> 4) & 1 : 0, pi = item & 15;
-          float a0 = 0.f, q0s = 0.f, a1 = 0.f, q1s = 0.f;
-          if (item < nitem) {
-            const ConvSrc& fsr = S0.s[fs];
-            if (fsr.C > 0 && 2 * pi < fsr.FG) {
-              int b = b_first + bl;
-              if (b >= fsr.bmod) b -= fsr.bmod;
-              const float* st = fsr.stats + ((size_t)b * fsr.n_ent * fsr.FG + 2 * pi) * 2;
-              if (fsr.FG >= 2) {
-                for (int e0 = part_i; e0 < fsr.n_ent; e0 += parts * 12) {  // 12 independent 16-byte L2 loads in flight
-                  float4 buf[12];
-#pragma unroll
-                  for (int u = 0; u < 12; ++u) {
-                    const int e = e0 + u * parts;
-                    buf[u] = e < fsr.n_ent ? __ldcg(reinterpret_cast<const float4*>(st + (size_t)e * fsr.FG * 2))
-                                           : make_float4(0.f, 0.f, 0.f, 0.f);
-                  }
-#pragma unroll
-                  for (int u = 0; u < 12; ++u) {
-                    a0 += buf[u].x;
-                    q0s += buf[u].y;
-                    a1 += buf[u].z;
-                    q1s += buf[u].w;
-                  }
-                }
-              } else {  // a single whole-tensor group (boundary tensors)
-                for (int e0 = part_i; e0 < fsr.n_ent; e0 += parts * 12) {
-                  float2 buf[12];
-#pragma unroll
-                  for (int u = 0; u < 12; ++u) {
-                    const int e = e0 + u * parts;
-                    buf[u] = e < fsr.n_ent ? __ldcg(reinterpret_cast<const float2*>(st + (size_t)e * fsr.FG * 2)) : make_float2(0.f, 0.f);
-                  }
-#pragma unroll
-                  for (int u = 0; u < 12; ++u) {
-                    a0 += buf[u].x;
-                    q0s += buf[u].y;
-                  }
-                }
-              }
+        // ---- per-(batch row, channel) affine coefficients of this CTA's channel slice, finished in place:
+        //      y = a*x + s,  a = scale*rstd*P,  s = Q - mean*rstd*P   (P, Q tabulated before the wait)
+        if (need_coef && has_gn) {
+          for (int bl = 0; bl < nbl; ++bl) {
+            for (int c = tid; c < my_ch; c += kProducers) {
+              const int ch = ch_base + c;
+              const int g = cpg_shift >= 0 ? ch >> cpg_shift : ch / cpg;
+              const float2 pq = coef[(size_t)bl * ch_cap + c];
+              const float rp = (ch < Ct) ? grstd[bl * 32 + g] * pq.x : 0.f;
+              const float scale = (ch >= S0.s[0].C ? S0.s[1] : S0.s[0]).scale;
+              coef[(size_t)bl * ch_cap + c] = make_float2(rp * scale, (ch < Ct) ? fmaf(-gmean[bl * 32 + g], rp, pq.y) : 0.f);
             }
           }
-          for (int o = 1; o < parts; o <<= 1) {
-            a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-            q0s += __shfl_xor_sync(0xffffffffu, q0s, o);
-            a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-            q1s += __shfl_xor_sync(0xffffffffu, q1s, o);
-          }
-          if (item < nitem && part_i == 0) {
-            const float sc = S0.s[fs].scale;
-            float4* fo = reinterpret_cast<float4*>(fine + ((bl * 2 + fs) * 32 + 2 * pi) * 2);
-            *fo = make_float4(a0 * sc, q0s * sc * sc, a1 * sc, q1s * sc * sc);
-          }
+          bar_sync_producers();
         }
-        bar_sync_producers();
-        // pass 2: one thread per (batch row, group)
-        for (int idx = tid; idx < nbl * p.G; idx += kProducers) {
-          const int bl = idx / p.G, g = idx - bl * p.G;
-          float ga = 0.f, gq = 0.f;
-  #pragma unroll
-          for (int sI = 0; sI < 2; ++sI) {
-            const int2 rg = grange[g * 2 + sI];
-            for (int fg = rg.x; fg < rg.y; ++fg) {
-              ga += fine[((bl * 2 + sI) * 32 + fg) * 2];
-              gq += fine[((bl * 2 + sI) * 32 + fg) * 2 + 1];
-            }
-          }
-          // fp32 is ample here: this kernel only serves bf16 storage (the strict fp32 mode runs the generic kernel)
-          const float mean = ga * inv_n;
-          float var = fmaf(-mean, mean, gq * inv_n);
-          if (var < 0.0f) var = 0.0f;
-          gmean[bl * 32 + g] = mean;
-          grstd[bl * 32 + g] = rsqrtf(var + p.eps);
-        }
-      }
-      bar_sync_producers();  // gmean / grstd, rowstat
-      if (tid == 0) TL_MARK(3);
-
-      // ---- per-(batch row, channel) affine coefficients of this CTA's channel slice, finished in place:
-      //      y = a*x + s,  a = scale*rstd*P,  s = Q - mean*rstd*P   (P, Q tabulated before the wait)
-      if (need_coef && has_gn) {
-        for (int bl = 0; bl < nbl; ++bl) {
-          for (int c = tid; c < my_ch; c += kProducers) {
-            const int ch = ch_base + c;
-            const int g = cpg_shift >= 0 ? ch >> cpg_shift : ch / cpg;
-            const float2 pq = coef[(size_t)bl * ch_cap + c];
-            const float rp = (ch < Ct) ? grstd[bl * 32 + g] * pq.x : 0.f;
-            const float scale = (ch >= S0.s[0].C ? S0.s[1] : S0.s[0]).scale;
-            coef[(size_t)bl * ch_cap + c] = make_float2(rp * scale, (ch < Ct) ? fmaf(-gmean[bl * 32 + g], rp, pq.y) : 0.f);
-          }
-        }
-        bar_sync_producers();
-      }
-      if (tid == 0) TL_MARK(4);
+        if (tid == 0) TL_MARK(4);
       }
       if (!can_issue) break;
 #pragma unroll
