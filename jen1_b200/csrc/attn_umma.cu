@@ -364,6 +364,12 @@ bool attn_umma_supported(const AttnParams& p) {
   return true;
 }
 
+// Function attributes are per device: called once per engine from Engine::finalize() after cudaSetDevice (a process
+// may hold one engine per GPU).
+cudaError_t attn_umma_init() {
+  return cudaFuncSetAttribute(attn_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
+
 cudaError_t launch_attention_umma(const AttnParams& p, bool pdl, cudaStream_t stream) {
   if (!attn_umma_supported(p)) return cudaErrorInvalidValue;
   AttnGeom g;
@@ -384,12 +390,6 @@ cudaError_t launch_attention_umma(const AttnParams& p, bool pdl, cudaStream_t st
   g.off_p = 0;  // P aliases Q / K (both dead once S has been computed)
   g.off_v = qk > pq ? qk : pq;
   g.smem = g.off_v + (k_bytes + 1023u) / 1024u * 1024u + 64u;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(attn_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return e;
-    attr = true;
-  }
   if (g.smem + 1024 > 227 * 1024) return cudaErrorInvalidValue;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));

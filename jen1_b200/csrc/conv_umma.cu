@@ -757,6 +757,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
         for (int j = 0; j < 16; ++j) part[(size_t)(c0 + j) * 128 + tid] = v[j];
       }
     }
+    if (tid == 0) TL_MARK(16);
     cluster_sync_all();  // every CTA's partial tile is visible cluster-wide
     if (tid == 0) TL_MARK(7);
   }
@@ -983,6 +984,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
       }
     }
     flush_stats();
+    if (tid == 0) TL_MARK(13);
     if (want_stats || want_rows) bar_sync_producers();
     if (want_stats) {
       // per (batch row, fine group) partial of this CTA's columns -> entry (tile index within the batch row, split
@@ -1032,6 +1034,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
     }
   }
 
+  if (tid == 0) TL_MARK(14);
   if (SK > 1) cluster_sync_all();  // nobody leaves while its partial tile may still be read remotely
 
   if (tid == 0) { TL_MARK(8); TL_GLOBAL(12); }

@@ -288,6 +288,9 @@ int Engine::finalize() {
       if (prop.major != 10) use_umma_ = false;  // tcgen05 needs sm_100
     }
     if (use_umma_ && conv_umma_init() != cudaSuccess) return fail("tcgen05 path initialisation failed");
+    // shared-memory opt-ins of the attention kernels are per device as well (one engine per GPU in one process)
+    if (attention_init() != cudaSuccess) return fail("attention kernel initialisation failed");
+    if (use_umma_ && attn_umma_init() != cudaSuccess) return fail("tcgen05 attention initialisation failed");
   }
   try {
     const int nl = d_.num_layers;
@@ -1182,9 +1185,10 @@ void Engine::dump_timeline(cudaStream_t st) {
     const long long gap = prev_end ? t[11] - prev_end : 0;
     sum_gap += gap;
     sum_body += t[12] - t[11];
-    fprintf(stderr, "[jen1-tl] u%03d gap_ns %lld body_ns %lld | cyc: early %lld stats %lld coef %lld panels %lld accfull %lld cluster %lld end %lld | mma first_a %lld issued %lld\n",
+    fprintf(stderr, "[jen1-tl] u%03d gap_ns %lld body_ns %lld | cyc: early %lld stats %lld coef %lld panels %lld accfull %lld cluster %lld end %lld part %lld eploop %lld epstats %lld | mma first_a %lld issued %lld\n",
             i, gap, t[12] - t[11], t[2] - t[0], t[3] - t[2], t[4] - t[2], t[5] - t[2], t[6] - t[2],
-            t[7] ? t[7] - t[2] : 0, t[8] - t[2], t[9] - t[2], t[10] - t[2]);
+            t[7] ? t[7] - t[2] : 0, t[8] - t[2], t[16] ? t[16] - t[2] : 0, t[13] ? t[13] - t[2] : 0,
+            t[14] ? t[14] - t[2] : 0, t[9] - t[2], t[10] - t[2]);
     prev_end = t[12];
   }
   fprintf(stderr, "[jen1-tl] total: %d tcgen05 ops, sum gap %.1f us, sum body %.1f us\n", tl_ops_, sum_gap / 1e3, sum_body / 1e3);
@@ -1215,7 +1219,8 @@ int Engine::sample_begin(const float* coef_host, int S, const float* cc, int B, 
     if (!ck(cudaMalloc((void**)&smp_.coef, (size_t)S * 8 * 4), "malloc coef")) return 1;
     smp_.coef_cap = (size_t)S * 8 * 4;
   }
-  if (!ck(cudaMemcpyAsync(smp_.coef, coef_host, (size_t)S * 8 * 4, cudaMemcpyHostToDevice, st), "memcpy coef")) return 1;
+  smp_.coef_h.assign(coef_host, coef_host + (size_t)S * 8);
+  if (!ck(cudaMemcpyAsync(smp_.coef, smp_.coef_h.data(), (size_t)S * 8 * 4, cudaMemcpyHostToDevice, st), "memcpy coef")) return 1;
   // A captured step graph stays valid across sample() calls as long as everything baked into it is unchanged:
   // shapes and mode flags (they select kernels / plans) and the buffers the nodes point at (arena, tables, caches
   // -- their owners destroy the graph when they reallocate).  Re-capturing 263 nodes costs ~10 ms per call.
@@ -1267,6 +1272,10 @@ int Engine::sample_step(int step, float* x, const float* noise, const uint8_t* d
   cudaSetDevice(device_);
   ok_ = true;
   if (step < 0 || step >= smp_.S) return fail("sample_step: step out of range");
+  // the update mixes sigma * noise unless this row is flagged as the last step (coef[step][7]): a NULL noise pointer
+  // is only legal there (graph and non-graph paths alike)
+  if (noise == nullptr && smp_.coef_h[(size_t)step * 8 + 7] == 0.0f)
+    return fail("sample_step: noise must not be NULL unless the step's coefficient row is flagged as last");
   const int B = smp_.B, T = smp_.T;
   const bool cfg = smp_.emb_scale != 1.0f;
   const int B2 = cfg ? 2 * B : B;

@@ -230,6 +230,7 @@ class Engine {
     float emb_scale = 1.f, phi = 0.7f;
     float* coef = nullptr;
     size_t coef_cap = 0;
+    std::vector<float> coef_h;  // host copy of the per-step scalars (is-last flag validates a NULL noise pointer)
     float* cc_copy = nullptr;  // persistent packed concat-cond lives at the arena base
     Act ccpk;
     size_t arena_base = 0;

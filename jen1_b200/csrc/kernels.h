@@ -82,6 +82,8 @@ struct AttnParams {
 };
 template <typename T>
 cudaError_t launch_attention(const AttnParams& p, cudaStream_t stream);
+cudaError_t attention_init();   // per-device function attributes (call after cudaSetDevice, once per engine)
+cudaError_t attn_umma_init();
 // tcgen05 / TMEM implementation for bf16 storage (attn_umma.cu): head dim in {16, 32, 64, 128}, up to 256 keys
 bool attn_umma_supported(const AttnParams& p);
 cudaError_t launch_attention_umma(const AttnParams& p, bool pdl, cudaStream_t stream);

@@ -275,6 +275,13 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnParams p) {
   }
 }
 
+// Function attributes are per device: called once per engine from Engine::finalize() after cudaSetDevice.
+cudaError_t attention_init() {
+  cudaError_t e = cudaFuncSetAttribute(attention_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(attention_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+}
+
 template <typename T>
 cudaError_t launch_attention(const AttnParams& p, cudaStream_t stream) {
   if (p.d > AT_MAXD || (p.d & 7) || (p.q_ld & 7) || (p.q_off & 7) || (p.C & 7)) return cudaErrorInvalidValue;
@@ -282,12 +289,6 @@ cudaError_t launch_attention(const AttnParams& p, cudaStream_t stream) {
   if (p.cross && ((p.kvc_ld & 7) || (p.kvc_off & 7))) return cudaErrorInvalidValue;
   dim3 grid((p.N + AT_QB - 1) / AT_QB, p.H, p.B2);
   size_t smem = (size_t)(AT_QB * p.d + 2 * AT_KT * (p.d + 1)) * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(attention_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    cudaFuncSetAttribute(attention_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    attr = true;
-  }
   attention_kernel<T><<<grid, 128, smem, stream>>>(p);
   return cudaGetLastError();
 }

@@ -135,7 +135,12 @@ class GaussianDiffusion:
                 extract(self._tab("posterior_log_variance_clipped", x_t), t, x_t.shape))
 
     def _call_model(self, model, x, t, conditioning, causal):
-        return model(x, t, embedding=conditioning["cross_attn_cond"], embedding_mask=conditioning["cross_attn_masks"],
+        extra = {}
+        if isinstance(model, UNetCFG1d) and self.cfg_dropout_proba > 0.0:
+            # the cond-dropout bernoulli (reference model.py:325) is drawn HERE, with this object's rng_device /
+            # shard rules, so the seed-parity guarantees also hold when the model is driven step by step
+            extra["drop_mask"] = self._bernoulli(x.shape[0], x.device)
+        return model(x, t, **extra, embedding=conditioning["cross_attn_cond"], embedding_mask=conditioning["cross_attn_masks"],
                      embedding_scale=self.embedding_scale, embedding_mask_proba=self.cfg_dropout_proba,
                      features=conditioning["global_cond"], channels_list=[conditioning["input_concat_cond"]],
                      batch_cfg=self.batch_cfg, scale_cfg=self.scale_cfg, causal=causal)
@@ -218,7 +223,9 @@ class GaussianDiffusion:
         device = eng.device
         B, Cc, T = shape
         pairs = self.time_pairs()
-        model.set_context(conditioning["cross_attn_cond"], conditioning["cross_attn_masks"])
+        # always rebuild the prompt K/V cache at the start of a trajectory (one small GEMM against 100 steps): the
+        # model-side cache key cannot see `.data` swaps or a direct engine.set_context with another batch
+        model.set_context(conditioning["cross_attn_cond"], conditioning["cross_attn_masks"], force=True)
         eng.set_timesteps([t for t, _ in pairs])
         use_cfg = self.embedding_scale != 1.0
         # CUDA graphs cannot be captured on the legacy default stream: run the loop on a side stream

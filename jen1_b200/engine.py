@@ -68,7 +68,7 @@ class Engine:
             shp = (C.c_int64 * len(shape))(*shape)
             self._ck(self.lib.jen1_engine_load_tensor(h, name.encode(), C.c_void_p(t.data_ptr()), shp, len(shape)))
         self._ck(self.lib.jen1_engine_finalize(h))
-        self._ctx_key = None
+        self.context_epoch = 0  # bumped by every set_context: callers caching "context is current" key on it
         self._t_rows: Dict[int, int] = {}
 
     # ------------------------------------------------------------------------------------------------
@@ -116,6 +116,7 @@ class Engine:
                                                   C.c_void_p(m.data_ptr()) if m is not None else None, B, S,
                                                   self._stream()))
         self._keep = (emb, m)
+        self.context_epoch += 1
 
     def set_timesteps(self, ts: Sequence[int]):
         ts = [int(v) for v in ts]

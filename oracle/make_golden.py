@@ -76,9 +76,26 @@ def run_unet_cases(desc, model, cases):
     return out
 
 
+def make_config2_golden():
+    """Full-size UNet at BASELINE config 2's shape (B=1, T=1515, CFG): pins the benchmarked configuration to the
+    live reference, not only to the port.  Kept in its own file so the round-1 fixtures stay byte-identical."""
+    ref_import.install_shims()
+    desc = UNetDesc()
+    sd = random_state_dict(desc, seed=0)
+    model = ref_import.build_reference_unet()
+    model.load_state_dict(sd, strict=True)
+    cases = {"T1515_B1": (1, 1515, 201, 0, ["cfg"])}
+    full = run_unet_cases(desc, model, cases)
+    torch.save(dict(weights_seed=0, cases=full), os.path.join(GOLD, "unet_full_c2.pt"))
+    print("  %-28s %8.1f KB" % ("unet_full_c2.pt", os.path.getsize(os.path.join(GOLD, "unet_full_c2.pt")) / 1024))
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     ref_import.install_shims()
+    if len(sys.argv) > 1 and sys.argv[1] == "c2":
+        make_config2_golden()
+        return
 
     # ---- 1. state_dict inventory of the reference (names, shapes, order) -------------------------------
     spec = {}
@@ -164,6 +181,7 @@ def main():
     for rec in full.values():  # keep the fixture small: fp32 [B,128,T]
         pass
     torch.save(dict(weights_seed=0, cases=full), os.path.join(GOLD, "unet_full.pt"))
+    make_config2_golden()
     print("golden fixtures written to", GOLD)
     for fn in sorted(os.listdir(GOLD)):
         print("  %-28s %8.1f KB" % (fn, os.path.getsize(os.path.join(GOLD, fn)) / 1024))

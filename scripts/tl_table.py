@@ -18,9 +18,10 @@ def main(path):
         gap, body = int(d['gap_ns']) / 1e3, int(d['body_ns']) / 1e3
         c = dict(re.findall(r'(\w+) (-?\d+)', t.split('cyc:')[1]))
         g = lambda k: int(c[k]) / F
-        print("%s B%d L%4d Ci%4d+%4d Co%4d k%d s%d p%d G%2d m%d NT%3d t%3dx%d sk%2d st%d | gap %5.1f body %5.1f | early %6.1f stats %4.1f coef %4.1f panels %5.1f acc %5.1f clus %5.1f end %5.1f | first_a %4.1f issued %4.1f"
+        print("%s B%d L%4d Ci%4d+%4d Co%4d k%d s%d p%d G%2d m%d NT%3d t%3dx%d sk%2d st%d | gap %5.1f body %5.1f | early %6.1f stats %4.1f coef %4.1f panels %5.1f acc %5.1f part %5.1f clus %5.1f eploop %5.1f epstats %5.1f end %5.1f | first_a %4.1f issued %4.1f"
               % (o[7:12], B, Lm, Ci, Ci2, Co, taps, st, ph, G, mode, NT, nt, mt, sk, stg, gap, body, g('early'), g('stats'), g('coef'),
-                 g('panels'), g('accfull'), g('cluster'), g('end'), g('first_a'), g('issued')))
+                 g('panels'), g('accfull'), g('part') if 'part' in c else 0.0, g('cluster'), g('eploop') if 'eploop' in c else 0.0,
+                 g('epstats') if 'epstats' in c else 0.0, g('end'), g('first_a'), g('issued')))
         key = "L%d" % Lm
         a = tot.setdefault(key, [0, 0.0, 0.0])
         a[0] += 1

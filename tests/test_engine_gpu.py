@@ -3,8 +3,10 @@ fixtures (outputs of the unmodified reference).  Run on the B200 box with `pytes
 
 Tolerances (stated per precision mode, SURVEY.md section 7 "hard parts" 3):
   fp32 strict mode : max-abs error <= 2e-4 * max|ref| for one UNet evaluation (fp32 FMA, different summation order)
-  bf16 mode        : rel-L2 error  <= 2e-2 for one UNet evaluation (bf16 storage, fp32 accumulate); the reference's
-                     own bf16-autocast run sits at 8.9e-3, random-init weights.
+  bf16 mode        : rel-L2 error  <= 1e-2 for one UNet evaluation (bf16 storage, fp32 accumulate; SURVEY.md section 7.3);
+                     the reference's own bf16-autocast run sits at 8.9e-3, random-init weights.  Per-stage taps (a
+                     localisation aid, not the gate) are allowed 2e-2: single stages of the tiny model sit above the
+                     end-to-end error.
 """
 import os
 
@@ -67,7 +69,7 @@ def _check_taps(model, taps, tol, tag):
 
 
 # fp32: 5e-4 (GroupNorm over as few as 4 elements at T<=8 amplifies summation-order differences; typical 1e-6)
-@pytest.mark.parametrize("dtype,tol", [("fp32", 5e-4), ("bf16", 2e-2)])
+@pytest.mark.parametrize("dtype,tol", [("fp32", 5e-4), ("bf16", 1e-2)])
 def test_tiny_unet_matches_reference_golden(tiny_models, golden_dir, dtype, tol):
     desc, sd, models = tiny_models
     model = models[dtype]
@@ -86,7 +88,7 @@ def test_tiny_unet_matches_reference_golden(tiny_models, golden_dir, dtype, tol)
             with torch.no_grad():
                 unet_cfg_forward(desc, sd, x, t, embedding=emb, embedding_mask=mask, channels_list=[cc], taps=taps, **kw)
             y = _run_engine(model, x, t, emb, mask, cc, **kw)
-            _check_taps(model, taps, tol, "%s/%s/%s" % (dtype, name, v))
+            _check_taps(model, taps, tol if dtype == "fp32" else 2e-2, "%s/%s/%s" % (dtype, name, v))
             err = rel_l2(y, ref)
             assert err < tol, "%s %s %s: rel-L2 %.3e vs reference golden" % (dtype, name, v, err)
             if dtype == "fp32":

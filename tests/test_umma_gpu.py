@@ -81,7 +81,7 @@ def test_full_unet_bf16_matches_reference_golden(ab_models, golden_dir):
             y = mu(x.cuda(), t.cuda(), embedding=emb.cuda(), embedding_mask=mask.cuda(), features=None,
                    channels_list=[cc.cuda()], **dict(VARIANTS[v])).cpu()
             err = ((y - ref).norm() / ref.norm()).item()
-            assert err < 2e-2, "full bf16 %s %s rel-L2 %.3e" % (name, v, err)
+            assert err < 1e-2, "full bf16 %s %s rel-L2 %.3e" % (name, v, err)  # SURVEY.md section 7.3 gate
 
 
 def test_full_size_batch_independence(ab_models):
