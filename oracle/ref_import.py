@@ -1,11 +1,13 @@
-"""Import shim for the UNMODIFIED reference at /root/reference (build container only).
+"""Import shim for the UNMODIFIED reference: /root/reference (build container) or the git-ignored install
+baseline/_ref/ made by scripts/install_reference.py (travels to the GPU box).
 
-TEST INFRASTRUCTURE -- never imported by the product path.  Only `oracle/make_golden.py`
-(fixture generation, run in the build container where /root/reference exists) uses this.
+TEST INFRASTRUCTURE -- never imported by the product path.  Used by `oracle/make_golden.py` (fixture generation
+in the build container) and by `bench.py --impl reference` (the reference's own CPU path as the timed baseline).
 Follows SURVEY.md Appendix A: two missing third-party modules are stubbed
 (`einops_exts.rearrange_many` -- reference jen1/model/blocks.py:8, utils/module.py:7;
 `dac.nn.layers.Snake1d` -- blocks.py:5, only constructed when use_snake=True).
 """
+import os
 import sys
 import types
 
@@ -13,9 +15,19 @@ import einops
 import torch
 
 REFERENCE_ROOT = "/root/reference"
+INSTALLED_ROOT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
 
 
-def install_shims():
+def reference_root(prefer_installed: bool = False):
+    """Where the reference can be imported from, or None."""
+    order = (INSTALLED_ROOT, REFERENCE_ROOT) if prefer_installed else (REFERENCE_ROOT, INSTALLED_ROOT)
+    for r in order:
+        if os.path.isdir(os.path.join(r, "jen1", "model")):
+            return r
+    return None
+
+
+def install_shims(root=None):
     if "einops_exts" not in sys.modules:
         ee = types.ModuleType("einops_exts")
         ee.rearrange_many = lambda ts, pattern, **kw: tuple(einops.rearrange(t, pattern, **kw) for t in ts)
@@ -29,8 +41,11 @@ def install_shims():
 
         dl.Snake1d = Snake1d
         sys.modules.update({"dac": dac, "dac.nn": dnn, "dac.nn.layers": dl})
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    root = root or reference_root()
+    if root is None:
+        raise ImportError("the reference is neither at %s nor installed at %s" % (REFERENCE_ROOT, INSTALLED_ROOT))
+    if root not in sys.path:
+        sys.path.insert(0, root)
 
 
 def reference_model_kwargs():

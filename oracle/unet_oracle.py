@@ -72,7 +72,7 @@ def attention(sd, p: str, x: Tensor, heads: int, context: Optional[Tensor], cont
     vh = v.view(B, M, heads, d).transpose(1, 2)
     sim = torch.matmul(qh, kh.transpose(-1, -2)) * (d ** -0.5)
     if causal:  # blocks.py:315-319 causal_mask: keep j <= i + (M - N)
-        keep = ~torch.ones((N, M), dtype=torch.bool).triu(M - N + 1)
+        keep = ~torch.ones((N, M), dtype=torch.bool, device=sim.device).triu(M - N + 1)
         sim = sim.masked_fill(~keep, -torch.finfo(sim.dtype).max)
     attn = sim.softmax(dim=-1, dtype=torch.float32)
     out = torch.matmul(attn, vh).transpose(1, 2).reshape(B, N, C)
@@ -192,14 +192,14 @@ def unet_cfg_forward(desc, sd: Dict[str, Tensor], x: Tensor, time: Tensor, *, em
     tok = F.gelu(F.linear(tf, sd["to_time_embedding.0.1.weight"], sd["to_time_embedding.0.1.bias"]))
     embedding = torch.cat([embedding, tok.unsqueeze(1)], dim=1)
     if embedding_mask is not None:
-        embedding_mask = torch.cat([embedding_mask, torch.ones((b, 1))], dim=1)  # bool -> float promotion
+        embedding_mask = torch.cat([embedding_mask, torch.ones((b, 1), device=embedding_mask.device)], dim=1)  # bool -> float promotion
     fixed = sd["fixed_embedding.embedding.weight"][: embedding.shape[1]].unsqueeze(0).expand(b, -1, -1)
     if embedding_mask_proba > 0.0:
         if drop_mask is None:
             if embedding_mask_proba == 1:
-                drop_mask = torch.ones((b, 1, 1), dtype=torch.bool)
+                drop_mask = torch.ones((b, 1, 1), dtype=torch.bool, device=embedding.device)
             else:
-                drop_mask = torch.bernoulli(torch.full((b, 1, 1), embedding_mask_proba)).to(torch.bool)
+                drop_mask = torch.bernoulli(torch.full((b, 1, 1), embedding_mask_proba, device=embedding.device)).to(torch.bool)
         embedding = torch.where(drop_mask.view(b, 1, 1), fixed, embedding)
     kw = dict(causal=causal, taps=taps)
     if embedding_scale == 1.0:
