@@ -121,6 +121,8 @@ __device__ __forceinline__ void bar_sync_producers() { asm volatile("bar.sync 1,
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("fence.acq_rel.cta;\n\tbarrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -132,9 +134,9 @@ __device__ __forceinline__ uint32_t map_cluster(uint32_t saddr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
   return r;
 }
-__device__ __forceinline__ float ld_cluster_f32(uint32_t addr) {
-  float v;
-  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+__device__ __forceinline__ float4 ld_cluster_f32x4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
   return v;
 }
 
@@ -164,10 +166,6 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
   return d;
 }
 
-__device__ __forceinline__ float ldf_cg(const bf16* p) {
-  const unsigned short u = __ldcg(reinterpret_cast<const unsigned short*>(p));
-  return __uint_as_float((uint32_t)u << 16);
-}
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
@@ -239,9 +237,9 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
   float2* coef = reinterpret_cast<float2*>(tabs + pl.off_coef);            // [slots][ch_cap] (a, s): y = a*x + s
   const int ch_cap = pl.ch_cap;
   // epilogue scratch aliases the weight ring (all MMAs have completed by then)
-  float* sred = reinterpret_cast<float*>(a_ring);                          // [kMaxSlots][128][2]
-  float* rowred = sred + kMaxSlots * 128 * 2;                              // [4][cols_own][2]
-  float* part = reinterpret_cast<float*>(a_ring + kSredBytes + 4 * NT * 8);  // [NT][128] fp32 partial tile (SK > 1)
+  // [0, kSredBytes): per-warp GroupNorm fine-group sums; then the fp32 staging tile [columns][128] (the whole partial
+  // tile with split-K, one chunk of columns otherwise)
+  float* part = reinterpret_cast<float*>(a_ring + kSredBytes);
 
   if (tid == kProducers) {  // warp 4 lane 0
     for (int i = 0; i < pl.stages; ++i) {
@@ -270,7 +268,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
   if (tid == 0) TL_MARK(1);
 
   // weight-only / pre-chain values of the epilogue threads (thread == output channel of the M tile)
-  const float bias = (warp < 4 && p.bias) ? __ldg(p.bias + mt * 128 + tid) : 0.0f;
+  const float4 bias4 = (warp < 4 && p.bias) ? __ldg(reinterpret_cast<const float4*>(p.bias + mt * 128) + lane)
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
 
   if (warp == 4) {
     // ======================================================================== weight streamer
@@ -405,7 +404,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
       int rb = eb;
       if (rb >= p.res_bmod) rb -= p.res_bmod;
       colmeta[c] = make_int4(valid ? (eb * p.Lout + o) * p.Cout : -1, valid ? (rb * p.Lout + o) * p.Cout : 0,
-                             eb - b_first, eb);
+                             eb - b_first, valid ? eb * p.Lout + o : 0);
     }
     // weight-only halves of the affine coefficients: P = gamma*(1+film_scale), Q = beta*(1+film_scale) + film_shift
     // (the FiLM table and the conditioning rows are written before the step's kernel chain starts)
@@ -605,10 +604,19 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
           // items = (batch row, source, PAIR of fine groups): one 16-byte load brings both (sum, sumsq) pairs of an entry
           const int two_src = S0.s[1].C > 0 ? 1 : 0;
           const int nitem = nbl * (16 << two_src);
-          int parts = 1, lparts = 0;
-          while (parts < 16 && nitem * parts * 2 <= kProducers) {
-            parts *= 2;
-            ++lparts;
+          // an item's entries are split over `parts` lanes so that the whole reduction is (ideally) ONE batch of <= 12
+          // independent L2 loads per thread: minimise (passes over the thread block) x (load batches per thread)
+          int n_ent_max = S0.s[0].n_ent;
+          if (two_src && S0.s[1].n_ent > n_ent_max) n_ent_max = S0.s[1].n_ent;
+          int parts = 1, lparts = 0, best_cost = 1 << 30;
+          for (int lp = 0; lp <= 4; ++lp) {
+            const int pp = 1 << lp;
+            const int cost = ((nitem * pp + kProducers - 1) / kProducers) * ((n_ent_max + pp * 12 - 1) / (pp * 12));
+            if (cost < best_cost) {
+              best_cost = cost;
+              parts = pp;
+              lparts = lp;
+            }
           }
           for (int base = 0; base < nitem * parts; base += kProducers) {
             const int idx = base + tid;
@@ -721,35 +729,55 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
   }
 
   // ============================================================================================ epilogue
-  // Column slice of this CTA: the whole tile without split-K, else columns [cb, ce) of the tile.
+  // One code path for every case.  The fp32 accumulator tile leaves TMEM (lane == output channel) through a shared-
+  // memory staging tile [column][128 channels]; it is then finished "row-wise": a warp owns one output COLUMN per
+  // round and each lane 4 consecutive channels, so
+  //   * split-K partials of all cluster ranks are read with 16-byte DSMEM loads (rank order: deterministic),
+  //   * bias / GELU / residual / bf16 conversion work on 4 channels at a time and the store is one 256-byte
+  //     contiguous row segment per warp (the residual read likewise) instead of 2-byte scattered stores,
+  //   * GroupNorm fine-group partials are combined with a fixed shuffle pattern inside the warp and LayerNorm row
+  //     partials are a plain warp reduction.
+  // Without split-K the tile is staged in chunks of CH columns (what the ring can hold); with split-K every CTA stages
+  // its whole partial tile, one cluster barrier makes all of them visible, and each CTA finishes columns [cb, ce).
+  // Residual rows are prefetched four rounds ahead (the first four before the accumulator is even ready).
   const int cols_per = (SK > 1) ? (NT + SK - 1) / SK : NT;
   const int cb = (SK > 1) ? min(NT, sk * cols_per) : 0;
   const int ce = min(NT, cb + cols_per);
+  const int nr = (ce - cb + 3) >> 2;  // rounds: 4 columns (one per warp) each
   const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
   const bool want_stats = p.stats_out != nullptr;
   const bool want_rows = p.rowpart_out != nullptr;
   const int b_first_e = q0 / Lq;
   const int nb_out = min(p.B - 1, (q0 + NT - 1) / Lq) - b_first_e + 1;
-  const int gs = want_stats ? p.Cout / p.FGo : 128;  // channels per fine group of the output
+  const int gs = want_stats ? p.Cout / p.FGo : 128;  // channels per fine group of the output (4, 8, 16 or 32)
   const int ngl = 128 / gs;                           // fine groups inside this M tile
+  const int lpg = gs >> 2;                            // lanes per fine group
+  float* sfg = reinterpret_cast<float*>(a_ring);      // [4 warps][kMaxSlots][32 fine groups][2]  (kSredBytes)
+  const int CH = (SK > 1) ? NT : min(NT, ((pl.ring_bytes - kSredBytes) / 512) & ~15);  // staged columns per chunk
 
-  const int nch = mt * 128 + (tid & 127);  // output channel of an epilogue thread
-  // split-K: residual values of this CTA's first columns are fetched before the accumulators are even ready
-  unsigned short res_pre[4] = {0, 0, 0, 0};
-  if (SK > 1) {
-    if (warp < 4) {
-      if (p.res) {
+  const int wq = warp & 3, q4 = lane * 4;
+  const unsigned short* resp = reinterpret_cast<const unsigned short*>(p.res);
+  auto res_load = [&](int r) -> uint2 {
+    uint2 v = make_uint2(0u, 0u);
+    const int c = cb + r * 4 + wq;
+    if (resp && r < nr && c < ce) {
+      const int4 cm = colmeta[c];
+      if (cm.x >= 0) v = __ldcg(reinterpret_cast<const uint2*>(resp + (size_t)(uint32_t)cm.y + mt * 128 + q4));
+    }
+    return v;
+  };
+  uint2 rq[4] = {make_uint2(0u, 0u), make_uint2(0u, 0u), make_uint2(0u, 0u), make_uint2(0u, 0u)};
+  if (warp < 4) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (cb + j < ce) {
-            const int4 cm = colmeta[cb + j];
-            if (cm.x >= 0) res_pre[j] = __ldcg(reinterpret_cast<const unsigned short*>(p.res) + (size_t)(uint32_t)cm.y + nch);
-          }
-        }
-      }
-      mbar_wait(acc_full, 0);
-      tc_fence_after();
-      if (tid == 0) TL_MARK(6);
+    for (int u = 0; u < 4; ++u) rq[u] = res_load(u);
+    mbar_wait(acc_full, 0);  // every MMA has completed: the ring (now scratch) is free, the accumulator is final
+    tc_fence_after();
+    if (tid == 0) TL_MARK(6);
+    if (want_stats) {
+      float4* z = reinterpret_cast<float4*>(sfg);
+      for (int i = tid; i < kSredBytes / 16; i += kProducers) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (SK > 1) {
       for (int c0 = 0; c0 < NT; c0 += 16) {
         float v[16];
         tmem_ld16(trow + (uint32_t)c0, v);
@@ -757,285 +785,163 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
         for (int j = 0; j < 16; ++j) part[(size_t)(c0 + j) * 128 + tid] = v[j];
       }
     }
+  }
+  if (SK > 1) {
     if (tid == 0) TL_MARK(16);
     cluster_sync_all();  // every CTA's partial tile is visible cluster-wide
     if (tid == 0) TL_MARK(7);
   }
 
   if (warp < 4) {
-    const int cl = tid;
-    const int b_first = b_first_e;
-    const bool multi = nb_out > 1;  // the tile spans several batch rows: statistics are kept per slot
-    if (SK == 1) {  // the scratch below aliases the weight ring: every MMA must have completed first
-      mbar_wait(acc_full, 0);
-      tc_fence_after();
-      if (tid == 0) TL_MARK(6);
-    }
-    if (want_stats) {
-      for (int bl = 0; bl < nb_out && bl < kMaxSlots; ++bl) {
-        sred[((size_t)bl * 128 + cl) * 2] = 0.f;
-        sred[((size_t)bl * 128 + cl) * 2 + 1] = 0.f;
-      }
-    }
-    int sb = 0;  // slot of the statistics run in progress
-    float colS = 0.f, colQ = 0.f;
-    auto flush_stats = [&]() {
+    const uint32_t mine = smem_u32(part);
+    uint32_t part_remote[kMaxCluster];
+#pragma unroll
+    for (int s = 0; s < kMaxCluster; ++s) part_remote[s] = (s < SK && SK > 1) ? map_cluster(mine, (uint32_t)s) : mine;
+    int sb = -1;  // slot (batch row of the tile) of the statistics run in progress
+    float aS[4] = {0.f, 0.f, 0.f, 0.f}, aQ[4] = {0.f, 0.f, 0.f, 0.f};
+    auto flush_stats = [&]() {  // warp-uniform: the fine-group sums of this warp's run -> its own (warp, slot) cell
       if (want_stats && sb >= 0 && sb < nb_out && sb < kMaxSlots) {
-        sred[((size_t)sb * 128 + cl) * 2] += colS;
-        sred[((size_t)sb * 128 + cl) * 2 + 1] += colQ;
-      }
-      colS = 0.f;
-      colQ = 0.f;
-    };
-    // one finished output element: bias / GELU / residual, store, statistics
-    auto finish = [&](float acc, float resv, int ooff, int col, int colrel) {
-      if (multi) {
-        const int slot = colmeta[col].z;
-        if (slot != sb) {
-          flush_stats();
-          sb = slot;
+        float s1 = (aS[0] + aS[1]) + (aS[2] + aS[3]);
+        float s2 = (aQ[0] + aQ[1]) + (aQ[2] + aQ[3]);
+        for (int o = 1; o < lpg; o <<= 1) {
+          s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+          s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        if ((lane & (lpg - 1)) == 0) {
+          float2* d = reinterpret_cast<float2*>(sfg) + ((wq * kMaxSlots + sb) * 32 + lane / lpg);
+          *d = make_float2(d->x + s1, d->y + s2);
         }
       }
-      float x = 0.0f;
-      if (ooff >= 0) {
-        x = acc + bias;
-        if (p.epi_act == ACT_GELU) x = gelu_f(x);
-        x += resv;
-        if (A.out_f32) {
-          ((float*)p.out)[(size_t)(uint32_t)ooff + nch] = x;
-        } else {
-          ((bf16*)p.out)[(size_t)(uint32_t)ooff + nch] = __float2bfloat16_rn(x);
-        }
-      }
-      colS += x;
-      colQ = fmaf(x, x, colQ);
-      if (want_rows) {
-        const float rs = warp_sum(x), rq = warp_sum(x * x);
-        if (lane == 0) {
-          rowred[((size_t)warp * cols_per + colrel) * 2] = rs;
-          rowred[((size_t)warp * cols_per + colrel) * 2 + 1] = rq;
-        }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        aS[e] = 0.f;
+        aQ[e] = 0.f;
       }
     };
-    if (SK == 1) {
-      const bool lean = !want_rows && p.epi_act == ACT_NONE;
-      if (lean) {
-        // The common case (conv + bias + optional residual, bf16 out, one batch row per tile) with a minimal body per
-        // column: the fully unrolled general path is ~2 KB of code per column and would stream the whole loop from
-        // the instruction cache hierarchy on every chunk.  Chunks of 16 columns; the metadata + residual loads of
-        // chunk k+1 are in flight while chunk k is finished (the residual is kept as raw bf16 bits until it is
-        // used, so that issuing the loads never waits on them).
-        const unsigned short* resp = reinterpret_cast<const unsigned short*>(p.res);
-        bf16* outp = (bf16*)p.out + nch;
-        float* outf = (float*)p.out + nch;
-        int ooA[16], ooB[16];
-        unsigned short rvA[16], rvB[16];
-        int nextb = (b_first + 1) * Lq - q0;  // first column of the next batch row (slot 1)
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int4 cm = colmeta[j];
-          ooA[j] = cm.x;
-          rvA[j] = (resp && cm.x >= 0) ? __ldcg(resp + (size_t)(uint32_t)cm.y + nch) : (unsigned short)0;
-        }
-        for (int c0 = 0; c0 < NT; c0 += 16) {
-          if (c0 + 16 < NT) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int4 cm = colmeta[c0 + 16 + j];
-              ooB[j] = cm.x;
-              rvB[j] = (resp && cm.x >= 0) ? __ldcg(resp + (size_t)(uint32_t)cm.y + nch) : (unsigned short)0;
-            }
-          }
+    for (int cs = 0; cs < ce - cb; cs += CH) {  // one chunk with split-K
+      if (SK == 1) {
+        if (cs > 0) bar_sync_producers();  // the previous chunk has been consumed
+        const int cn = min(CH, NT - cs);
+        for (int c0 = 0; c0 < cn; c0 += 16) {
           float v[16];
-          tmem_ld16(trow + (uint32_t)c0, v);
-          if (nextb >= c0 + 16) {  // no batch-row boundary inside this chunk (CTA-uniform)
+          tmem_ld16(trow + (uint32_t)(cs + c0), v);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float x = 0.f;
-              if (ooA[j] >= 0) {
-                x = (v[j] + bias) + __uint_as_float((uint32_t)rvA[j] << 16);
-                if (A.out_f32) {
-                  outf[(size_t)(uint32_t)ooA[j]] = x;
-                } else {
-                  outp[(size_t)(uint32_t)ooA[j]] = __float2bfloat16_rn(x);
-                }
-              }
-              colS += x;
-              colQ = fmaf(x, x, colQ);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              if (c0 + j == nextb) {  // the statistics of the next batch row start here
-                flush_stats();
-                ++sb;
-                nextb += Lq;
-              }
-              float x = 0.f;
-              if (ooA[j] >= 0) {
-                x = (v[j] + bias) + __uint_as_float((uint32_t)rvA[j] << 16);
-                if (A.out_f32) {
-                  outf[(size_t)(uint32_t)ooA[j]] = x;
-                } else {
-                  outp[(size_t)(uint32_t)ooA[j]] = __float2bfloat16_rn(x);
-                }
-              }
-              colS += x;
-              colQ = fmaf(x, x, colQ);
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            ooA[j] = ooB[j];
-            rvA[j] = rvB[j];
-          }
+          for (int j = 0; j < 16; ++j) part[(size_t)(c0 + j) * 128 + tid] = v[j];
         }
-      } else {
-        // general path (GELU / fp32 out / per-row LayerNorm partials / several batch rows per tile): rolled over the
-        // columns of a chunk to keep it compact (these launches have few columns)
-        for (int c0 = 0; c0 < NT; c0 += 16) {
-          float v[16];
-          tmem_ld16(trow + (uint32_t)c0, v);
-#pragma unroll 1
-          for (int j = 0; j < 16; ++j) {
-            const int4 cm = colmeta[c0 + j];
-            const float resv = (p.res && cm.x >= 0) ? ldf_cg((const bf16*)p.res + (size_t)(uint32_t)cm.y + nch) : 0.f;
-            finish(v[j], resv, cm.x, c0 + j, c0 + j);
-          }
-        }
+        bar_sync_producers();
       }
-    } else {
-      // split-K: this CTA finishes columns [cb, ce) from the partial tiles of all cluster ranks (fixed order)
-      const uint32_t mine = smem_u32(part);
-      uint32_t part_remote[kMaxCluster];
-#pragma unroll
-      for (int s = 0; s < kMaxCluster; ++s) part_remote[s] = s < SK ? map_cluster(mine, (uint32_t)s) : mine;
-      const bool lean = !want_rows && p.epi_act == ACT_NONE;
-      if (lean) {
-        // four columns per round: 64 DSMEM loads in flight, minimal per-column code
-        bf16* outp = (bf16*)p.out + nch;
-        float* outf = (float*)p.out + nch;
-        const unsigned short* resp = reinterpret_cast<const unsigned short*>(p.res);
+      const int r_end = min(nr, (cs + CH) >> 2);
 #pragma unroll 1
-        for (int c = cb; c < ce; c += 4) {
-          int oo[4], sl[4];
-          unsigned short rr[4];
-          float tv[4][kMaxCluster];
+      for (int r0 = cs >> 2; r0 < r_end; r0 += 4) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            oo[j] = -1;
-            sl[j] = sb;
-            rr[j] = 0;
-            if (c + j < ce) {
-              const int4 cm = colmeta[c + j];
-              oo[j] = cm.x;
-              sl[j] = cm.z;
-              if (c == cb) {
-                rr[j] = res_pre[j];
-              } else if (resp && cm.x >= 0) {
-                rr[j] = __ldcg(resp + (size_t)(uint32_t)cm.y + nch);
+        for (int u = 0; u < 4; ++u) {
+          const int r = r0 + u;
+          if (r < r_end) {
+            const int c = cb + r * 4 + wq;
+            const uint2 rr = rq[u];
+            rq[u] = res_load(r + 4);
+            if (c < ce) {  // warp-uniform
+              const int4 cm = colmeta[c];
+              float4 acc;
+              if (SK == 1) {
+                acc = *reinterpret_cast<const float4*>(part + (size_t)(c - cs) * 128 + q4);
+              } else {
+                const uint32_t off = (uint32_t)((c * 128 + q4) * 4);
+                float4 tv[kMaxCluster];
+#pragma unroll
+                for (int s2 = 0; s2 < kMaxCluster; ++s2)
+                  if (s2 < SK) tv[s2] = ld_cluster_f32x4(part_remote[s2] + off);
+                acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int s2 = 0; s2 < kMaxCluster; ++s2)
+                  if (s2 < SK) {  // rank order: deterministic
+                    acc.x += tv[s2].x;
+                    acc.y += tv[s2].y;
+                    acc.z += tv[s2].z;
+                    acc.w += tv[s2].w;
+                  }
               }
-              const uint32_t off = (uint32_t)(((c + j) * 128 + cl) * 4);
-#pragma unroll
-              for (int s2 = 0; s2 < kMaxCluster; ++s2) tv[j][s2] = ld_cluster_f32(part_remote[s2] + off);
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (c + j < ce) {
-              float acc = 0.f;
-#pragma unroll
-              for (int s2 = 0; s2 < kMaxCluster; ++s2) acc += (s2 < SK) ? tv[j][s2] : 0.f;  // rank order: deterministic
-              if (multi && sl[j] != sb) {
+              if (cm.z != sb) {
                 flush_stats();
-                sb = sl[j];
+                sb = cm.z;
               }
-              float x = 0.f;
-              if (oo[j] >= 0) {
-                x = (acc + bias) + __uint_as_float((uint32_t)rr[j] << 16);
+              float x[4] = {0.f, 0.f, 0.f, 0.f};
+              if (cm.x >= 0) {
+                x[0] = acc.x + bias4.x;
+                x[1] = acc.y + bias4.y;
+                x[2] = acc.z + bias4.z;
+                x[3] = acc.w + bias4.w;
+                if (p.epi_act == ACT_GELU) {
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) x[e] = gelu_f(x[e]);
+                }
+                x[0] += __uint_as_float(rr.x << 16);
+                x[1] += __uint_as_float(rr.x & 0xffff0000u);
+                x[2] += __uint_as_float(rr.y << 16);
+                x[3] += __uint_as_float(rr.y & 0xffff0000u);
+                const size_t oo = (size_t)(uint32_t)cm.x + mt * 128 + q4;
                 if (A.out_f32) {
-                  outf[(size_t)(uint32_t)oo[j]] = x;
+                  *reinterpret_cast<float4*>((float*)p.out + oo) = make_float4(x[0], x[1], x[2], x[3]);
                 } else {
-                  outp[(size_t)(uint32_t)oo[j]] = __float2bfloat16_rn(x);
+                  *reinterpret_cast<uint2*>((bf16*)p.out + oo) = make_uint2(pack2(x[0], x[1]), pack2(x[2], x[3]));
                 }
               }
-              colS += x;
-              colQ = fmaf(x, x, colQ);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                aS[e] += x[e];
+                aQ[e] = fmaf(x[e], x[e], aQ[e]);
+              }
+              if (want_rows) {  // LayerNorm partial of this row over the 128 channels of the M tile
+                const float rs = warp_sum((x[0] + x[1]) + (x[2] + x[3]));
+                const float rq2 = warp_sum(fmaf(x[0], x[0], x[1] * x[1]) + fmaf(x[2], x[2], x[3] * x[3]));
+                if (lane == 0 && cm.x >= 0)
+                  *reinterpret_cast<float2*>(p.rowpart_out + ((size_t)(uint32_t)cm.w * pl.m_tiles + mt) * 2) = make_float2(rs, rq2);
+              }
             }
           }
-        }
-      } else {
-#pragma unroll 1
-        for (int c = cb; c < ce; ++c) {
-          const int4 cm = colmeta[c];
-          const int jr = c - cb;
-          const unsigned short rraw = jr == 0 ? res_pre[0] : (jr == 1 ? res_pre[1] : (jr == 2 ? res_pre[2] : res_pre[3]));
-          float resv = __uint_as_float((uint32_t)rraw << 16);
-          if (jr >= 4) resv = (p.res && cm.x >= 0) ? ldf_cg((const bf16*)p.res + (size_t)(uint32_t)cm.y + nch) : 0.f;
-          const uint32_t off = (uint32_t)((c * 128 + cl) * 4);
-          float tv[kMaxCluster];
-#pragma unroll
-          for (int s = 0; s < kMaxCluster; ++s) tv[s] = ld_cluster_f32(part_remote[s] + off);
-          float acc = 0.f;
-#pragma unroll
-          for (int s = 0; s < kMaxCluster; ++s) acc += (s < SK) ? tv[s] : 0.f;
-          finish(acc, resv, cm.x, c, jr);
         }
       }
     }
     flush_stats();
     if (tid == 0) TL_MARK(13);
-    if (want_stats || want_rows) bar_sync_producers();
-    if (want_stats) {
-      // per (batch row, fine group) partial of this CTA's columns -> entry (tile index within the batch row, split
-      // rank); the last tile of a batch row also zeroes the unused trailing entries so consumers sum a fixed n_ent.
-      const int n_ent = pl.E_max * p.nphase;  // E_max = tiles per batch row (max) * SK
-      for (int idx = tid; idx < nb_out * ngl; idx += kProducers) {
-        const int bl = idx / ngl, gl = idx - bl * ngl;
-        float a = 0.f, q = 0.f;
-        if (bl < kMaxSlots) {
-          for (int c = gl * gs; c < (gl + 1) * gs; ++c) {
-            a += sred[((size_t)bl * 128 + c) * 2];
-            q += sred[((size_t)bl * 128 + c) * 2 + 1];
-          }
-        }
-        const int bb = b_first + bl;
-        const int t_first = (bb * Lq) / NT;
-        int t_last = ((bb + 1) * Lq - 1) / NT;
-        if (t_last > pl.n_tiles - 1) t_last = pl.n_tiles - 1;
-        const int e = (nt - t_first) * SK + sk;
-        const int fg = (mt * 128) / gs + gl;
-        float* so = p.stats_out + (((size_t)bb * n_ent + (size_t)e * p.nphase + z) * p.FGo + fg) * 2;
-        so[0] = a;
-        so[1] = q;
-        if (nt == t_last) {
-          for (int e2 = e + SK; e2 < pl.E_max; e2 += SK) {
-            float* s2 = p.stats_out + (((size_t)bb * n_ent + (size_t)e2 * p.nphase + z) * p.FGo + fg) * 2;
-            s2[0] = 0.f;
-            s2[1] = 0.f;
-          }
+  }
+  // this CTA no longer reads remote partial tiles: arrive now, wait only before leaving (nobody may exit while its
+  // partial tile can still be read)
+  if (SK > 1) cluster_arrive_relaxed();
+  if (warp < 4 && want_stats) {
+    bar_sync_producers();
+    // per (batch row, fine group) partial of this CTA's columns -> entry (tile index within the batch row, split
+    // rank); the last tile of a batch row also zeroes the unused trailing entries so consumers sum a fixed n_ent.
+    const int n_ent = pl.E_max * p.nphase;  // E_max = tiles per batch row (max) * SK
+    for (int idx = tid; idx < nb_out * ngl; idx += kProducers) {
+      const int bl = idx / ngl, gl = idx - bl * ngl;
+      float a = 0.f, q = 0.f;
+      if (bl < kMaxSlots) {
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {  // warp order: deterministic
+          const float2 v = reinterpret_cast<const float2*>(sfg)[(w * kMaxSlots + bl) * 32 + gl];
+          a += v.x;
+          q += v.y;
         }
       }
-    }
-    if (want_rows) {
-      for (int col = cb + tid; col < ce; col += kProducers) {
-        const int4 cm = colmeta[col];
-        if (cm.x >= 0) {
-          float a = 0.f, qq = 0.f;
-          for (int w = 0; w < 4; ++w) {
-            a += rowred[((size_t)w * cols_per + (col - cb)) * 2];
-            qq += rowred[((size_t)w * cols_per + (col - cb)) * 2 + 1];
-          }
-          float* ro = p.rowpart_out + ((size_t)(cm.x / p.Cout) * pl.m_tiles + mt) * 2;
-          ro[0] = a;
-          ro[1] = qq;
+      const int bb = b_first_e + bl;
+      const int t_first = (bb * Lq) / NT;
+      int t_last = ((bb + 1) * Lq - 1) / NT;
+      if (t_last > pl.n_tiles - 1) t_last = pl.n_tiles - 1;
+      const int e = (nt - t_first) * SK + sk;
+      const int fg = (mt * 128) / gs + gl;
+      float* so = p.stats_out + (((size_t)bb * n_ent + (size_t)e * p.nphase + z) * p.FGo + fg) * 2;
+      *reinterpret_cast<float2*>(so) = make_float2(a, q);
+      if (nt == t_last) {
+        for (int e2 = e + SK; e2 < pl.E_max; e2 += SK) {
+          float* s2 = p.stats_out + (((size_t)bb * n_ent + (size_t)e2 * p.nphase + z) * p.FGo + fg) * 2;
+          *reinterpret_cast<float2*>(s2) = make_float2(0.f, 0.f);
         }
       }
     }
   }
-
   if (tid == 0) TL_MARK(14);
-  if (SK > 1) cluster_sync_all();  // nobody leaves while its partial tile may still be read remotely
+  if (SK > 1) cluster_wait();
 
   if (tid == 0) { TL_MARK(8); TL_GLOBAL(12); }
   tc_fence_before();
@@ -1152,7 +1058,7 @@ UmmaPlan conv_umma_plan(const ConvParams& p, bool want_stats, int num_sms) {
     // the epilogue scratch (+ the fp32 partial tile of the cluster reduction) aliases the ring
     const int budget = 110 * 1024;
     int stages = (budget - 2 * c.panel_bytes - misc) / kABytes;
-    const int scratch = kSredBytes + 4 * NT * 8 + (sk > 1 ? NT * 512 : 0);
+    const int scratch = kSredBytes + (sk > 1 ? NT * 512 : 16 * 512);  // statistics cells + staging tile (see the epilogue)
     if (stages < 2) stages = 2;
     if (stages > 6) stages = 6;
     c.stages = stages;
