@@ -52,6 +52,19 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// GroupNorm statistics side channel: (sum, sumsq) per (batch row, fine group) accumulated by every producer CTA with
+// 64-bit FIXED-POINT atomics (scale 2^26).  Integer addition is associative, so the result is bit-identical whatever
+// order the CTAs arrive in (deterministic without a reduction pass), the adds are fire-and-forget (no return value ->
+// no latency on the producer side), and a consumer reads 16 bytes per fine group instead of reducing one entry per
+// producer tile.  Range: |sum| < 2^63 / 2^26 = 1.4e11; resolution 1.5e-8 per add (below fp32 rounding of the partial).
+constexpr float kStatScale = 67108864.0f;
+constexpr double kStatInv = 1.0 / 67108864.0;
+__device__ __forceinline__ void stat_add(long long* p, float v) {
+  atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)__float2ll_rn(v * kStatScale));
+}
+__device__ __forceinline__ float stat_get(long long v) { return (float)((double)v * kStatInv); }
+__device__ __forceinline__ double stat_get_d(long long v) { return (double)v * kStatInv; }
+
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 }  // namespace jen1

@@ -21,7 +21,6 @@ __global__ void __launch_bounds__(NT) conv_generic_kernel(const ConvParams p) {
   __shared__ __align__(16) float As[2][TK][LDA];
   __shared__ __align__(16) float Bs[2][TK][LDB];
   __shared__ double fine[2][32][2];
-  __shared__ double finep[4][64][2];
   __shared__ float gmean[32], grstd[32];
   __shared__ float rmu[TM], rrs[TM];
 
@@ -38,29 +37,18 @@ __global__ void __launch_bounds__(NT) conv_generic_kernel(const ConvParams p) {
   // ------------------------------------------------------------------ prologue coefficients
   if (p.mode == PRO_AFFINE) {
     if (p.G > 0) {
-      {  // reduce the producer's per-tile partial statistics (fixed order => deterministic)
-        const int idx = tid & 63, part = tid >> 6;
-        const int s = idx >> 5, fg = idx & 31;
-        const ConvSrc& sr = s0.s[s];
+      if (tid < 64) {  // the producers' fixed-point accumulators (order-independent => deterministic)
+        const int sI = tid >> 5, fg = tid & 31;
+        const ConvSrc& sr = s0.s[sI];
         double a = 0.0, q = 0.0;
         if (sr.C > 0 && fg < sr.FG) {
-          const float* st = sr.stats + (size_t)(b % sr.bmod) * sr.n_ent * sr.FG * 2;
-          for (int e = part; e < sr.n_ent; e += 4) {
-            a += (double)st[(e * sr.FG + fg) * 2];
-            q += (double)st[(e * sr.FG + fg) * 2 + 1];
-          }
+          const long long* st = sr.stats + ((size_t)(b % sr.bmod) * sr.FG + fg) * 2;
+          a = stat_get_d(st[0]);
+          q = stat_get_d(st[1]);
         }
-        finep[part][idx][0] = a;
-        finep[part][idx][1] = q;
-      }
-      __syncthreads();
-      if (tid < 64) {
-        const int s = tid >> 5, fg = tid & 31;
-        const double sc = (double)s0.s[s].scale;
-        double a = ((finep[0][tid][0] + finep[1][tid][0]) + finep[2][tid][0]) + finep[3][tid][0];
-        double q = ((finep[0][tid][1] + finep[1][tid][1]) + finep[2][tid][1]) + finep[3][tid][1];
-        fine[s][fg][0] = a * sc;
-        fine[s][fg][1] = q * sc * sc;
+        const double sc = (double)sr.scale;
+        fine[sI][fg][0] = a * sc;
+        fine[sI][fg][1] = q * sc * sc;
       }
       __syncthreads();
       if (tid < p.G) {
@@ -274,7 +262,7 @@ __global__ void __launch_bounds__(NT) conv_generic_kernel(const ConvParams p) {
     }
   }
 
-  if (p.stats_out) {  // per-tile GroupNorm partials of the output at fine-group granularity, fixed-order reduce
+  if (p.stats_out) {  // GroupNorm partials of this tile at fine-group granularity -> fixed-point accumulators
     float* part = &As[0][0][0];  // [16][64][2] floats = 8 KB (main loop is finished with As)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -303,11 +291,9 @@ __global__ void __launch_bounds__(NT) conv_generic_kernel(const ConvParams p) {
           a += csum[c * 2];
           q += csum[c * 2 + 1];
         }
-        const int n_ent = gridDim.x * p.nphase;
-        const int ent = blockIdx.x * p.nphase + z;
-        float* so = p.stats_out + (((size_t)b * n_ent + ent) * p.FGo + fg) * 2;
-        so[0] = a;
-        so[1] = q;
+        long long* so = p.stats_out + ((size_t)b * p.FGo + fg) * 2;
+        stat_add(so, a);
+        stat_add(so + 1, q);
       }
     }
     __syncthreads();

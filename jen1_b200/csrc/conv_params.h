@@ -24,10 +24,9 @@ namespace jen1 {
 
 struct ConvSrc {
   const void* ptr;     // T [Bsrc][L][C] channels-last
-  const float* stats;  // [Bsrc][n_ent][FG][2] (sum, sumsq) partials of this tensor, or nullptr
+  const long long* stats;  // [Bsrc][FG][2] fixed-point (sum, sumsq) accumulators of this tensor (common.cuh), or nullptr
   int C;               // channels (0 = source absent)
   int FG;              // fine groups in `stats`
-  int n_ent;           // partial entries per batch row
   int bmod;            // batch row used = b % bmod
   float scale;         // raw values are multiplied by this (skip scale 2^-1/2, reference blocks.py:734)
 };
@@ -72,7 +71,7 @@ struct ConvParams {
   int res_bmod;
   void* out;           // TO [B][Lout][Cout]          (exactly one of out / out_ncl is set)
   float* out_ncl;      // fp32 [B][Cout][Lout]
-  float* stats_out;    // [B][n_ent_out][FGo][2] or nullptr;  n_ent_out = gridDim.x * nphase
+  long long* stats_out;  // [B][FGo][2] fixed-point accumulators (zeroed by the host before the launch chain) or nullptr
   int FGo;
   float* rowpart_out;  // [B][Lout][gridDim.y][2] or nullptr
 };

@@ -601,79 +601,22 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
         //      fine-group sums of every (batch row, source, fine group) item from the producer's partial entries (an item
         //      is split over `parts` lanes combined by shuffles in a fixed order), then one thread per group.
         if (has_gn) {
-          // items = (batch row, source, PAIR of fine groups): one 16-byte load brings both (sum, sumsq) pairs of an entry
+          // one item per (batch row, source, fine group): a single 16-byte load of the producers' fixed-point
+          // accumulators (common.cuh) -- no per-tile entries to reduce
           const int two_src = S0.s[1].C > 0 ? 1 : 0;
-          const int nitem = nbl * (16 << two_src);
-          // an item's entries are split over `parts` lanes so that the whole reduction is (ideally) ONE batch of <= 12
-          // independent L2 loads per thread: minimise (passes over the thread block) x (load batches per thread)
-          int n_ent_max = S0.s[0].n_ent;
-          if (two_src && S0.s[1].n_ent > n_ent_max) n_ent_max = S0.s[1].n_ent;
-          int parts = 1, lparts = 0, best_cost = 1 << 30;
-          for (int lp = 0; lp <= 4; ++lp) {
-            const int pp = 1 << lp;
-            const int cost = ((nitem * pp + kProducers - 1) / kProducers) * ((n_ent_max + pp * 12 - 1) / (pp * 12));
-            if (cost < best_cost) {
-              best_cost = cost;
-              parts = pp;
-              lparts = lp;
+          const int nitem = nbl * (32 << two_src);
+          for (int idx = tid; idx < nitem; idx += kProducers) {
+            const int bl = idx >> (5 + two_src), fs = two_src ? (idx >> 5) & 1 : 0, fg = idx & 31;
+            const ConvSrc& fsr = S0.s[fs];
+            float2 v = make_float2(0.f, 0.f);
+            if (fsr.C > 0 && fg < fsr.FG) {
+              int b = b_first + bl;
+              if (b >= fsr.bmod) b -= fsr.bmod;
+              const longlong2 acc = __ldcg(reinterpret_cast<const longlong2*>(fsr.stats + ((size_t)b * fsr.FG + fg) * 2));
+              const float sc = fsr.scale;
+              v = make_float2(stat_get(acc.x) * sc, stat_get(acc.y) * sc * sc);
             }
-          }
-          for (int base = 0; base < nitem * parts; base += kProducers) {
-            const int idx = base + tid;
-            const int item = idx >> lparts, part_i = idx & (parts - 1);
-            const int bl = item >> (4 + two_src), fs = two_src ? (item >> 4) & 1 : 0, pi = item & 15;
-            float a0 = 0.f, q0s = 0.f, a1 = 0.f, q1s = 0.f;
-            if (item < nitem) {
-              const ConvSrc& fsr = S0.s[fs];
-              if (fsr.C > 0 && 2 * pi < fsr.FG) {
-                int b = b_first + bl;
-                if (b >= fsr.bmod) b -= fsr.bmod;
-                const float* st = fsr.stats + ((size_t)b * fsr.n_ent * fsr.FG + 2 * pi) * 2;
-                if (fsr.FG >= 2) {
-                  for (int e0 = part_i; e0 < fsr.n_ent; e0 += parts * 12) {  // 12 independent 16-byte L2 loads in flight
-                    float4 buf[12];
-#pragma unroll
-                    for (int u = 0; u < 12; ++u) {
-                      const int e = e0 + u * parts;
-                      buf[u] = e < fsr.n_ent ? __ldcg(reinterpret_cast<const float4*>(st + (size_t)e * fsr.FG * 2))
-                                             : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-#pragma unroll
-                    for (int u = 0; u < 12; ++u) {
-                      a0 += buf[u].x;
-                      q0s += buf[u].y;
-                      a1 += buf[u].z;
-                      q1s += buf[u].w;
-                    }
-                  }
-                } else {  // a single whole-tensor group (boundary tensors)
-                  for (int e0 = part_i; e0 < fsr.n_ent; e0 += parts * 12) {
-                    float2 buf[12];
-#pragma unroll
-                    for (int u = 0; u < 12; ++u) {
-                      const int e = e0 + u * parts;
-                      buf[u] = e < fsr.n_ent ? __ldcg(reinterpret_cast<const float2*>(st + (size_t)e * fsr.FG * 2)) : make_float2(0.f, 0.f);
-                    }
-#pragma unroll
-                    for (int u = 0; u < 12; ++u) {
-                      a0 += buf[u].x;
-                      q0s += buf[u].y;
-                    }
-                  }
-                }
-              }
-            }
-            for (int o = 1; o < parts; o <<= 1) {
-              a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-              q0s += __shfl_xor_sync(0xffffffffu, q0s, o);
-              a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-              q1s += __shfl_xor_sync(0xffffffffu, q1s, o);
-            }
-            if (item < nitem && part_i == 0) {
-              const float sc = S0.s[fs].scale;
-              float4* fo = reinterpret_cast<float4*>(fine + ((bl * 2 + fs) * 32 + 2 * pi) * 2);
-              *fo = make_float4(a0 * sc, q0s * sc * sc, a1 * sc, q1s * sc * sc);
-            }
+            *reinterpret_cast<float2*>(fine + ((bl * 2 + fs) * 32 + fg) * 2) = v;
           }
           bar_sync_producers();
           // pass 2: one thread per (batch row, group)
@@ -910,34 +853,21 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
   if (SK > 1) cluster_arrive_relaxed();
   if (warp < 4 && want_stats) {
     bar_sync_producers();
-    // per (batch row, fine group) partial of this CTA's columns -> entry (tile index within the batch row, split
-    // rank); the last tile of a batch row also zeroes the unused trailing entries so consumers sum a fixed n_ent.
-    const int n_ent = pl.E_max * p.nphase;  // E_max = tiles per batch row (max) * SK
+    // per (batch row, fine group) partial of this CTA's columns -> fixed-point accumulators (fire-and-forget atomics)
     for (int idx = tid; idx < nb_out * ngl; idx += kProducers) {
       const int bl = idx / ngl, gl = idx - bl * ngl;
       float a = 0.f, q = 0.f;
       if (bl < kMaxSlots) {
 #pragma unroll
-        for (int w = 0; w < 4; ++w) {  // warp order: deterministic
+        for (int w = 0; w < 4; ++w) {
           const float2 v = reinterpret_cast<const float2*>(sfg)[(w * kMaxSlots + bl) * 32 + gl];
           a += v.x;
           q += v.y;
         }
       }
-      const int bb = b_first_e + bl;
-      const int t_first = (bb * Lq) / NT;
-      int t_last = ((bb + 1) * Lq - 1) / NT;
-      if (t_last > pl.n_tiles - 1) t_last = pl.n_tiles - 1;
-      const int e = (nt - t_first) * SK + sk;
-      const int fg = (mt * 128) / gs + gl;
-      float* so = p.stats_out + (((size_t)bb * n_ent + (size_t)e * p.nphase + z) * p.FGo + fg) * 2;
-      *reinterpret_cast<float2*>(so) = make_float2(a, q);
-      if (nt == t_last) {
-        for (int e2 = e + SK; e2 < pl.E_max; e2 += SK) {
-          float* s2 = p.stats_out + (((size_t)bb * n_ent + (size_t)e2 * p.nphase + z) * p.FGo + fg) * 2;
-          *reinterpret_cast<float2*>(s2) = make_float2(0.f, 0.f);
-        }
-      }
+      long long* so = p.stats_out + ((size_t)(b_first_e + bl) * p.FGo + (mt * 128) / gs + gl) * 2;
+      stat_add(so, a);
+      stat_add(so + 1, q);
     }
   }
   if (tid == 0) TL_MARK(14);
@@ -1041,7 +971,6 @@ UmmaPlan conv_umma_plan(const ConvParams& p, bool want_stats, int num_sms) {
     if (need_coef && nslot * ch_cap_of(sk) * 8 > coef_budget) return false;
     c.splitk = sk;
     c.ch_cap = ch_cap_of(sk);
-    c.E_max = ((c.Lq - 1) / NT + 2) * sk;
     // tables
     const int rows0 = f * c.R;
     int off = rows0 * 16;
@@ -1096,7 +1025,6 @@ UmmaPlan conv_umma_plan(const ConvParams& p, bool want_stats, int num_sms) {
     double t = steps * (0.6 + 0.15 * rows / 16.0);      // K loop: fixed round trip + panel rows
     t += (wkb > prefetch ? (wkb - prefetch) / 60.0 : 0.0);  // weight bytes beyond the PDL prefetch at ~60 GB/s per SM
     t += (c.splitk > 1 ? 0.12 * cols + 0.6 : 0.04 * cols);  // epilogue columns (DSMEM reduction vs TMEM), cluster exchange
-    t += 0.01 * (double)c.E_max;                        // statistics entries the consumer must reduce
     return t * waves * over_mul + over_add;
   };
   static const int cand[] = {16, 32, 48, 64, 96, 128, 192, 256};

@@ -422,10 +422,28 @@ Act Engine::new_act(int Bt, int L, int C, bool f32) {
 // 4+4 split of GN(8) over a channel concat); narrow tensors (C | 64) keep one whole-tensor group (GN(1) only).
 static int fine_groups(int C) { return (C % 32 == 0) ? 32 : ((C > 0 && 64 % C == 0) ? 1 : 0); }
 
-void Engine::add_stats(Act& a, int n_ent) {
+// GroupNorm statistics accumulators live in one contiguous zone per forward so that a single memset (one graph node)
+// zeroes them before the launch chain starts; the dry run sizes the zone.
+void* Engine::salloc(size_t bytes) {
+  const size_t a = (szone_off_ + 15) & ~(size_t)15;
+  szone_off_ = a + bytes;
+  if (dry_) return (void*)(uintptr_t)(a + 256);
+  if (szone_off_ > szone_cap_) {
+    fail("internal: statistics zone overflow");
+    return szone_;
+  }
+  return szone_ + a;
+}
+bool Engine::begin_stats_zone(cudaStream_t st) {
+  szone_cap_ = (szone_need_ + 255) & ~(size_t)255;
+  szone_ = (char*)aalloc(szone_cap_);
+  szone_off_ = 0;
+  if (!ok_) return false;
+  return ck(cudaMemsetAsync(szone_, 0, szone_cap_, st), "memset(statistics zone)");
+}
+void Engine::add_stats(Act& a) {
   a.FG = fine_groups(a.C);
-  a.n_ent = n_ent;
-  a.stats = (float*)aalloc((size_t)a.Bt * n_ent * a.FG * 2 * sizeof(float));
+  a.stats = (long long*)salloc((size_t)a.Bt * a.FG * 2 * sizeof(long long));
 }
 void Engine::add_rowpart(Act& a, int nct) {
   a.rp_nct = nct;
@@ -497,7 +515,6 @@ static ConvSrc make_src(const Act* a, float scale) {
     s.stats = a->stats;
     s.C = a->C;
     s.FG = a->FG;
-    s.n_ent = a->n_ent;
     s.bmod = a->Bt;
     s.scale = scale;
   }
@@ -619,7 +636,7 @@ Act Engine::conv_build(const DConv& W, int Bout, const Act& a0, const Act* a1, f
   } else {
     p.res_bmod = 1;
   }
-  const int TMr = conv_generic_row_tile(), TNc = conv_generic_col_tile();
+  const int TNc = conv_generic_col_tile();
   const bool out_is_f32 = o.out_f32 || dtype_ == JEN1_DTYPE_F32;
   if (o.want_stats && fine_groups(W.Cout) == 0) {
     fail("statistics requested for an unsupported channel count (need C % 32 == 0 or C | 64)");
@@ -645,7 +662,7 @@ Act Engine::conv_build(const DConv& W, int Bout, const Act& a0, const Act* a1, f
     out = new_act(Bout, o.Lout, W.Cout, o.out_f32);
   }
   if (o.want_stats) {
-    add_stats(out, plan.ok ? plan.E_max * o.nphase : cdivi(o.Lm, TMr) * o.nphase);
+    add_stats(out);
     p.stats_out = out.stats;
   }
   if (o.want_rowpart) {
@@ -922,12 +939,10 @@ bool Engine::unet(const Act& xpk, const Act& ccpk, int B, int B2, int T, bool ca
 }
 
 bool Engine::pack_inputs(const float* x, int B, int T, Act* xpk, bool with_cc, const float* cc, Act* ccpk) {
-  const int pr = pack_rows_per_entry();
   auto one = [&](const float* src, int C, int Cp, Act* a) {
     *a = new_act(B, T, Cp);
     a->FG = 1;
-    a->n_ent = cdivi(T, pr);
-    a->stats = (float*)aalloc((size_t)B * a->n_ent * 2 * sizeof(float));
+    a->stats = (long long*)salloc((size_t)B * 2 * sizeof(long long));
     if (dry_ || !ok_) return;
     cudaError_t e = (dtype_ == JEN1_DTYPE_F32) ? launch_pack_ncl<float>(src, (float*)a->ptr, a->stats, B, C, Cp, T, st_)
                                                : launch_pack_ncl<bf16>(src, (bf16*)a->ptr, a->stats, B, C, Cp, T, st_);
@@ -1085,10 +1100,12 @@ size_t Engine::workspace_bytes(int B, int T) {
   dry_ = true;
   ok_ = true;
   arena_off_ = 0;
+  szone_off_ = 0;
   Act xpk, ccpk, y;
   pack_inputs(nullptr, B, T, &xpk, true, nullptr, &ccpk);
   unet(xpk, ccpk, B, 2 * B, T, false, &y);
-  const size_t need = arena_off_ + 4096;
+  szone_need_ = szone_off_ + 256;
+  const size_t need = arena_off_ + szone_need_ + 8192;
   dry_ = false;
   arena_off_ = off0;
   ctx_B_ = cb;
@@ -1148,6 +1165,7 @@ int Engine::forward(const float* x, const float* cc, const int32_t* cond_rows, c
   if (!upload_ctl(c, st)) return 1;
   if (drop && !ck(cudaMemcpyAsync(d_ctl_->drop, drop, (size_t)B, cudaMemcpyDeviceToDevice, st), "memcpy drop")) return 1;
   Act xpk, ccpk, y;
+  if (!begin_stats_zone(st)) return 1;
   if (!pack_inputs(x, B, T, &xpk, true, cc, &ccpk)) return 1;
   if (!unet(xpk, ccpk, B, B2, T, causal != 0, &y)) return 1;
   tap("y", y);
@@ -1247,17 +1265,17 @@ int Engine::sample_begin(const float* coef_host, int S, const float* cc, int B, 
   st_ = st;
   dry_ = false;
   arena_off_ = 0;
-  const int pr = pack_rows_per_entry();
   smp_.ccpk = new_act(B, T, cc_pad_);
   smp_.ccpk.FG = 1;
-  smp_.ccpk.n_ent = cdivi(T, pr);
-  smp_.ccpk.stats = (float*)aalloc((size_t)B * smp_.ccpk.n_ent * 2 * sizeof(float));
+  smp_.ccpk.stats = (long long*)aalloc((size_t)B * 2 * sizeof(long long));  // persistent: outside the per-step zone
+  if (!ck(cudaMemsetAsync(smp_.ccpk.stats, 0, (size_t)B * 2 * sizeof(long long), st), "memset(cc statistics)")) return 1;
   cudaError_t e = (dtype_ == JEN1_DTYPE_F32)
                       ? launch_pack_ncl<float>(cc, (float*)smp_.ccpk.ptr, smp_.ccpk.stats, B, d_.context_channels, cc_pad_, T, st)
                       : launch_pack_ncl<bf16>(cc, (bf16*)smp_.ccpk.ptr, smp_.ccpk.stats, B, d_.context_channels, cc_pad_, T, st);
   ++launches_;
   if (!ck(e, "pack(cc)")) return 1;
   smp_.arena_base = arena_off_;
+  smp_.szone_need = szone_need_;
   smp_.active = true;
   if (!smp_.exec) {
     smp_.g_x = nullptr;
@@ -1290,6 +1308,8 @@ int Engine::sample_step(int step, float* x, const float* noise, const uint8_t* d
     arena_off_ = smp_.arena_base;
     tl_ops_ = 0;
     Act xpk, y, unused;
+    szone_need_ = smp_.szone_need;
+    if (!begin_stats_zone(st)) return false;
     if (!pack_inputs(x, B, T, &xpk, false, nullptr, &unused)) return false;
     if (!unet(xpk, smp_.ccpk, B, B2, T, smp_.causal != 0, &y)) return false;
     SamplerParams sp;

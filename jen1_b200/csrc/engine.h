@@ -71,8 +71,8 @@ struct DUp {
 struct Act {  // channels-last activation [Bt][L][C] in the arena
   void* ptr = nullptr;
   int Bt = 0, L = 0, C = 0;
-  float* stats = nullptr;  // GroupNorm partials [Bt][n_ent][FG][2]
-  int FG = 0, n_ent = 0;
+  long long* stats = nullptr;  // GroupNorm statistics [Bt][FG][2], fixed-point accumulators (common.cuh)
+  int FG = 0;
   float* rowpart = nullptr;  // LayerNorm partials [Bt][L][rp_nct][2]
   int rp_nct = 0;
   bool f32 = false;
@@ -129,7 +129,9 @@ class Engine {
   // ---- arena
   void* aalloc(size_t bytes);
   Act new_act(int Bt, int L, int C, bool f32 = false);
-  void add_stats(Act& a, int n_ent);
+  void add_stats(Act& a);
+  void* salloc(size_t bytes);  // from the per-forward statistics zone (zeroed by one memset before the launch chain)
+  bool begin_stats_zone(cudaStream_t st);
   void add_rowpart(Act& a, int nct);
   size_t esz() const { return dtype_ == JEN1_DTYPE_F32 ? 4 : 2; }
 
@@ -216,6 +218,8 @@ class Engine {
   // arena
   char* arena_ = nullptr;
   size_t arena_cap_ = 0, arena_off_ = 0;
+  char* szone_ = nullptr;          // statistics zone of the forward in progress (inside the arena)
+  size_t szone_off_ = 0, szone_cap_ = 0, szone_need_ = 0;  // szone_need_: bytes the last dry run asked for
   bool dry_ = false;
   cudaStream_t st_ = nullptr;
   bool ok_ = true;
@@ -234,6 +238,7 @@ class Engine {
     float* cc_copy = nullptr;  // persistent packed concat-cond lives at the arena base
     Act ccpk;
     size_t arena_base = 0;
+    size_t szone_need = 0;  // statistics-zone bytes of one step (from the dry run of sample_begin)
     cudaGraphExec_t exec = nullptr;
     float* g_x = nullptr;
     const float* g_noise = nullptr;

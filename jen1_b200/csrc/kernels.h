@@ -30,7 +30,6 @@ struct UmmaPlan {
   int R, PS, panel_bytes; // panel rows, rows per sub-panel, bytes of one panel (all sub-panels)
   int steps0, steps1;     // 64-channel K blocks of segment 0 / 1
   int stages, tmem_cols;
-  int E_max;              // GroupNorm partial entries per batch row (per phase) this launch writes (N tiles x splitk)
   int ring_bytes;         // weight ring (also the epilogue scratch / partial tile)
   int ch_cap;             // seg-0 input channels one CTA may own (coefficient-table stride)
   int off_rowmeta1, off_colmeta, off_rowstat, off_coef;  // shared-memory table offsets
@@ -46,10 +45,9 @@ cudaError_t launch_conv_umma(const ConvParams& p, const UmmaPlan& plan, const vo
                              bool out_f32, bool pdl, cudaStream_t stream, long long* timeline = nullptr);
 
 // ---- boundary: [Bx][C][L] fp32 (reference layout) -> channels-last T [Bx][L][Cp] (channels C..Cp-1 zero-filled so
-//      rows stay 16-byte aligned for the tcgen05 path) + GroupNorm partials (FG = 1)
+//      rows stay 16-byte aligned for the tcgen05 path) + GroupNorm statistics (FG = 1, fixed-point accumulators [Bx][1][2])
 template <typename T>
-cudaError_t launch_pack_ncl(const float* x, T* out, float* stats, int Bx, int C, int Cp, int L, cudaStream_t stream);
-int pack_rows_per_entry();
+cudaError_t launch_pack_ncl(const float* x, T* out, long long* stats, int Bx, int C, int Cp, int L, cudaStream_t stream);
 
 // ---- per-row (sum, sumsq) of a [R][C] matrix -> rowpart [R][1][2]
 template <typename T>

@@ -17,7 +17,7 @@ int pack_rows_per_entry() { return PK_ROWS; }
 
 template <typename T>
 __global__ void __launch_bounds__(256) pack_ncl_kernel(const float* __restrict__ x, T* __restrict__ out,
-                                                      float* __restrict__ stats, int C, int Cp, int L) {
+                                                      long long* __restrict__ stats, int C, int Cp, int L) {
   extern __shared__ float tile[];  // [PK_ROWS][C + 1]
   __shared__ float red[8][2];
   const int b = blockIdx.y, l0 = blockIdx.x * PK_ROWS;
@@ -48,21 +48,20 @@ __global__ void __launch_bounds__(256) pack_ncl_kernel(const float* __restrict__
       a += red[w][0];
       qq += red[w][1];
     }
-    float* so = stats + ((size_t)b * gridDim.x + blockIdx.x) * 2;
-    so[0] = a;
-    so[1] = qq;
+    stat_add(stats + (size_t)b * 2, a);
+    stat_add(stats + (size_t)b * 2 + 1, qq);
   }
 }
 
 template <typename T>
-cudaError_t launch_pack_ncl(const float* x, T* out, float* stats, int Bx, int C, int Cp, int L, cudaStream_t stream) {
+cudaError_t launch_pack_ncl(const float* x, T* out, long long* stats, int Bx, int C, int Cp, int L, cudaStream_t stream) {
   dim3 grid((L + PK_ROWS - 1) / PK_ROWS, Bx);
   size_t smem = (size_t)PK_ROWS * (C + 1) * sizeof(float);
   pack_ncl_kernel<T><<<grid, 256, smem, stream>>>(x, out, stats, C, Cp, L);
   return cudaGetLastError();
 }
-template cudaError_t launch_pack_ncl<float>(const float*, float*, float*, int, int, int, int, cudaStream_t);
-template cudaError_t launch_pack_ncl<bf16>(const float*, bf16*, float*, int, int, int, int, cudaStream_t);
+template cudaError_t launch_pack_ncl<float>(const float*, float*, long long*, int, int, int, int, cudaStream_t);
+template cudaError_t launch_pack_ncl<bf16>(const float*, bf16*, long long*, int, int, int, int, cudaStream_t);
 
 // =====================================================================================================
 // per-row (sum, sumsq): one warp per row
