@@ -106,6 +106,7 @@ int64_t jen1_engine_launch_count(void* handle);        /* kernels launched (or r
 int64_t jen1_engine_weight_bytes(void* handle);        /* device bytes of packed weights streamed per step */
 int64_t jen1_engine_umma_launch_count(void* handle);   /* how many of those launches were the tcgen05 conv kernel */
 int64_t jen1_engine_umma_attn_launch_count(void* handle); /* ... and the tcgen05 attention kernel */
+int64_t jen1_engine_fused_transformer_launch_count(void* handle); /* ... and the fused Transformer1d kernel (tcgen05 linears + attention) */
 int jen1_engine_debug_tensor(void* handle, const char* name, float* host_out, int64_t capacity, int64_t* shape3);
 
 #ifdef __cplusplus

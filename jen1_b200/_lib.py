@@ -47,6 +47,7 @@ SIGNATURES = {
     "jen1_engine_weight_bytes": (C.c_int64, [C.c_void_p]),
     "jen1_engine_umma_launch_count": (C.c_int64, [C.c_void_p]),
     "jen1_engine_umma_attn_launch_count": (C.c_int64, [C.c_void_p]),
+    "jen1_engine_fused_transformer_launch_count": (C.c_int64, [C.c_void_p]),
     "jen1_engine_debug_tensor": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
 }
 

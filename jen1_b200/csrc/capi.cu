@@ -123,6 +123,7 @@ int64_t jen1_engine_launch_count(void* h) { return h ? E(h)->launch_count() : 0;
 int64_t jen1_engine_weight_bytes(void* h) { return h ? E(h)->weight_bytes() : 0; }
 int64_t jen1_engine_umma_launch_count(void* h) { return h ? E(h)->umma_launch_count() : 0; }
 int64_t jen1_engine_umma_attn_launch_count(void* h) { return h ? E(h)->umma_attn_launch_count() : 0; }
+int64_t jen1_engine_fused_transformer_launch_count(void* h) { return h ? E(h)->fused_tr_launch_count() : 0; }
 
 int jen1_engine_debug_tensor(void* h, const char* name, float* host_out, int64_t capacity, int64_t* shape3) {
   if (!h || !name || !host_out || !shape3) return 1;

@@ -672,21 +672,22 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
   }
 
   // ============================================================================================ epilogue
-  // One code path for every case.  The fp32 accumulator tile leaves TMEM (lane == output channel) through a shared-
-  // memory staging tile [column][128 channels]; it is then finished "row-wise": a warp owns one output COLUMN per
-  // round and each lane 4 consecutive channels, so
+  // One COMPACT code path for every case (the instruction cache is 32 KB per SM and this code runs once per CTA: rolled
+  // loops, no per-case copies).  The fp32 accumulator tile leaves TMEM (lane == output channel) through a shared-memory
+  // staging tile [column][128 channels]; it is then finished "row-wise": a warp owns one output COLUMN per round and each
+  // lane 4 consecutive channels, so
   //   * split-K partials of all cluster ranks are read with 16-byte DSMEM loads (rank order: deterministic),
   //   * bias / GELU / residual / bf16 conversion work on 4 channels at a time and the store is one 256-byte
-  //     contiguous row segment per warp (the residual read likewise) instead of 2-byte scattered stores,
+  //     contiguous row segment per warp instead of 2-byte scattered stores,
+  //   * the residual rows arrive through cp.async in a shared-memory tile while the accumulator is being staged,
   //   * GroupNorm fine-group partials are combined with a fixed shuffle pattern inside the warp and LayerNorm row
   //     partials are a plain warp reduction.
-  // Without split-K the tile is staged in chunks of CH columns (what the ring can hold); with split-K every CTA stages
-  // its whole partial tile, one cluster barrier makes all of them visible, and each CTA finishes columns [cb, ce).
-  // Residual rows are prefetched four rounds ahead (the first four before the accumulator is even ready).
+  // Without split-K the tile is staged in chunks of CH columns (what the ring can hold, residual double-buffered); with
+  // split-K every CTA stages its whole partial tile, one cluster barrier makes all of them visible, and each CTA finishes
+  // columns [cb, ce).
   const int cols_per = (SK > 1) ? (NT + SK - 1) / SK : NT;
   const int cb = (SK > 1) ? min(NT, sk * cols_per) : 0;
   const int ce = min(NT, cb + cols_per);
-  const int nr = (ce - cb + 3) >> 2;  // rounds: 4 columns (one per warp) each
   const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
   const bool want_stats = p.stats_out != nullptr;
   const bool want_rows = p.rowpart_out != nullptr;
@@ -696,29 +697,33 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
   const int ngl = 128 / gs;                           // fine groups inside this M tile
   const int lpg = gs >> 2;                            // lanes per fine group
   float* sfg = reinterpret_cast<float*>(a_ring);      // [4 warps][kMaxSlots][32 fine groups][2]  (kSredBytes)
-  const int CH = (SK > 1) ? NT : min(NT, ((pl.ring_bytes - kSredBytes) / 512) & ~15);  // staged columns per chunk
-
+  // staged columns per chunk: split-K stages the whole tile; otherwise 1 KB per column (fp32 row + two bf16 residual rows)
+  const int CH = (SK > 1) ? NT : min(NT, ((pl.ring_bytes - kSredBytes) >> 10) & ~15);
+  uint8_t* resbuf = reinterpret_cast<uint8_t*>(part + (size_t)CH * 128);  // [2 (SK == 1)][columns][128] bf16
   const int wq = warp & 3, q4 = lane * 4;
   const unsigned short* resp = reinterpret_cast<const unsigned short*>(p.res);
-  auto res_load = [&](int r) -> uint2 {
-    uint2 v = make_uint2(0u, 0u);
-    const int c = cb + r * 4 + wq;
-    if (resp && r < nr && c < ce) {
-      const int4 cm = colmeta[c];
-      if (cm.x >= 0) v = __ldcg(reinterpret_cast<const uint2*>(resp + (size_t)(uint32_t)cm.y + mt * 128 + q4));
+  // residual rows of columns [c0, c0 + n) -> resbuf (16 bytes per cp.async, fire-and-forget)
+  auto res_fetch = [&](int c0, int n, uint8_t* dst) {
+    if (resp == nullptr) return;
+    for (int i = tid; i < n * 16; i += kProducers) {
+      const int4 cm = colmeta[c0 + (i >> 4)];
+      if (cm.x >= 0) {
+        const unsigned short* src = resp + (size_t)(uint32_t)cm.y + mt * 128 + (i & 15) * 8;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + (size_t)i * 16)), "l"(src) : "memory");
+      }
     }
-    return v;
+    asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  uint2 rq[4] = {make_uint2(0u, 0u), make_uint2(0u, 0u), make_uint2(0u, 0u), make_uint2(0u, 0u)};
   if (warp < 4) {
-#pragma unroll
-    for (int u = 0; u < 4; ++u) rq[u] = res_load(u);
     mbar_wait(acc_full, 0);  // every MMA has completed: the ring (now scratch) is free, the accumulator is final
     tc_fence_after();
     if (tid == 0) TL_MARK(6);
+    // (the residual tile lives in the ring: it can only be requested now; its latency overlaps the TMEM staging and the
+    //  cluster exchange)
+    res_fetch(cb, (SK > 1) ? ce - cb : min(CH, NT), resbuf);
     if (want_stats) {
-      float4* z = reinterpret_cast<float4*>(sfg);
-      for (int i = tid; i < kSredBytes / 16; i += kProducers) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4* zf = reinterpret_cast<float4*>(sfg);
+      for (int i = tid; i < kSredBytes / 16; i += kProducers) zf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     if (SK > 1) {
       for (int c0 = 0; c0 < NT; c0 += 16) {
@@ -727,19 +732,17 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
 #pragma unroll
         for (int j = 0; j < 16; ++j) part[(size_t)(c0 + j) * 128 + tid] = v[j];
       }
+      asm volatile("cp.async.wait_all;" ::: "memory");
     }
   }
   if (SK > 1) {
     if (tid == 0) TL_MARK(16);
-    cluster_sync_all();  // every CTA's partial tile is visible cluster-wide
+    cluster_sync_all();  // every CTA's partial tile is visible cluster-wide (and this CTA's residual tile CTA-wide)
     if (tid == 0) TL_MARK(7);
   }
 
   if (warp < 4) {
     const uint32_t mine = smem_u32(part);
-    uint32_t part_remote[kMaxCluster];
-#pragma unroll
-    for (int s = 0; s < kMaxCluster; ++s) part_remote[s] = (s < SK && SK > 1) ? map_cluster(mine, (uint32_t)s) : mine;
     int sb = -1;  // slot (batch row of the tile) of the statistics run in progress
     float aS[4] = {0.f, 0.f, 0.f, 0.f}, aQ[4] = {0.f, 0.f, 0.f, 0.f};
     auto flush_stats = [&]() {  // warp-uniform: the fine-group sums of this warp's run -> its own (warp, slot) cell
@@ -761,9 +764,12 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
         aQ[e] = 0.f;
       }
     };
+    int rbsel = 0;
+#pragma unroll 1
     for (int cs = 0; cs < ce - cb; cs += CH) {  // one chunk with split-K
+      const uint8_t* rcur = resbuf + (size_t)rbsel * CH * 256;
       if (SK == 1) {
-        if (cs > 0) bar_sync_producers();  // the previous chunk has been consumed
+        if (cs > 0) bar_sync_producers();  // the previous chunk has been consumed (staging tile + other residual buffer)
         const int cn = min(CH, NT - cs);
         for (int c0 = 0; c0 < cn; c0 += 16) {
           float v[16];
@@ -771,77 +777,71 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
 #pragma unroll
           for (int j = 0; j < 16; ++j) part[(size_t)(c0 + j) * 128 + tid] = v[j];
         }
+        asm volatile("cp.async.wait_all;" ::: "memory");  // this chunk's residual rows have landed
         bar_sync_producers();
+        if (cs + CH < NT) res_fetch(cs + CH, min(CH, NT - cs - CH), resbuf + (size_t)(rbsel ^ 1) * CH * 256);
+        rbsel ^= 1;
       }
-      const int r_end = min(nr, (cs + CH) >> 2);
+      const int c_end = min(ce, cb + cs + CH);
 #pragma unroll 1
-      for (int r0 = cs >> 2; r0 < r_end; r0 += 4) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int r = r0 + u;
-          if (r < r_end) {
-            const int c = cb + r * 4 + wq;
-            const uint2 rr = rq[u];
-            rq[u] = res_load(r + 4);
-            if (c < ce) {  // warp-uniform
-              const int4 cm = colmeta[c];
-              float4 acc;
-              if (SK == 1) {
-                acc = *reinterpret_cast<const float4*>(part + (size_t)(c - cs) * 128 + q4);
-              } else {
-                const uint32_t off = (uint32_t)((c * 128 + q4) * 4);
-                float4 tv[kMaxCluster];
-#pragma unroll
-                for (int s2 = 0; s2 < kMaxCluster; ++s2)
-                  if (s2 < SK) tv[s2] = ld_cluster_f32x4(part_remote[s2] + off);
-                acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int s2 = 0; s2 < kMaxCluster; ++s2)
-                  if (s2 < SK) {  // rank order: deterministic
-                    acc.x += tv[s2].x;
-                    acc.y += tv[s2].y;
-                    acc.z += tv[s2].z;
-                    acc.w += tv[s2].w;
-                  }
-              }
-              if (cm.z != sb) {
-                flush_stats();
-                sb = cm.z;
-              }
-              float x[4] = {0.f, 0.f, 0.f, 0.f};
-              if (cm.x >= 0) {
-                x[0] = acc.x + bias4.x;
-                x[1] = acc.y + bias4.y;
-                x[2] = acc.z + bias4.z;
-                x[3] = acc.w + bias4.w;
-                if (p.epi_act == ACT_GELU) {
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) x[e] = gelu_f(x[e]);
-                }
-                x[0] += __uint_as_float(rr.x << 16);
-                x[1] += __uint_as_float(rr.x & 0xffff0000u);
-                x[2] += __uint_as_float(rr.y << 16);
-                x[3] += __uint_as_float(rr.y & 0xffff0000u);
-                const size_t oo = (size_t)(uint32_t)cm.x + mt * 128 + q4;
-                if (A.out_f32) {
-                  *reinterpret_cast<float4*>((float*)p.out + oo) = make_float4(x[0], x[1], x[2], x[3]);
-                } else {
-                  *reinterpret_cast<uint2*>((bf16*)p.out + oo) = make_uint2(pack2(x[0], x[1]), pack2(x[2], x[3]));
-                }
-              }
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                aS[e] += x[e];
-                aQ[e] = fmaf(x[e], x[e], aQ[e]);
-              }
-              if (want_rows) {  // LayerNorm partial of this row over the 128 channels of the M tile
-                const float rs = warp_sum((x[0] + x[1]) + (x[2] + x[3]));
-                const float rq2 = warp_sum(fmaf(x[0], x[0], x[1] * x[1]) + fmaf(x[2], x[2], x[3] * x[3]));
-                if (lane == 0 && cm.x >= 0)
-                  *reinterpret_cast<float2*>(p.rowpart_out + ((size_t)(uint32_t)cm.w * pl.m_tiles + mt) * 2) = make_float2(rs, rq2);
-              }
-            }
+      for (int c = cb + cs + wq; c < c_end; c += 4) {  // warp-uniform
+        const int4 cm = colmeta[c];
+        float4 acc;
+        if (SK == 1) {
+          acc = *reinterpret_cast<const float4*>(part + (size_t)(c - cs) * 128 + q4);
+        } else {
+          const uint32_t off = mine + (uint32_t)((c * 128 + q4) * 4);
+          acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+          for (int s0 = 0; s0 < SK; s0 += 4) {  // four ranks in flight, summed in rank order: deterministic
+            float4 t0 = ld_cluster_f32x4(map_cluster(off, (uint32_t)s0)), t1 = make_float4(0.f, 0.f, 0.f, 0.f), t2 = t1, t3 = t1;
+            if (s0 + 1 < SK) t1 = ld_cluster_f32x4(map_cluster(off, (uint32_t)(s0 + 1)));
+            if (s0 + 2 < SK) t2 = ld_cluster_f32x4(map_cluster(off, (uint32_t)(s0 + 2)));
+            if (s0 + 3 < SK) t3 = ld_cluster_f32x4(map_cluster(off, (uint32_t)(s0 + 3)));
+            acc.x = (((acc.x + t0.x) + t1.x) + t2.x) + t3.x;
+            acc.y = (((acc.y + t0.y) + t1.y) + t2.y) + t3.y;
+            acc.z = (((acc.z + t0.z) + t1.z) + t2.z) + t3.z;
+            acc.w = (((acc.w + t0.w) + t1.w) + t2.w) + t3.w;
           }
+        }
+        if (cm.z != sb) {
+          flush_stats();
+          sb = cm.z;
+        }
+        float x[4] = {0.f, 0.f, 0.f, 0.f};
+        if (cm.x >= 0) {
+          x[0] = acc.x + bias4.x;
+          x[1] = acc.y + bias4.y;
+          x[2] = acc.z + bias4.z;
+          x[3] = acc.w + bias4.w;
+          if (p.epi_act == ACT_GELU) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) x[e] = gelu_f(x[e]);
+          }
+          if (resp) {
+            const uint2 rr = *reinterpret_cast<const uint2*>(rcur + (size_t)(c - cb - cs) * 256 + lane * 8);
+            x[0] += __uint_as_float(rr.x << 16);
+            x[1] += __uint_as_float(rr.x & 0xffff0000u);
+            x[2] += __uint_as_float(rr.y << 16);
+            x[3] += __uint_as_float(rr.y & 0xffff0000u);
+          }
+          const size_t oo = (size_t)(uint32_t)cm.x + mt * 128 + q4;
+          if (A.out_f32) {
+            *reinterpret_cast<float4*>((float*)p.out + oo) = make_float4(x[0], x[1], x[2], x[3]);
+          } else {
+            *reinterpret_cast<uint2*>((bf16*)p.out + oo) = make_uint2(pack2(x[0], x[1]), pack2(x[2], x[3]));
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          aS[e] += x[e];
+          aQ[e] = fmaf(x[e], x[e], aQ[e]);
+        }
+        if (want_rows) {  // LayerNorm partial of this row over the 128 channels of the M tile
+          const float rs = warp_sum((x[0] + x[1]) + (x[2] + x[3]));
+          const float rq2 = warp_sum(fmaf(x[0], x[0], x[1] * x[1]) + fmaf(x[2], x[2], x[3] * x[3]));
+          if (lane == 0 && cm.x >= 0)
+            *reinterpret_cast<float2*>(p.rowpart_out + ((size_t)(uint32_t)cm.w * pl.m_tiles + mt) * 2) = make_float2(rs, rq2);
         }
       }
     }
@@ -987,7 +987,8 @@ UmmaPlan conv_umma_plan(const ConvParams& p, bool want_stats, int num_sms) {
     // the epilogue scratch (+ the fp32 partial tile of the cluster reduction) aliases the ring
     const int budget = 110 * 1024;
     int stages = (budget - 2 * c.panel_bytes - misc) / kABytes;
-    const int scratch = kSredBytes + (sk > 1 ? NT * 512 : 16 * 512);  // statistics cells + staging tile (see the epilogue)
+    // statistics cells + staging tile + residual tile (see the epilogue)
+    const int scratch = kSredBytes + (sk > 1 ? NT * 512 + ((NT + sk - 1) / sk) * 256 : 16 * 1024);
     if (stages < 2) stages = 2;
     if (stages > 6) stages = 6;
     c.stages = stages;

@@ -291,6 +291,9 @@ int Engine::finalize() {
     // shared-memory opt-ins of the attention kernels are per device as well (one engine per GPU in one process)
     if (attention_init() != cudaSuccess) return fail("attention kernel initialisation failed");
     if (use_umma_ && attn_umma_init() != cudaSuccess) return fail("tcgen05 attention initialisation failed");
+    const char* ftr = getenv("JEN1_FUSED_TR");  // "1": run every Transformer1d as ONE fused launch (tr_umma.cu)
+    use_fused_tr_ = ftr && strcmp(ftr, "1") == 0;
+    if (use_umma_ && use_fused_tr_ && tr_umma_init() != cudaSuccess) return fail("fused transformer initialisation failed");
   }
   try {
     const int nl = d_.num_layers;
@@ -784,10 +787,124 @@ Act Engine::attention_core(const Act& q, const Act* kvself, const DAttn* cross, 
   return out;
 }
 
+// Fused Transformer1d: builds the op list of tr_umma.cu (same op order, same intermediate tensors and the same debug tap
+// names as the unfused chain below, so the A/B harness compares them op by op).
+Act Engine::transformer_fused(const DTransformer& Tr, const Act& x, bool causal, int Bout) {
+  const int C = Tr.C, N = x.L, H = d_.attention_heads;
+  TrParams tp;
+  memset(&tp, 0, sizeof(tp));
+  tp.B2 = Bout;
+  tp.N = N;
+  tp.C = C;
+  tp.H = H;
+  tp.d = C / H;
+  tp.Bc = ctx_B_;
+  tp.causal = causal ? 1 : 0;
+  tp.CS = (C >= 512 && conv_umma_max_cluster() >= 16) ? 16 : 8;
+  tp.scale = (float)std::pow((double)tp.d, -0.5);
+  tp.gn_eps = 1e-6f;
+  tp.gn_stats = x.stats;
+  tp.gn_gamma = Tr.gn.gamma;
+  tp.gn_beta = Tr.gn.beta;
+  tp.kv_cond = (const bf16*)kv_cond_;
+  tp.kv_fixed = (const bf16*)kv_fixed_;
+  tp.kv_time = (const bf16*)tt_kv_;
+  tp.kvc_ld = (int)kvc_total_;
+  tp.drop = d_ctl_->drop;
+  tp.mask = ctx_has_mask_ ? ctx_mask_ : nullptr;
+  tp.cond_row = d_ctl_->cond_row;
+  int n = 0;
+  auto tap_as = [&](const char* pref, int& counter, const Act& a) {
+    if (debug_ && !dry_) {
+      char nm[32];
+      snprintf(nm, sizeof nm, "%s%03d", pref, counter);
+      taps_[nm] = a;
+    }
+    if (debug_ && !dry_) ++counter;
+  };
+  auto gemm = [&](const DConv& W, const Act& src, int pro, bool gelu, const Act* res, int Cout, bool stats) -> Act {
+    Act dst = new_act(Bout, N, Cout);
+    TrOp& o = tp.ops[n++];
+    o.type = TR_GEMM;
+    o.src = (const bf16*)src.ptr;
+    o.src_ld = src.C;
+    o.src_bmod = src.Bt;
+    o.K = src.C;
+    o.pro = pro;
+    o.w = (const bf16*)W.wu;
+    o.bias = W.bias;
+    o.Cout = Cout;
+    o.gelu = gelu ? 1 : 0;
+    o.res = res ? (const bf16*)res->ptr : nullptr;
+    o.res_ld = res ? res->C : 0;
+    o.dst = (bf16*)dst.ptr;
+    o.dst_ld = Cout;
+    o.stats = stats ? 1 : 0;
+    tap_as("op", op_index_, dst);
+    return dst;
+  };
+  auto attn = [&](const Act& q, const Act* kvself, const DAttn* cross) -> Act {
+    Act ao = new_act(Bout, N, C);
+    TrOp& o = tp.ops[n++];
+    o.type = TR_ATTN;
+    o.q = (const bf16*)q.ptr;
+    o.q_ld = q.C;
+    o.ao = (bf16*)ao.ptr;
+    if (!cross) {
+      o.cross = 0;
+      o.M = N;
+      o.kv = (const bf16*)kvself->ptr;
+      o.kv_ld = kvself->C;
+      o.k_off = C;
+      o.v_off = 2 * C;
+    } else {
+      o.cross = 1;
+      o.M = ctx_S_ + 1;
+      o.kvc_off = (int)cross->kvc_off;
+    }
+    tap_as("at", at_index_, ao);
+    return ao;
+  };
+  Act t = gemm(Tr.conv, x, TRP_GN, false, nullptr, C, false);
+  for (const DTrBlock& blk : Tr.blocks) {
+    Act qkv = gemm(blk.self.qkv, t, TRP_LN, false, nullptr, 3 * C, false);
+    Act ao = attn(qkv, &qkv, nullptr);
+    Act t1 = gemm(blk.self.out, ao, TRP_RAW, false, &t, C, false);
+    Act q = gemm(blk.cross.qkv, t1, TRP_LN, false, nullptr, C, false);
+    Act ao2 = attn(q, nullptr, &blk.cross);
+    Act t2 = gemm(blk.cross.out, ao2, TRP_RAW, false, &t1, C, false);
+    Act hdn = gemm(blk.ff1, t2, TRP_RAW, true, nullptr, C, false);
+    t = gemm(blk.ff2, hdn, TRP_RAW, false, &t2, C, false);
+  }
+  Act out = gemm(Tr.conv, t, TRP_RAW, false, nullptr, C, true);
+  add_stats(out);
+  tp.stats_out = out.stats;
+  tp.FGo = out.FG;
+  tp.n_ops = n;
+  if (dry_ || !ok_) return out;
+  if (timeline_ && tr_tl_n_ < 16) tp.timeline = timeline_ + 1024 * 32 + (size_t)(tr_tl_n_++) * TR_MAX_OPS * 8;
+  cudaError_t e = launch_tr_umma(tp, use_pdl_, st_);
+  ++launches_;
+  ++fused_tr_launches_;
+  ck(e, "fused transformer launch");
+  return out;
+}
+
 // Transformer1d (reference blocks.py:528-537) with TransformerBlock (:483-489).  Tokens are the channels-last
 // rows themselves, so the two rearranges are free and nn.Linear == 1x1 conv.
 Act Engine::transformer(const DTransformer& Tr, const Act& x, bool causal, int Bout) {
   const int C = Tr.C, N = x.L;
+  // ---- fused path: the whole Transformer1d as ONE launch (tr_umma.cu); the chain below is the fallback (fp32 engine,
+  //      shapes outside the fused kernel's envelope, JEN1_FUSED_TR=0)
+  if (use_umma_ && use_fused_tr_ && !x.f32 && x.stats && x.FG == 32 && d_.attention_multiplier == 1 && Tr.conv.wu &&
+      x.Bt >= 1 && (Bout == x.Bt || Bout == 2 * x.Bt) &&
+      tr_umma_supported(N, C, d_.attention_heads, ctx_S_ + 1, (int)Tr.blocks.size()) &&
+      tr_umma_smem_bytes(N, C, d_.attention_heads, std::max(N, ctx_S_ + 1)) <= (size_t)227 * 1024) {
+    bool packed = true;
+    for (const DTrBlock& b : Tr.blocks)
+      packed = packed && b.self.qkv.wu && b.self.out.wu && b.cross.qkv.wu && b.cross.out.wu && b.ff1.wu && b.ff2.wu;
+    if (packed) return transformer_fused(Tr, x, causal, Bout);
+  }
   ConvOpts oin;
   oin.Lm = oin.Lout = N;
   oin.G = 32;
@@ -1156,10 +1273,11 @@ int Engine::forward(const float* x, const float* cc, const int32_t* cond_rows, c
   at_index_ = 0;
   trace_ = getenv("JEN1_TRACE") != nullptr;
   if (getenv("JEN1_TIMELINE") && !timeline_) {
-    cudaMalloc((void**)&timeline_, 1024 * 32 * sizeof(long long));
+    cudaMalloc((void**)&timeline_, (1024 * 32 + 16 * TR_MAX_OPS * 8) * sizeof(long long));
   }
-  if (timeline_) cudaMemsetAsync(timeline_, 0, 1024 * 32 * sizeof(long long), st);
+  if (timeline_) cudaMemsetAsync(timeline_, 0, (1024 * 32 + 16 * TR_MAX_OPS * 8) * sizeof(long long), st);
   tl_ops_ = 0;
+  tr_tl_n_ = 0;
   taps_.clear();
   arena_off_ = 0;
   if (!upload_ctl(c, st)) return 1;
@@ -1209,6 +1327,21 @@ void Engine::dump_timeline(cudaStream_t st) {
             t[14] ? t[14] - t[2] : 0, t[9] - t[2], t[10] - t[2]);
     prev_end = t[12];
   }
+  {  // fused transformer launches: per op (us from the kernel's first op): start, barrier passed, panel/tiles staged,
+     // first accumulator ready (attention: softmax done), op body done, fence done
+    std::vector<long long> ht((size_t)16 * TR_MAX_OPS * 8);
+    cudaMemcpy(ht.data(), timeline_ + 1024 * 32, ht.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    for (int k = 0; k < tr_tl_n_ && k < 16; ++k) {
+      const long long* t = &ht[(size_t)k * TR_MAX_OPS * 8];
+      const long long t0 = t[0];
+      for (int oi = 0; oi < TR_MAX_OPS && t[oi * 8] != 0; ++oi) {
+        const long long* o = t + oi * 8;
+        fprintf(stderr, "[jen1-trtl] tr%02d op%02d start %.2f wait %.2f staged %.2f acc %.2f body %.2f fence %.2f\n", k, oi,
+                (o[0] - t0) / 1965.0, (o[1] - t0) / 1965.0, (o[2] - t0) / 1965.0, (o[3] - t0) / 1965.0, (o[4] - t0) / 1965.0,
+                (o[5] - t0) / 1965.0);
+      }
+    }
+  }
   fprintf(stderr, "[jen1-tl] total: %d tcgen05 ops, sum gap %.1f us, sum body %.1f us\n", tl_ops_, sum_gap / 1e3, sum_body / 1e3);
 }
 
@@ -1217,8 +1350,8 @@ int Engine::sample_begin(const float* coef_host, int S, const float* cc, int B, 
                          int scale_cfg, float phi, int objective, int use_graph, cudaStream_t st) {
   ok_ = true;
   if (getenv("JEN1_TIMELINE") && !timeline_) {
-    cudaMalloc((void**)&timeline_, 1024 * 32 * sizeof(long long));
-    cudaMemset(timeline_, 0, 1024 * 32 * sizeof(long long));
+    cudaMalloc((void**)&timeline_, (1024 * 32 + 16 * TR_MAX_OPS * 8) * sizeof(long long));
+    cudaMemset(timeline_, 0, (1024 * 32 + 16 * TR_MAX_OPS * 8) * sizeof(long long));
   }
   if (!finalized_) return fail("engine not finalized");
   cudaSetDevice(device_);
@@ -1347,7 +1480,7 @@ int Engine::sample_step(int step, float* x, const float* noise, const uint8_t* d
     }
     if (noise == nullptr) return fail("sample_step: the first graph-captured step needs a noise buffer");
     cudaGraph_t graph = nullptr;
-    const int64_t l0 = launches_, u0 = umma_launches_, a0 = umma_attn_launches_;
+    const int64_t l0 = launches_, u0 = umma_launches_, a0 = umma_attn_launches_, f0 = fused_tr_launches_;
     if (!ck(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal), "begin capture")) return 1;
     const bool good = body();
     cudaError_t e = cudaStreamEndCapture(st, &graph);
@@ -1359,7 +1492,9 @@ int Engine::sample_step(int step, float* x, const float* noise, const uint8_t* d
     smp_.launches_per_step = launches_ - l0;
     smp_.umma_per_step = umma_launches_ - u0;
     smp_.umma_attn_per_step = umma_attn_launches_ - a0;
+    smp_.fused_tr_per_step = fused_tr_launches_ - f0;
     umma_attn_launches_ = a0;
+    fused_tr_launches_ = f0;
     launches_ = l0;
     umma_launches_ = u0;
     e = cudaGraphInstantiate(&smp_.exec, graph, 0);
@@ -1372,6 +1507,7 @@ int Engine::sample_step(int step, float* x, const float* noise, const uint8_t* d
   launches_ += smp_.launches_per_step;
   umma_launches_ += smp_.umma_per_step;
   umma_attn_launches_ += smp_.umma_attn_per_step;
+  fused_tr_launches_ += smp_.fused_tr_per_step;
   if (timeline_) {
     const char* e = getenv("JEN1_TIMELINE_STEP");
     if (e && atoi(e) == step) dump_timeline(st);

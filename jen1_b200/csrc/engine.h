@@ -107,6 +107,7 @@ class Engine {
   int64_t weight_bytes() const { return step_weight_bytes_; }
   int64_t umma_launch_count() const { return umma_launches_; }
   int64_t umma_attn_launch_count() const { return umma_attn_launches_; }
+  int64_t fused_tr_launch_count() const { return fused_tr_launches_; }
 
  private:
   // ---- errors
@@ -158,6 +159,7 @@ class Engine {
   Act resblock(const DRes& R, const Act& x, const Act* skip, float sscale, int groups, bool causal, int Bout,
                bool out_f32);
   Act transformer(const DTransformer& Tr, const Act& x, bool causal, int Bout);
+  Act transformer_fused(const DTransformer& Tr, const Act& x, bool causal, int Bout);
   Act attention_core(const Act& q, const Act* kvself, const DAttn* cross, int C, bool causal);
   bool unet(const Act& xpk, const Act& ccpk, int B, int B2, int T, bool causal, Act* y);
   void tap(const char* name, const Act& a);
@@ -208,12 +210,13 @@ class Engine {
   // control
   CtlBlock* d_ctl_ = nullptr;
   // tcgen05 path
-  bool use_umma_ = false, use_pdl_ = true, use_umma_attn_ = true;
+  bool use_umma_ = false, use_pdl_ = true, use_umma_attn_ = true, use_fused_tr_ = true;
+  int64_t fused_tr_launches_ = 0;
   int64_t umma_attn_launches_ = 0;
   int num_sms_ = 148;
   int64_t umma_launches_ = 0;
   long long* timeline_ = nullptr;
-  int tl_ops_ = 0;
+  int tl_ops_ = 0, tr_tl_n_ = 0;
   void dump_timeline(cudaStream_t st);
   // arena
   char* arena_ = nullptr;
@@ -242,7 +245,7 @@ class Engine {
     cudaGraphExec_t exec = nullptr;
     float* g_x = nullptr;
     const float* g_noise = nullptr;
-    int64_t launches_per_step = 0, umma_per_step = 0, umma_attn_per_step = 0;
+    int64_t launches_per_step = 0, umma_per_step = 0, umma_attn_per_step = 0, fused_tr_per_step = 0;
     struct Sig {  // everything a captured step graph depends on
       int B, T, causal, scale_cfg, objective, use_graph, ctx_B, ctx_S, ctx_has_mask;
       float emb_scale, phi;

@@ -86,6 +86,54 @@ cudaError_t attn_umma_init();
 bool attn_umma_supported(const AttnParams& p);
 cudaError_t launch_attention_umma(const AttnParams& p, bool pdl, cudaStream_t stream);
 
+// ---- fused Transformer1d (tr_umma.cu): one launch per transformer, a thread-block cluster per batch row walks the op list
+//      (k=1 linears with GroupNorm / LayerNorm / raw prologues and bias / GELU / residual epilogues, tcgen05 attention)
+enum { TR_GEMM = 0, TR_ATTN = 1 };
+enum { TRP_RAW = 0, TRP_LN = 1, TRP_GN = 2 };
+constexpr int TR_MAX_OPS = 20;
+struct TrOp {
+  int type;
+  // TR_GEMM: dst[row][token][Cout] = epi(W * pro(src[row % src_bmod][token][K]) + bias) (+ res[row][token][Cout])
+  const bf16* src;
+  int src_ld, src_bmod, K, pro;
+  const bf16* w;      // tcgen05 blob stream of the [Cout][K] weight (conv_umma_pack, one tap)
+  const float* bias;  // [Cout] or nullptr
+  int Cout, gelu;
+  const bf16* res;
+  int res_ld;
+  bf16* dst;
+  int dst_ld;
+  int stats;          // add GroupNorm fine-group sums of dst to TrParams::stats_out
+  // TR_ATTN: ao[row][token][C] = softmax(q k^T * scale) v per head
+  int cross, M;       // keys: N (self) or context length + 1 (cross)
+  const bf16* q;
+  int q_ld;
+  const bf16* kv;     // self: rows of the qkv buffer, K at k_off, V at v_off
+  int kv_ld, k_off, v_off;
+  int kvc_off;        // cross: this layer's column offset in the K/V caches (V at + C)
+  bf16* ao;
+};
+struct TrParams {
+  int B2, N, C, H, d, Bc, causal, n_ops, CS;
+  int NT, panel_bytes, smem_bytes, work_bytes, kvx_bytes, prestage, cross_op;  // filled by launch_tr_umma
+  float scale, gn_eps;
+  const long long* gn_stats;        // [Bx][32][2] fixed-point statistics of the input x (GroupNorm(32))
+  const float *gn_gamma, *gn_beta;
+  const bf16 *kv_cond, *kv_fixed, *kv_time;
+  int kvc_ld;
+  const uint8_t* drop;
+  const float* mask;
+  const int* cond_row;
+  long long* stats_out;             // [B2][FGo][2]
+  int FGo;
+  long long* timeline;              // optional [TR_MAX_OPS][8] phase clocks of CTA (0, 0) (JEN1_TIMELINE debugging)
+  TrOp ops[TR_MAX_OPS];
+};
+bool tr_umma_supported(int N, int C, int H, int M, int n_blocks);
+size_t tr_umma_smem_bytes(int N, int C, int H, int M);
+cudaError_t tr_umma_init();
+cudaError_t launch_tr_umma(const TrParams& p, bool pdl, cudaStream_t stream);
+
 // ---- classifier-free-guidance combine + std rescale (reference model.py:362-369) fused with the x0/eps
 //      conversion, clamp and DDIM update (reference gdm.py:128-141, 212-222)
 struct SamplerParams {

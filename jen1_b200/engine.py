@@ -189,6 +189,9 @@ class Engine:
     def umma_attn_launch_count(self) -> int:
         return int(self.lib.jen1_engine_umma_attn_launch_count(self._h))
 
+    def fused_transformer_launch_count(self) -> int:
+        return int(self.lib.jen1_engine_fused_transformer_launch_count(self._h))
+
     def weight_bytes(self) -> int:
         return int(self.lib.jen1_engine_weight_bytes(self._h))
 
