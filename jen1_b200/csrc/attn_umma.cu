@@ -5,7 +5,7 @@
 //                             K = head dim; Q and K staged K-major in 128-byte-swizzled shared-memory tiles
 //   P = softmax(S * scale)    warp-specialised: the four softmax warps own one query row per thread (TMEM lane ==
 //                             thread), two passes over the TMEM row (max, then exp / sum), fp32; P is written bf16
-//                             into a K-major swizzled tile that aliases the (now dead) Q / K tiles
+//                             into its own K-major swizzled tile
 //   O = P V                   tcgen05.mma, M = 128 queries, N = head dim, K = keys; V is consumed as an MN-major
 //                             operand straight from its [key][channel] layout (no transpose), O re-uses S's columns
 //   out = O / rowsum(P)       tcgen05.ld -> registers -> 16-byte bf16 stores
@@ -105,7 +105,7 @@ struct AttnGeom {
   int DB;         // 64-channel blocks of the head dim
   int cpr_shift;  // log2(head dim / 8): 16-byte chunks per head row
   int tmem_cols;
-  uint32_t off_k, off_v, off_p;  // byte offsets of the tiles (Q at 0; P aliases Q / K)
+  uint32_t off_k, off_v, off_p;  // byte offsets of the tiles (Q at 0)
   uint32_t smem;
 };
 
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(kAtThreads, 1) attn_umma_kernel(const __grid_c
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + g.smem - 64);  // in_full, s_full, p_full, o_full
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
 
-  if (tid == 0) {
+  if (tid == 128) {  // the MMA-issuing thread owns the barriers (it is the first to wait on them)
     mbar_init(&bars[0], kAtThreads);
     mbar_init(&bars[1], 1);
     mbar_init(&bars[2], 128);
@@ -148,80 +148,38 @@ __global__ void __launch_bounds__(kAtThreads, 1) attn_umma_kernel(const __grid_c
   const int trow_time = p.cross ? p.cond_row[r] : 0;
   const int cpr = 1 << g.cpr_shift;
 
-  // ---- stage Q, K, V: items = 16-byte chunks; [0, nq) Q chunks, then K chunks, then V chunks.  Cross-attention
-  //      keys / values come from per-step constant caches, so they are staged BEFORE the PDL wait (while the
-  //      producer of Q is still running); only what the previous kernel wrote is loaded after it.
-  // query rows beyond N are never stored: their tile rows are left as they are (an MMA row only feeds its own
-  // output row), so only the real rows are staged
-  const int nq = min(128, p.N - i0) << g.cpr_shift;
-  const int nk = g.KR << g.cpr_shift;
-  const int total = nq + 2 * nk;
-  auto stage = [&](int lo, int hi) {
-    for (int base = lo; base < hi; base += kAtThreads * 8) {
-      uint4 val[8];
-      float mk[8];
-      uint32_t dst[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int it = base + u * kAtThreads + tid;
-        val[u] = make_uint4(0u, 0u, 0u, 0u);
-        mk[u] = 1.0f;
-        dst[u] = 0xffffffffu;
-        if (it < hi) {
-          int kind, idx;
-          if (it < nq) {
-            kind = 0;
-            idx = it;
-          } else if (it < nq + nk) {
-            kind = 1;
-            idx = it - nq;
-          } else {
-            kind = 2;
-            idx = it - nq - nk;
-          }
-          const int row = idx >> g.cpr_shift, part = idx & (cpr - 1);
-          const int blk = part >> 3, ch = part & 7;
-          const uint32_t tile = kind == 0 ? 0u : (kind == 1 ? g.off_k : g.off_v);
-          const uint32_t rows_per_blk = kind == 0 ? 128u : (uint32_t)g.KR;
-          dst[u] = tile + ((uint32_t)blk * rows_per_blk + (uint32_t)row) * 128u + (uint32_t)((ch ^ (row & 7)) * 16);
-          const bf16* src = nullptr;
-          if (kind == 0) {
-            const int i = i0 + row;
-            if (i < p.N) src = (const bf16*)p.q + ((size_t)r * p.N + i) * p.q_ld + p.q_off + h * d + part * 8;
-          } else if (row < p.M) {
-            const int j = row;
-            if (!p.cross) {
-              src = (const bf16*)p.kv + ((size_t)r * p.N + j) * p.kv_ld + (kind == 1 ? p.k_off : p.v_off) + h * d + part * 8;
-            } else {
-              const bf16* rowp;
-              if (j < S) {
-                rowp = fixed ? (const bf16*)p.kv_fixed + (size_t)j * p.kvc_ld
-                             : (const bf16*)p.kv_cond + ((size_t)bc * S + j) * p.kvc_ld;
-                if (p.mask) mk[u] = __ldg(p.mask + (size_t)bc * S + j);
-              } else {
-                rowp = fixed ? (const bf16*)p.kv_fixed + (size_t)S * p.kvc_ld
-                             : (const bf16*)p.kv_time + (size_t)trow_time * p.kvc_ld;
-              }
-              src = rowp + p.kvc_off + (kind == 2 ? p.C : 0) + h * d + part * 8;
-            }
-          }
-          if (src) val[u] = __ldcg(reinterpret_cast<const uint4*>(src));
-        }
+  // ---- stage Q, K, V with cp.async (16-byte chunks, rolled loops, everything in flight at once, no registers -- this
+  //      code runs once per CTA, so its instruction footprint matters more than its instruction count).  Cross-attention
+  //      keys / values come from per-step constant caches, so they are requested BEFORE the PDL wait (while the producer
+  //      of Q is still running); only what the previous kernel wrote is loaded after it.  Query rows beyond N are never
+  //      stored (an MMA row only feeds its own output row); key rows beyond M are zero-filled (P is 0 there and
+  //      0 * garbage could be NaN).
+  const int sh = g.cpr_shift;
+  auto cp16 = [&](uint8_t* dst, const bf16* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+  };
+  auto stage_kv = [&]() {
+    for (int i = tid; i < (g.KR << (sh + 1)); i += kAtThreads) {
+      const int v = i >= (g.KR << sh) ? 1 : 0;  // 0: K tile, 1: V tile
+      const int j = i - (v ? (g.KR << sh) : 0);
+      const int rw = j >> sh, part = j & (cpr - 1);
+      uint8_t* dst = (v ? Vs : Ks) + ((uint32_t)(part >> 3) * (uint32_t)g.KR + (uint32_t)rw) * 128u + (uint32_t)(((part & 7) ^ (rw & 7)) * 16);
+      if (rw >= p.M) {
+        *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+        continue;
       }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        if (dst[u] != 0xffffffffu) {
-          uint4 o = val[u];
-          if (mk[u] != 1.0f) {
-            const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&val[u]);
-            o.x = pack2(__low2float(hh[0]) * mk[u], __high2float(hh[0]) * mk[u]);
-            o.y = pack2(__low2float(hh[1]) * mk[u], __high2float(hh[1]) * mk[u]);
-            o.z = pack2(__low2float(hh[2]) * mk[u], __high2float(hh[2]) * mk[u]);
-            o.w = pack2(__low2float(hh[3]) * mk[u], __high2float(hh[3]) * mk[u]);
-          }
-          *reinterpret_cast<uint4*>(smem + dst[u]) = o;
-        }
+      const bf16* sp;
+      if (!p.cross) {
+        sp = (const bf16*)p.kv + ((size_t)r * p.N + rw) * p.kv_ld + (v ? p.v_off : p.k_off);
+      } else {
+        const bf16* rowp;
+        if (rw < S)
+          rowp = fixed ? (const bf16*)p.kv_fixed + (size_t)rw * p.kvc_ld : (const bf16*)p.kv_cond + ((size_t)bc * S + rw) * p.kvc_ld;
+        else
+          rowp = fixed ? (const bf16*)p.kv_fixed + (size_t)S * p.kvc_ld : (const bf16*)p.kv_time + (size_t)trow_time * p.kvc_ld;
+        sp = rowp + p.kvc_off + (v ? p.C : 0);
       }
+      cp16(dst, sp + h * d + part * 8);
     }
   };
   // chunks beyond the head dim inside the last 64-channel block must read as zero (d = 16 / 32)
@@ -230,24 +188,45 @@ __global__ void __launch_bounds__(kAtThreads, 1) attn_umma_kernel(const __grid_c
     const int zc = 8 - cpr;
     for (int it = tid; it < rows_all * zc; it += kAtThreads) {
       const int row_all = it / zc, ch = cpr + (it - row_all * zc);
-      uint32_t tile;
-      int row;
-      if (row_all < 128) {
-        tile = 0u;
-        row = row_all;
-      } else if (row_all < 128 + g.KR) {
-        tile = g.off_k;
-        row = row_all - 128;
-      } else {
-        tile = g.off_v;
-        row = row_all - 128 - g.KR;
-      }
-      *reinterpret_cast<uint4*>(smem + tile + (uint32_t)row * 128u + (uint32_t)((ch ^ (row & 7)) * 16)) = make_uint4(0u, 0u, 0u, 0u);
+      uint8_t* tile = row_all < 128 ? Qs : (row_all < 128 + g.KR ? Ks : Vs);
+      const int row = row_all < 128 ? row_all : (row_all < 128 + g.KR ? row_all - 128 : row_all - 128 - g.KR);
+      *reinterpret_cast<uint4*>(tile + (uint32_t)row * 128u + (uint32_t)((ch ^ (row & 7)) * 16)) = make_uint4(0u, 0u, 0u, 0u);
     }
   }
-  if (p.cross) stage(nq, total);
+  if (p.cross) stage_kv();
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  stage(0, p.cross ? nq : total);
+  if (!p.cross) stage_kv();
+  {
+    const int nqr = min(128, p.N - i0);
+    const bf16* qsrc = (const bf16*)p.q + ((size_t)r * p.N + i0) * p.q_ld + p.q_off + h * d;
+    for (int i = tid; i < (nqr << sh); i += kAtThreads) {
+      const int rw = i >> sh, part = i & (cpr - 1);
+      cp16(Qs + ((uint32_t)(part >> 3) * 128u + (uint32_t)rw) * 128u + (uint32_t)(((part & 7) ^ (rw & 7)) * 16),
+           qsrc + (size_t)rw * p.q_ld + part * 8);
+    }
+  }
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_all;" ::: "memory");
+  if (p.cross && p.mask) {
+    // masked context keys: K and V rows times the mask (logit 0, value 0 -- reference blocks.py:431-434); every thread
+    // revisits exactly the chunks it requested itself
+    for (int i = tid; i < (g.KR << (sh + 1)); i += kAtThreads) {
+      const int v = i >= (g.KR << sh) ? 1 : 0;
+      const int j = i - (v ? (g.KR << sh) : 0);
+      const int rw = j >> sh, part = j & (cpr - 1);
+      if (rw >= S) continue;
+      const float mk = __ldg(p.mask + (size_t)bc * S + rw);
+      if (mk == 1.0f) continue;
+      uint4* cell = reinterpret_cast<uint4*>((v ? Vs : Ks) + ((uint32_t)(part >> 3) * (uint32_t)g.KR + (uint32_t)rw) * 128u +
+                                             (uint32_t)(((part & 7) ^ (rw & 7)) * 16));
+      const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(cell);
+      uint4 o;
+      o.x = pack2(__low2float(hh[0]) * mk, __high2float(hh[0]) * mk);
+      o.y = pack2(__low2float(hh[1]) * mk, __high2float(hh[1]) * mk);
+      o.z = pack2(__low2float(hh[2]) * mk, __high2float(hh[2]) * mk);
+      o.w = pack2(__low2float(hh[3]) * mk, __high2float(hh[3]) * mk);
+      *cell = o;
+    }
+  }
   fence_async_smem();
   mbar_arrive(&bars[0]);
 
@@ -387,9 +366,11 @@ cudaError_t launch_attention_umma(const AttnParams& p, bool pdl, cudaStream_t st
   g.off_k = q_bytes;
   const uint32_t qk = (q_bytes + k_bytes + 1023u) / 1024u * 1024u;
   const uint32_t pq = (p_bytes + 1023u) / 1024u * 1024u;
-  g.off_p = 0;  // P aliases Q / K (both dead once S has been computed)
-  g.off_v = qk > pq ? qk : pq;
-  g.smem = g.off_v + (k_bytes + 1023u) / 1024u * 1024u + 64u;
+  // P has its own tile (aliasing it over the dead Q / K tiles saves 48 KB the kernel does not need -- one CTA per SM --
+  // and makes compute-sanitizer racecheck, which cannot see mbarrier / tcgen05.commit ordering, report the reuse)
+  g.off_v = qk;
+  g.off_p = g.off_v + (k_bytes + 1023u) / 1024u * 1024u;
+  g.smem = g.off_p + pq + 64u;
   if (g.smem + 1024 > 227 * 1024) return cudaErrorInvalidValue;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));

@@ -23,6 +23,8 @@
 // Warp roles (192 threads): warps 0-3 build panels / stage attention tiles, run softmax and every epilogue; warp 4 lane 0
 // streams weights; warp 5 allocates TMEM and its lane 0 issues every tcgen05.mma.
 #include <float.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -138,6 +140,9 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t lbo
   d |= (uint64_t)2 << 61;
   return d;
 }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
@@ -190,7 +195,8 @@ __global__ void __launch_bounds__(kThreads, 1) tr_umma_kernel(const __grid_const
   uint8_t* panel = work;                                           // [K/64 blocks][NT rows][128 B]
   float* stage = reinterpret_cast<float*>(work + P.panel_bytes);   // [NT][128] fp32
   float* sfg = stage + (size_t)NT * 128;                           // [4 warps][32 fine groups][2]
-  float* rowred = sfg + 4 * 32 * 2;                                // [NT][4][2] LayerNorm row partials / GN thread partials
+  float* rowred = sfg + 4 * 32 * 2;                                // [NT][4][2] LayerNorm row partials
+  uint8_t* resbuf = reinterpret_cast<uint8_t*>(rowred + (size_t)NT * 4 * 2);  // [NT][128] bf16 residual rows of one M tile
   const bool prestage = P.prestage != 0;                           // cross-attention K / V tiles staged at kernel start
   uint8_t* kvx = work + P.work_bytes;                              // [K tile][V tile] of head `crank` (prestage only)
   const uint32_t kvx_half = (uint32_t)P.kvx_bytes >> 1;
@@ -349,104 +355,88 @@ __global__ void __launch_bounds__(kThreads, 1) tr_umma_kernel(const __grid_const
 #pragma unroll
     for (int j = 0; j < 16; ++j) opbar_remote[j] = map_cluster(smem_u32(opbar), (uint32_t)(j < CS ? j : 0));
 
-    // Attention tile staging (16-byte chunks; K-major 128-byte-swizzled rows as in attn_umma.cu).  Items: [0, nq) Q rows,
-    // then K rows, then V rows; `with_kv` = 0 stages Q only, `with_q` = 0 stages K / V only.
-    auto stage_attn = [&](const TrOp& op, int h, bool with_kv, uint8_t* qb, uint8_t* kb, uint8_t* vb, bool with_q) {
+    // Attention tile staging (16-byte chunks; K-major 128-byte-swizzled rows as in attn_umma.cu) with cp.async: rolled
+    // loops, every chunk in flight at once, no registers.  kinds: bit 0 = Q rows, bit 1 = K and V rows.  The caller waits
+    // (cp.async.wait_all) and then calls finish_attn for the masked-key scaling.
+    auto stage_attn = [&](const TrOp& op, int h, int kinds, uint8_t* qb, uint8_t* kb, uint8_t* vb) {
       const AttnTiles g = attn_tiles(op.M, P.d);
       const int d = P.d, M = op.M, S = M - 1;
-      const int cpr = 1 << g.cpr_shift;
+      const int sh = g.cpr_shift, cpr = 1 << sh;
       const int bc = row % P.Bc;
       const bool fixed = op.cross && ((row >= P.Bc) || (P.drop && P.drop[bc]));
       const int trow_time = op.cross ? P.cond_row[row] : 0;
-      const int nq = N << g.cpr_shift, nk = g.KP << g.cpr_shift;
-      const int lo = with_q ? 0 : nq, hi = with_kv ? nq + 2 * nk : nq;
+      if (kinds & 1) {
+        const bf16* qsrc = op.q + (size_t)row * N * op.q_ld + h * d;
+        for (int i = tid; i < (N << sh); i += kProd) {
+          const int rw = i >> sh, part = i & (cpr - 1);
+          uint8_t* dst = qb + ((uint32_t)(part >> 3) * 128u + (uint32_t)rw) * 128u + (uint32_t)(((part & 7) ^ (rw & 7)) * 16);
+          cp_async16(dst, qsrc + (size_t)rw * op.q_ld + part * 8);
+        }
+      }
+      if (kinds & 2) {
+        for (int i = tid; i < (g.KP << (sh + 1)); i += kProd) {
+          const int v = i >= (g.KP << sh) ? 1 : 0;  // 0: K tile, 1: V tile
+          const int j = i - (v ? (g.KP << sh) : 0);
+          const int rw = j >> sh, part = j & (cpr - 1);
+          uint8_t* dst = (v ? vb : kb) + ((uint32_t)(part >> 3) * (uint32_t)g.KP + (uint32_t)rw) * 128u + (uint32_t)(((part & 7) ^ (rw & 7)) * 16);
+          if (rw >= M) {  // rows beyond the key count must be exact zeros (P is 0 there, 0 * garbage could be NaN)
+            *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+            continue;
+          }
+          const bf16* sp;
+          if (!op.cross) {
+            sp = op.kv + ((size_t)row * N + rw) * op.kv_ld + (v ? op.v_off : op.k_off);
+          } else {
+            const bf16* rowp;
+            if (rw < S)
+              rowp = fixed ? P.kv_fixed + (size_t)rw * P.kvc_ld : P.kv_cond + ((size_t)bc * S + rw) * P.kvc_ld;
+            else
+              rowp = fixed ? P.kv_fixed + (size_t)S * P.kvc_ld : P.kv_time + (size_t)trow_time * P.kvc_ld;
+            sp = rowp + op.kvc_off + (v ? P.C : 0);
+          }
+          cp_async16(dst, sp + h * d + part * 8);
+        }
+      }
       if (cpr < 8) {  // chunks beyond the head dim inside the 64-channel block must read as zero (d = 16 / 32)
         const int zc = 8 - cpr;
-        const int r_lo = with_q ? 0 : 128, r_hi = with_kv ? 128 + 2 * g.KP : 128;
+        const int r_lo = (kinds & 1) ? 0 : 128, r_hi = (kinds & 2) ? 128 + 2 * g.KP : 128;
         for (int it = r_lo * zc + tid; it < r_hi * zc; it += kProd) {
           const int row_all = it / zc, chz = cpr + (it - row_all * zc);
-          uint8_t* tile;
-          int rw;
-          if (row_all < 128) {
-            tile = qb;
-            rw = row_all;
-          } else if (row_all < 128 + g.KP) {
-            tile = kb;
-            rw = row_all - 128;
-          } else {
-            tile = vb;
-            rw = row_all - 128 - g.KP;
-          }
+          uint8_t* tile = row_all < 128 ? qb : (row_all < 128 + g.KP ? kb : vb);
+          const int rw = row_all < 128 ? row_all : (row_all < 128 + g.KP ? row_all - 128 : row_all - 128 - g.KP);
           *reinterpret_cast<uint4*>(tile + (uint32_t)rw * 128u + (uint32_t)((chz ^ (rw & 7)) * 16)) = make_uint4(0u, 0u, 0u, 0u);
         }
       }
-      for (int base = lo; base < hi; base += kProd * 8) {
-        uint4 val[8];
-        float mk[8];
-        uint8_t* dst[8];
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // masked context keys: K and V rows are multiplied by the mask (logit 0, value 0 -- reference blocks.py:431-434);
+    // every thread revisits exactly the chunks it requested itself (visible to it after cp.async.wait_all)
+    auto finish_attn = [&](const TrOp& op, uint8_t* kb, uint8_t* vb) {
+      if (!op.cross || P.mask == nullptr) return;
+      const AttnTiles g = attn_tiles(op.M, P.d);
+      const int sh = g.cpr_shift, cpr = 1 << sh, S = op.M - 1, bc = row % P.Bc;
+      for (int i = tid; i < (g.KP << (sh + 1)); i += kProd) {
+        const int v = i >= (g.KP << sh) ? 1 : 0;
+        const int j = i - (v ? (g.KP << sh) : 0);
+        const int rw = j >> sh, part = j & (cpr - 1);
+        if (rw >= S) continue;
+        const float mk = __ldg(P.mask + (size_t)bc * S + rw);
+        if (mk == 1.0f) continue;
+        uint4* cell = reinterpret_cast<uint4*>((v ? vb : kb) + ((uint32_t)(part >> 3) * (uint32_t)g.KP + (uint32_t)rw) * 128u +
+                                               (uint32_t)(((part & 7) ^ (rw & 7)) * 16));
+        float f[8];
+        unpack8(*cell, f);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int it = base + u * kProd + tid;
-          val[u] = make_uint4(0u, 0u, 0u, 0u);
-          mk[u] = 1.0f;
-          dst[u] = nullptr;
-          if (it < hi) {
-            int kind, idx;
-            if (it < nq) {
-              kind = 0;
-              idx = it;
-            } else if (it < nq + nk) {
-              kind = 1;
-              idx = it - nq;
-            } else {
-              kind = 2;
-              idx = it - nq - nk;
-            }
-            const int rw = idx >> g.cpr_shift, part = idx & (cpr - 1);
-            const int blk = part >> 3, chn = part & 7;
-            uint8_t* tile = kind == 0 ? qb : (kind == 1 ? kb : vb);
-            const uint32_t rows_per_blk = kind == 0 ? 128u : (uint32_t)g.KP;
-            dst[u] = tile + ((uint32_t)blk * rows_per_blk + (uint32_t)rw) * 128u + (uint32_t)((chn ^ (rw & 7)) * 16);
-            const bf16* sp = nullptr;
-            if (kind == 0) {
-              sp = op.q + ((size_t)row * N + rw) * op.q_ld + h * d + part * 8;
-            } else if (rw < M) {
-              if (!op.cross) {
-                sp = op.kv + ((size_t)row * N + rw) * op.kv_ld + (kind == 1 ? op.k_off : op.v_off) + h * d + part * 8;
-              } else {
-                const bf16* rowp;
-                if (rw < S) {
-                  rowp = fixed ? P.kv_fixed + (size_t)rw * P.kvc_ld : P.kv_cond + ((size_t)bc * S + rw) * P.kvc_ld;
-                  if (P.mask) mk[u] = __ldg(P.mask + (size_t)bc * S + rw);
-                } else {
-                  rowp = fixed ? P.kv_fixed + (size_t)S * P.kvc_ld : P.kv_time + (size_t)trow_time * P.kvc_ld;
-                }
-                sp = rowp + op.kvc_off + (kind == 2 ? P.C : 0) + h * d + part * 8;
-              }
-            }
-            if (sp) val[u] = __ldcg(reinterpret_cast<const uint4*>(sp));
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          if (dst[u]) {
-            uint4 o = val[u];
-            if (mk[u] != 1.0f) {
-              float v[8];
-              unpack8(val[u], v);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] *= mk[u];
-              o = pack8(v);
-            }
-            *reinterpret_cast<uint4*>(dst[u]) = o;
-          }
-        }
+        for (int e = 0; e < 8; ++e) f[e] *= mk;
+        *cell = pack8(f);
       }
     };
     // The cross-attention K / V tiles of this CTA's head are per-step constants (prompt / null-embedding caches + the
     // time-token row written before the step's kernel chain): staged now, while the previous kernel is still running.
     if (prestage && crank < P.H) {
-      stage_attn(P.ops[P.cross_op], crank, true, work, kvx, kvx + kvx_half, false);
+      stage_attn(P.ops[P.cross_op], crank, 2, work, kvx, kvx + kvx_half);
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      finish_attn(P.ops[P.cross_op], kvx, kvx + kvx_half);
       fence_async_smem();
     }
 
@@ -461,26 +451,21 @@ __global__ void __launch_bounds__(kThreads, 1) tr_umma_kernel(const __grid_const
       TR_MARK(1);
 
       if (op.type == TR_GEMM) {
-        const int K = op.K, kb_n = K >> 6, mtiles = op.Cout >> 7;
+        const int K = op.K, mtiles = op.Cout >> 7;
         if (crank < mtiles) {
           // ------------------------------------------------------------------ panel: the row's whole input, transformed
-          const int cpr = K >> 3;                       // 16-byte chunks per token row (32, 64 or 128)
-          const int rows_per_pass = kProd / cpr;        // 4, 2 or 1
-          const int ch = tid & (cpr - 1), r0 = tid / cpr;
-          const bf16* src = op.src + (size_t)(row % op.src_bmod) * N * op.src_ld + ch * 8;
-          const uint32_t blk_off = (uint32_t)(ch >> 3) * (uint32_t)NT * 128u;
-          const int npass = (N + rows_per_pass - 1) / rows_per_pass;
-          // every 16-byte chunk of this thread is requested up front (one L2 round trip for the whole panel); the
-          // GroupNorm coefficients / LayerNorm row statistics are then formed from registers and the transformed rows are
-          // written to the panel ONCE (bf16, swizzled)
-          constexpr int kMaxPass = 20;  // ceil(N / rows_per_pass) chunks per thread: N * K <= 20 * 1024 (checked on the host)
-          uint4 raw[kMaxPass];
-#pragma unroll
-          for (int u = 0; u < kMaxPass; ++u) {
-            const int r = u * rows_per_pass + r0;
-            raw[u] = make_uint4(0u, 0u, 0u, 0u);
-            if (u < npass && r < N) raw[u] = __ldcg(reinterpret_cast<const uint4*>(src + (size_t)r * op.src_ld));
+          // raw rows -> panel with cp.async (one L2 round trip for everything, rolled loop); GroupNorm-apply / LayerNorm
+          // then run in place over shared memory.  A thread always meets the same 16-byte channel chunk `ch`.
+          const int lg = K == 256 ? 5 : (K == 512 ? 6 : 7);  // log2(16-byte chunks per token row)
+          const int cpr = 1 << lg, total = N << lg;
+          const int ch = tid & (cpr - 1);
+          const bf16* src = op.src + (size_t)(row % op.src_bmod) * N * op.src_ld;
+          uint8_t* pcol = panel + (uint32_t)(ch >> 3) * (uint32_t)NT * 128u;  // this thread's 64-channel block
+          for (int i = tid; i < total; i += kProd) {
+            const int r = i >> lg;
+            cp_async16(pcol + (uint32_t)r * 128u + (uint32_t)(((ch & 7) ^ (r & 7)) * 16), src + (size_t)r * op.src_ld + ch * 8);
           }
+          asm volatile("cp.async.commit_group;" ::: "memory");
           float ga[8], gb[8];  // GN: per-channel (a, s) of this thread's chunk: y = a * x + s
           if (op.pro == TRP_GN) {
             const int gsz = K >> 5;  // channels per group (8, 16 or 32)
@@ -498,17 +483,17 @@ __global__ void __launch_bounds__(kThreads, 1) tr_umma_kernel(const __grid_const
               gb[e] = fmaf(-mean, gm, __ldg(P.gn_beta + ch * 8 + e));
             }
           }
-          const int nw = cpr >= 32 ? (cpr >> 5) : 1;  // warps per token row
-          if (op.pro == TRP_LN) {
-            // per-row (sum, sumsq): a token row is spread over nw warps -> one cell per (row, warp-in-row), summed in a
-            // fixed order below
-            const int wir = warp & (nw - 1);
-#pragma unroll
-            for (int u = 0; u < kMaxPass; ++u) {
-              const int r = u * rows_per_pass + r0;
-              if (u < npass) {  // warp-uniform
+          asm volatile("cp.async.wait_all;" ::: "memory");
+          if (op.pro != TRP_RAW) {
+            // (every thread only revisits the chunks it copied itself: no barrier needed before this pass)
+            const int nw = cpr >> 5;  // warps per token row (1, 2 or 4)
+            if (op.pro == TRP_LN) {
+              const int wir = warp & (nw - 1);
+#pragma unroll 1
+              for (int i = tid; i < total; i += kProd) {  // warp-uniform trip count (total is a multiple of 32)
+                const int r = i >> lg;
                 float v[8];
-                unpack8(raw[u], v);
+                unpack8(*reinterpret_cast<const uint4*>(pcol + (uint32_t)r * 128u + (uint32_t)(((ch & 7) ^ (r & 7)) * 16)), v);
                 float a = 0.f, q = 0.f;
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
@@ -517,40 +502,35 @@ __global__ void __launch_bounds__(kThreads, 1) tr_umma_kernel(const __grid_const
                 }
                 a = warp_sum(a);
                 q = warp_sum(q);
-                if (lane == 0 && r < N) *reinterpret_cast<float2*>(rowred + ((size_t)r * 4 + wir) * 2) = make_float2(a, q);
+                if (lane == 0) *reinterpret_cast<float2*>(rowred + ((size_t)r * 4 + wir) * 2) = make_float2(a, q);
               }
+              bar_prod();
             }
-            bar_prod();
-          }
-          const float inv_k = 1.0f / (float)K;
-#pragma unroll
-          for (int u = 0; u < kMaxPass; ++u) {
-            const int r = u * rows_per_pass + r0;
-            if (u < npass && r < NT) {
-              uint4 o = raw[u];
-              if (op.pro != TRP_RAW && r < N) {
-                float v[8];
-                unpack8(raw[u], v);
-                if (op.pro == TRP_LN) {
-                  float a = 0.f, q = 0.f;
-                  for (int w = 0; w < nw; ++w) {
-                    const float2 pr = *reinterpret_cast<const float2*>(rowred + ((size_t)r * 4 + w) * 2);
-                    a += pr.x;
-                    q += pr.y;
-                  }
-                  const float mean = a * inv_k;
-                  float var = q * inv_k - mean * mean;
-                  if (var < 0.f) var = 0.f;
-                  const float rstd = 1.0f / sqrtf(var + 1e-5f);
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) v[e] = (v[e] - mean) * rstd;
-                } else {
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) v[e] = fmaf(ga[e], v[e], gb[e]);
+            const float inv_k = 1.0f / (float)K;
+#pragma unroll 1
+            for (int i = tid; i < total; i += kProd) {
+              const int r = i >> lg;
+              uint4* cell = reinterpret_cast<uint4*>(pcol + (uint32_t)r * 128u + (uint32_t)(((ch & 7) ^ (r & 7)) * 16));
+              float v[8];
+              unpack8(*cell, v);
+              if (op.pro == TRP_LN) {
+                float a = 0.f, q = 0.f;
+                for (int w = 0; w < nw; ++w) {
+                  const float2 pr = *reinterpret_cast<const float2*>(rowred + ((size_t)r * 4 + w) * 2);
+                  a += pr.x;
+                  q += pr.y;
                 }
-                o = pack8(v);
+                const float mean = a * inv_k;
+                float var = q * inv_k - mean * mean;
+                if (var < 0.f) var = 0.f;
+                const float rstd = 1.0f / sqrtf(var + 1e-5f);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = (v[e] - mean) * rstd;
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = fmaf(ga[e], v[e], gb[e]);
               }
-              *reinterpret_cast<uint4*>(panel + blk_off + (uint32_t)r * 128u + (uint32_t)(((ch & 7) ^ (r & 7)) * 16)) = o;
+              *cell = pack8(v);
             }
           }
           fence_async_smem();
@@ -558,17 +538,15 @@ __global__ void __launch_bounds__(kThreads, 1) tr_umma_kernel(const __grid_const
           TR_MARK(2);
 
           // ------------------------------------------------------------------ epilogue of every M tile of this CTA
+          const unsigned short* resp = reinterpret_cast<const unsigned short*>(op.res);
+          const size_t rbase = (size_t)row * N;
           for (int mt = crank; mt < mtiles; mt += CS) {
             const float4 bias4 = op.bias ? __ldg(reinterpret_cast<const float4*>(op.bias + mt * 128) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
-            const unsigned short* resp = reinterpret_cast<const unsigned short*>(op.res);
-            const size_t rbase = (size_t)row * N;
-            auto res_load = [&](int c) -> uint2 {
-              if (resp && c < N) return __ldcg(reinterpret_cast<const uint2*>(resp + (rbase + c) * op.res_ld + mt * 128 + q4));
-              return make_uint2(0u, 0u);
-            };
-            uint2 rq[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) rq[u] = res_load(warp + 4 * u);
+            if (resp) {  // residual rows of this tile -> shared memory (fire-and-forget; not aliased with anything live)
+              for (int i = tid; i < N * 16; i += kProd)
+                cp_async16(resbuf + (size_t)i * 16, resp + (rbase + (i >> 4)) * op.res_ld + mt * 128 + (i & 15) * 8);
+              asm volatile("cp.async.commit_group;" ::: "memory");
+            }
             mbar_wait(acc_full, n_acc & 1);
             ++n_acc;
             tc_fence_after();
@@ -581,35 +559,29 @@ __global__ void __launch_bounds__(kThreads, 1) tr_umma_kernel(const __grid_const
             }
             tc_fence_before();
             mbar_arrive(acc_empty);  // the accumulator may be overwritten by the next tile / op
+            asm volatile("cp.async.wait_all;" ::: "memory");
             bar_prod();
             float aS[4] = {0.f, 0.f, 0.f, 0.f}, aQ[4] = {0.f, 0.f, 0.f, 0.f};
-            const int nr = (N + 3) >> 2;
 #pragma unroll 1
-            for (int rr0 = 0; rr0 < nr; rr0 += 4) {
+            for (int c = warp; c < N; c += 4) {
+              const float4 acc = *reinterpret_cast<const float4*>(stage + (size_t)c * 128 + q4);
+              float x[4] = {acc.x + bias4.x, acc.y + bias4.y, acc.z + bias4.z, acc.w + bias4.w};
+              if (op.gelu) {
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const int r = rr0 + u;
-                const int c = r * 4 + warp;
-                const uint2 rv = rq[u];
-                rq[u] = res_load(c + 16);
-                if (r < nr && c < N) {
-                  const float4 acc = *reinterpret_cast<const float4*>(stage + (size_t)c * 128 + q4);
-                  float x[4] = {acc.x + bias4.x, acc.y + bias4.y, acc.z + bias4.z, acc.w + bias4.w};
-                  if (op.gelu) {
+                for (int e = 0; e < 4; ++e) x[e] = gelu_f(x[e]);
+              }
+              if (resp) {
+                const uint2 rv = *reinterpret_cast<const uint2*>(resbuf + (size_t)c * 256 + lane * 8);
+                x[0] += __uint_as_float(rv.x << 16);
+                x[1] += __uint_as_float(rv.x & 0xffff0000u);
+                x[2] += __uint_as_float(rv.y << 16);
+                x[3] += __uint_as_float(rv.y & 0xffff0000u);
+              }
+              *reinterpret_cast<uint2*>(op.dst + (rbase + c) * op.dst_ld + mt * 128 + q4) = make_uint2(pack2(x[0], x[1]), pack2(x[2], x[3]));
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) x[e] = gelu_f(x[e]);
-                  }
-                  x[0] += __uint_as_float(rv.x << 16);
-                  x[1] += __uint_as_float(rv.x & 0xffff0000u);
-                  x[2] += __uint_as_float(rv.y << 16);
-                  x[3] += __uint_as_float(rv.y & 0xffff0000u);
-                  *reinterpret_cast<uint2*>(op.dst + (rbase + c) * op.dst_ld + mt * 128 + q4) = make_uint2(pack2(x[0], x[1]), pack2(x[2], x[3]));
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    aS[e] += x[e];
-                    aQ[e] = fmaf(x[e], x[e], aQ[e]);
-                  }
-                }
+              for (int e = 0; e < 4; ++e) {
+                aS[e] += x[e];
+                aQ[e] = fmaf(x[e], x[e], aQ[e]);
               }
             }
             if (op.stats) {  // GroupNorm fine-group sums of the output for the next consumer (fixed-point accumulators)
@@ -635,7 +607,7 @@ __global__ void __launch_bounds__(kThreads, 1) tr_umma_kernel(const __grid_const
                 stat_add(so + 1, q);
               }
             }
-            bar_prod();  // staging tile / stat cells are free again
+            bar_prod();  // staging tile / residual tile / stat cells are free again
           }
         }
       } else {
@@ -645,7 +617,11 @@ __global__ void __launch_bounds__(kThreads, 1) tr_umma_kernel(const __grid_const
         for (int h = crank; h < P.H; h += CS) {
           // stage Q (and K, V unless this head's cross-attention K/V tiles were staged at kernel start)
           const bool ext = prestage && op.cross && h == crank;
-          stage_attn(op, h, !ext, work, ext ? kvx : work + g.off_k, ext ? kvx + kvx_half : work + g.off_v, true);
+          uint8_t* kb = ext ? kvx : work + g.off_k;
+          uint8_t* vb = ext ? kvx + kvx_half : work + g.off_v;
+          stage_attn(op, h, ext ? 1 : 3, work, kb, vb);
+          asm volatile("cp.async.wait_all;" ::: "memory");
+          if (!ext) finish_attn(op, kb, vb);
           fence_async_smem();
           mbar_arrive(panel_full);
           if (h == crank) TR_MARK(2);
@@ -755,7 +731,6 @@ bool tr_umma_supported(int N, int C, int H, int M, int n_blocks) {
   const int d = C / H;
   if (!(d == 16 || d == 32 || d == 64 || d == 128)) return false;
   if (N < 1 || N > 128 || M < 1 || M > 256) return false;   // one 128-query tile, keys within one TMEM accumulator
-  if ((N * C + 1023) / 1024 > 20) return false;             // panel chunks per producer thread held in registers
   if (n_blocks < 1 || 2 + 8 * n_blocks > TR_MAX_OPS) return false;
   return true;
 }
@@ -764,7 +739,7 @@ static size_t tr_work_bytes(int N, int C, int H, int M) {
   const int NT = (N + 15) / 16 * 16;
   const int d = C / H;
   const size_t panel = (size_t)(C / 64) * NT * 128;
-  const size_t gemm = panel + (size_t)NT * 512 + kSfgBytes + (size_t)NT * 4 * 8 + 1024;
+  const size_t gemm = panel + (size_t)NT * 512 + kSfgBytes + (size_t)NT * 4 * 8 + (size_t)NT * 256 + 1024;
   const int Mx = M > N ? M : N;
   const int KP = (Mx + 15) / 16 * 16, DB = (d + 63) / 64;
   const size_t q_bytes = (size_t)DB * 128 * 128, k_bytes = (size_t)DB * KP * 128, p_bytes = (size_t)((KP + 63) / 64) * 128 * 128;
@@ -813,6 +788,33 @@ cudaError_t launch_tr_umma(const TrParams& p_in, bool pdl, cudaStream_t stream) 
       p.kvx_bytes = (int)kvx;
       p.smem_bytes += (int)kvx;
     }
+  }
+  // Cluster size: 16 CTAs per row when all rows' clusters can be resident at once, else 8 (a second wave of clusters
+  // doubles the launch's duration; co-residency of 16-CTA clusters is limited by the SMs per GPC).
+  if (p.CS == 16) {
+    static int active16 = -1;
+    static int active16_smem = -1;
+    if (active16 < 0 || active16_smem != p.smem_bytes) {
+      cudaLaunchConfig_t q;
+      memset(&q, 0, sizeof(q));
+      q.gridDim = dim3(16, 64, 1);
+      q.blockDim = dim3(kThreads);
+      q.dynamicSmemBytes = p.smem_bytes;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = 16;
+      qa[0].val.clusterDim.y = 1;
+      qa[0].val.clusterDim.z = 1;
+      q.attrs = qa;
+      q.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, tr_umma_kernel, &q) != cudaSuccess) n = 0;
+      (void)cudaGetLastError();
+      active16 = n;
+      active16_smem = p.smem_bytes;
+      if (getenv("JEN1_TRACE")) fprintf(stderr, "[jen1] fused transformer: %d clusters of 16 CTAs can be resident (smem %d B)\n", n, p.smem_bytes);
+    }
+    if (active16 < p.B2) p.CS = 8;
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));

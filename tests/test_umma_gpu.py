@@ -108,3 +108,27 @@ def test_full_size_batch_independence(ab_models):
     e_perm = ((yp - y[perm]).norm() / y.norm()).item()
     e_one = ((y1 - y[1:2]).norm() / y[1:2].norm()).item()
     assert e_perm < 1e-2 and e_one < 1e-2, (e_perm, e_one)
+
+
+def test_fused_transformer_kernel_matches_unfused_and_reference(ab_models, golden_dir, monkeypatch):
+    """The fused Transformer1d kernel (tr_umma.cu, opt-in JEN1_FUSED_TR=1: a thread-block cluster per batch row walks the
+    10-op chain with cluster-scope barriers) against the unfused chain op by op, and against the reference golden."""
+    import umma_debug
+    from oracle.make_golden import VARIANTS, make_inputs
+    desc, sd, (mg, _) = ab_models
+    monkeypatch.setenv("JEN1_FUSED_TR", "1")
+    mf = umma_debug.make(desc, sd, "umma")
+    monkeypatch.delenv("JEN1_FUSED_TR")
+    for T, B, variant in ((150, 2, "cfg"), (333, 1, "causal")):
+        nbad, worst, efinal, _ = umma_debug.compare(T, B, variant, verbose=False, models=(mg, mf))
+        assert nbad == 0 and worst < 2e-2 and efinal < 1e-2, (T, B, variant, nbad, worst, efinal)
+    assert mf.engine.fused_transformer_launch_count() > 0 and mf.engine.umma_attn_launch_count() == 0
+    nbad, worst, efinal, _ = umma_debug.compare(150, 2, "cfg", verbose=False, models=(mg, mf), masked_tail=100)
+    assert nbad == 0 and worst < 2e-2 and efinal < 1e-2, (nbad, worst, efinal)
+    fx = torch.load(os.path.join(golden_dir, "unet_full.pt"))
+    rec = fx["cases"]["T150_B1"]
+    x, t, emb, mask, cc = make_inputs(desc, rec["B"], rec["T"], rec["seed"], rec["masked_tail"])
+    y = mf(x.cuda(), t.cuda(), embedding=emb.cuda(), embedding_mask=mask.cuda(), features=None,
+           channels_list=[cc.cuda()], **dict(VARIANTS["cfg"])).cpu()
+    err = ((y - rec["outputs"]["cfg"]).norm() / rec["outputs"]["cfg"].norm()).item()
+    assert err < 1e-2, err
