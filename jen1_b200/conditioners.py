@@ -10,6 +10,7 @@ available offline, therefore `EmbeddingConditioner` (caller-supplied embeddings)
 from __future__ import annotations
 
 import hashlib
+import math
 from typing import Any, Dict, List, Sequence, Tuple, Union
 
 import torch
@@ -116,6 +117,47 @@ class IntConditioner(Conditioner):
         return [e, torch.ones(e.shape[0], 1).to(device)]
 
 
+class NumberEmbedder(torch.nn.Module):
+    """reference utils/module.py:58-101: [x, sin(2 pi x w), cos(2 pi x w)] (w in R^{dim/2}, learned) -> Linear(dim + 1, features)."""
+
+    def __init__(self, features: int, dim: int = 256):
+        super().__init__()
+        assert dim % 2 == 0
+        self.features = features
+        self.weights = torch.nn.Parameter(torch.randn(dim // 2))
+        self.linear = torch.nn.Linear(dim + 1, features)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        shape = x.shape
+        x = x.reshape(-1, 1).to(self.weights.dtype)
+        freqs = x * self.weights.unsqueeze(0) * 2 * math.pi
+        f = torch.cat((x, freqs.sin(), freqs.cos()), dim=-1)
+        return self.linear(f).view(*shape, self.features)
+
+    def load_reference_state_dict(self, sd: Dict[str, torch.Tensor], prefix: str = "embedder."):
+        """Reference key names: `embedder.embedding.0.weights`, `embedder.embedding.1.{weight,bias}`."""
+        self.weights.data.copy_(sd[prefix + "embedding.0.weights"])
+        self.linear.weight.data.copy_(sd[prefix + "embedding.1.weight"])
+        self.linear.bias.data.copy_(sd[prefix + "embedding.1.bias"])
+        return self
+
+
+class NumberConditioner(Conditioner):
+    """reference conditioners.py:135-164: floats clamped to [min_val, max_val], normalised to [0, 1], embedded by
+    NumberEmbedder; returns [emb[B, 1, D], ones[B, 1]]."""
+
+    def __init__(self, output_dim: int, min_val: float = 0, max_val: float = 1):
+        super().__init__(output_dim, output_dim, 1)
+        self.min_val, self.max_val = min_val, max_val
+        self.embedder = NumberEmbedder(features=output_dim)
+
+    def __call__(self, floats: List[float], device=None):
+        v = torch.tensor([float(x) for x in floats]).to(device).clamp(self.min_val, self.max_val)
+        v = (v - self.min_val) / (self.max_val - self.min_val)
+        e = self.embedder.to(device)(v).unsqueeze(1)
+        return [e, torch.ones(e.shape[0], 1).to(device)]
+
+
 class MultiConditioner:
     """reference conditioners.py:167-208: apply each conditioner to its key of the per-sample metadata dicts."""
 
@@ -141,3 +183,36 @@ class MultiConditioner:
         return out
 
     forward = __call__
+
+
+def create_multi_conditioner(config=None, *, text_conditioner: Conditioner = None) -> MultiConditioner:
+    """reference utils/script_util.py:151-178 with its INTENDED semantics: one conditioner per entry of
+    `conditioning_type` (the reference returns from inside the loop, so only 't5' is ever built -- SURVEY.md 3.6).
+    `config` is a ConditionerConfig-like namespace (utils/conditioner_config.py:10-37): cond_dim, default_keys,
+    conditioning_type and the per-type sub-configs with an `id` (= the metadata key).  `text_conditioner` replaces the
+    T5 encoder (its pretrained weights are not reachable offline): e.g. EmbeddingConditioner / RandomTextConditioner."""
+    from types import SimpleNamespace
+    if config is None:
+        config = SimpleNamespace(cond_dim=1024, default_keys={}, conditioning_type=["t5", "int", "number"],
+                                 t5_config=SimpleNamespace(id="prompt", t5_model_name="google/flan-t5-large", max_length=128, project_out=True),
+                                 int_config=SimpleNamespace(id="seconds_start", min_val=0, max_val=512),
+                                 number_config=SimpleNamespace(id="seconds_total", min_val=0, max_val=512))
+
+    def as_dict(c):
+        d = {k: getattr(c, k) for k in dir(c) if not k.startswith("_") and not callable(getattr(c, k))}
+        return d.pop("id", None), d
+
+    conds: Dict[str, Conditioner] = {}
+    for kind in config.conditioning_type:
+        if kind == "t5":
+            cid, kw = as_dict(config.t5_config)
+            conds[cid] = text_conditioner if text_conditioner is not None else T5Conditioner(output_dim=config.cond_dim, **kw)
+        elif kind == "int":
+            cid, kw = as_dict(config.int_config)
+            conds[cid] = IntConditioner(output_dim=config.cond_dim, **kw)
+        elif kind == "number":
+            cid, kw = as_dict(config.number_config)
+            conds[cid] = NumberConditioner(output_dim=config.cond_dim, **kw)
+        else:
+            raise NotImplementedError("Invalid conditioner type: %s" % kind)
+    return MultiConditioner(conds, default_keys=dict(config.default_keys))

@@ -31,6 +31,51 @@ from .model import UNetCFG1d
 from .weights import load_checkpoint_state_dict, random_state_dict
 
 
+def resample_frac(x: torch.Tensor, old_sr: int, new_sr: int, zeros: int = 24, rolloff: float = 0.945) -> torch.Tensor:
+    """Fractional resampling by windowed-sinc polyphase filtering -- the published algorithm of `julius.resample_frac`
+    (julius 0.2.x, the dependency `encodec.utils.convert_audio` calls; reference generation.py:95): reduce old_sr / new_sr
+    by their gcd, low-pass at rolloff * min(old, new) / 2 with `zeros` zero crossings and a Hann^2-shaped (cos^2) window,
+    one FIR phase per output sample of a period, replicate padding, output length floor(new_sr * L / old_sr).
+    julius is not installed in this image: parity with it is UNPINNED (checked only through resampling identities)."""
+    old_sr, new_sr = int(old_sr), int(new_sr)
+    if old_sr == new_sr:
+        return x
+    g = math.gcd(old_sr, new_sr)
+    old_sr, new_sr = old_sr // g, new_sr // g
+    sr = min(new_sr, old_sr) * rolloff
+    width = math.ceil(zeros * old_sr / sr)
+    idx = torch.arange(-width, width + old_sr, dtype=torch.float32)
+    kernels = []
+    for i in range(new_sr):
+        t = ((-i / new_sr + idx / old_sr) * sr).clamp_(-zeros, zeros) * math.pi
+        window = torch.cos(t / zeros / 2) ** 2
+        k = torch.sinc(t / math.pi) * window
+        kernels.append(k / k.sum())
+    kernel = torch.stack(kernels).view(new_sr, 1, -1).to(x)
+    shape = x.shape
+    length = shape[-1]
+    y = torch.nn.functional.pad(x.reshape(-1, 1, length), (width, width + old_sr), mode="replicate")
+    y = torch.nn.functional.conv1d(y, kernel, stride=old_sr)            # [*, new_sr, time]
+    y = y.transpose(1, 2).reshape(*shape[:-1], -1)
+    return y[..., : int(new_sr * length / old_sr)]
+
+
+def convert_audio(wav: torch.Tensor, sr: int, target_sr: int, target_channels: int) -> torch.Tensor:
+    """`encodec.utils.convert_audio` (reference generation.py:95): channel adaptation (mono <- mean, mono -> expand,
+    equal -> as is), then resampling to the model rate."""
+    assert wav.dim() >= 2 and wav.shape[-2] in (1, 2), "audio must be [..., channels (1 or 2), samples]"
+    *lead, channels, length = wav.shape
+    if target_channels == 1:
+        wav = wav.mean(-2, keepdim=True)
+    elif target_channels == 2:
+        wav = wav.expand(*lead, target_channels, length)
+    elif channels == 1:
+        wav = wav.expand(target_channels, -1)
+    else:
+        raise RuntimeError("Impossible to convert from %d to %d channels" % (channels, target_channels))
+    return resample_frac(wav, sr, target_sr)
+
+
 class Jen1:
     def __init__(self, ckpt_path: Optional[str], device="cuda:0", sample_rate: int = 48000,
                  cross_attn_cond_ids: Sequence[str] = ("prompt",), global_cond_ids: Sequence[str] = (),
@@ -110,8 +155,8 @@ class Jen1:
         if init_audio is not None and init_latent is None:
             if init_audio.dim() == 2:
                 init_audio = init_audio.unsqueeze(0).repeat(B, 1, 1)
-            if init_audio_sr is not None and init_audio_sr != self.sample_rate:
-                raise NotImplementedError("resampling needs torchaudio; pass audio at the model sample rate")
+            channels = getattr(self.codec, "channels", init_audio.shape[1])
+            init_audio = convert_audio(init_audio, init_audio_sr or self.sample_rate, self.sample_rate, channels)
             init_latent = self.get_emb(init_audio.to(dev))
         if init_latent is not None:
             init_latent = init_latent.to(dev, torch.float32)

@@ -90,11 +90,30 @@ def make_config2_golden():
     print("  %-28s %8.1f KB" % ("unet_full_c2.pt", os.path.getsize(os.path.join(GOLD, "unet_full_c2.pt")) / 1024))
 
 
+def make_conditioner_golden():
+    """Int / Number conditioners of the reference (jen1/conditioners.py:114-164) on seeded weights: state dicts, inputs
+    and outputs (the T5 conditioner's pretrained weights are unreachable offline: parity unpinned for it)."""
+    ref_import.install_shims()
+    from jen1.conditioners import IntConditioner, NumberConditioner
+    torch.manual_seed(3)
+    ic, nc = IntConditioner(64, 0, 512), NumberConditioner(64, 0, 512)
+    ints, floats = [3, 600, 0, 77], [3.0, 700.0, 100.5, 0.25]
+    with torch.no_grad():
+        io, no = ic(ints, "cpu"), nc(floats, "cpu")
+    torch.save(dict(int_sd=ic.state_dict(), num_sd=nc.state_dict(), ints=ints, floats=floats,
+                    int_out=[t.clone() for t in io], num_out=[t.clone() for t in no]),
+               os.path.join(GOLD, "conditioners.pt"))
+    print("  %-28s %8.1f KB" % ("conditioners.pt", os.path.getsize(os.path.join(GOLD, "conditioners.pt")) / 1024))
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     ref_import.install_shims()
     if len(sys.argv) > 1 and sys.argv[1] == "c2":
         make_config2_golden()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "cond":
+        make_conditioner_golden()
         return
 
     # ---- 1. state_dict inventory of the reference (names, shapes, order) -------------------------------
@@ -182,6 +201,7 @@ def main():
         pass
     torch.save(dict(weights_seed=0, cases=full), os.path.join(GOLD, "unet_full.pt"))
     make_config2_golden()
+    make_conditioner_golden()
     print("golden fixtures written to", GOLD)
     for fn in sorted(os.listdir(GOLD)):
         print("  %-28s %8.1f KB" % (fn, os.path.getsize(os.path.join(GOLD, fn)) / 1024))

@@ -92,3 +92,62 @@ def test_latent_frame_algebra_and_level_lengths():
     assert d.level_lengths(4545) == [4545, 4545, 1137, 285, 72, 36, 18, 9, 5, 3]
     assert d.level_lengths(1515) == [1515, 1515, 379, 95, 24, 12, 6, 3, 2, 1]
     assert d.num_params() == 296543106
+
+
+def test_int_and_number_conditioners_match_reference_golden(golden_dir):
+    """reference jen1/conditioners.py:114-164 (+ utils/module.py NumberEmbedder) on the reference's own seeded weights."""
+    import os
+
+    import torch
+
+    from jen1_b200.conditioners import IntConditioner, NumberConditioner
+    fx = torch.load(os.path.join(golden_dir, "conditioners.pt"))
+    ic = IntConditioner(64, 0, 512)
+    ic.int_embedder.weight.data.copy_(fx["int_sd"]["int_embedder.weight"])
+    nc = NumberConditioner(64, 0, 512)
+    nc.embedder.load_reference_state_dict(fx["num_sd"])
+    with torch.no_grad():
+        io, no = ic(fx["ints"], "cpu"), nc(fx["floats"], "cpu")
+    assert torch.equal(io[0], fx["int_out"][0]) and torch.equal(io[1], fx["int_out"][1])
+    assert torch.allclose(no[0], fx["num_out"][0], atol=1e-6, rtol=0) and torch.equal(no[1], fx["num_out"][1])
+
+
+def test_multi_conditioner_factory_builds_every_type():
+    """reference utils/script_util.py:151-178, intended semantics (the reference returns inside its loop)."""
+    from jen1_b200.conditioners import RandomTextConditioner, create_multi_conditioner
+    mc = create_multi_conditioner(text_conditioner=RandomTextConditioner())
+    out = mc([{"prompt": "a song", "seconds_start": 3, "seconds_total": 100.0},
+              {"prompt": ["wrapped"], "seconds_start": 600, "seconds_total": 30}], "cpu")
+    assert set(out) == {"prompt", "seconds_start", "seconds_total"}
+    assert out["prompt"][0].shape == (2, 128, 1024) and out["prompt"][1].shape == (2, 128)
+    assert out["seconds_start"][0].shape == (2, 1, 1024) and out["seconds_total"][0].shape == (2, 1, 1024)
+    import pytest
+    with pytest.raises(ValueError, match="not found in batch metadata"):
+        mc([{"prompt": "x"}], "cpu")
+
+
+def test_convert_audio_resampling_identities():
+    """`convert_audio` (reference generation.py:95 -> encodec.utils / julius.resample_frac; parity unpinned, julius is not
+    installed): output length floor(new * L / old), DC preserved, a band-limited sine survives 44.1k -> 48k -> 44.1k, and
+    channel adaptation follows the encodec rules."""
+    import math
+
+    import torch
+
+    from jen1_b200.generation import convert_audio, resample_frac
+    L, old, new = 44100, 44100, 48000
+    t = torch.arange(L) / old
+    x = torch.stack([torch.sin(2 * math.pi * 440 * t), torch.ones(L) * 0.3]).unsqueeze(0)  # [1, 2, L]
+    y = resample_frac(x, old, new)
+    assert y.shape == (1, 2, int(new * L / old))
+    assert (y[0, 1, 100:-100] - 0.3).abs().max() < 1e-4
+    t2 = torch.arange(y.shape[-1]) / new
+    assert (y[0, 0, 500:-500] - torch.sin(2 * math.pi * 440 * t2)[500:-500]).abs().max() < 2e-3
+    back = resample_frac(y, new, old)
+    n = min(back.shape[-1], L)
+    assert (back[0, 0, 500:n - 500] - x[0, 0, 500:n - 500]).abs().max() < 4e-3
+    assert resample_frac(x, 48000, 48000) is x
+    mono = convert_audio(x, 48000, 48000, 1)
+    assert mono.shape == (1, 1, L) and torch.allclose(mono[0, 0], x[0].mean(0))
+    st = convert_audio(x[:, :1], 48000, 48000, 2)
+    assert st.shape == (1, 2, L) and torch.equal(st[0, 0], st[0, 1])
