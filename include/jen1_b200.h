@@ -101,6 +101,13 @@ int jen1_sample_begin(void* handle, const float* coef_host, int S, const float* 
 int jen1_sample_step(void* handle, int step, float* x, const float* noise, const uint8_t* drop_mask,
                      jen1_stream_t stream);
 
+/* The attention core alone -- reference jen1/model/blocks.py:355-380 (AttentionBase.forward: softmax(q k^T d^-1/2) v per head,
+ * causal mask :304-319) -- on a packed DEVICE bf16 tensor qkv[B][N][3*H*d] (q | k | v, what Attention.to_q / to_kv produce);
+ * out: DEVICE bf16 [B][N][H*d].  impl 0: tcgen05 kernels (single-tile up to 256 keys, key-tiled online softmax beyond),
+ * 1: fp32-FMA core (the strict-mode kernel), 2: force the key-tiled kernel.  bf16 engines only. */
+int jen1_attention_forward(void* handle, const void* qkv_bf16, void* out_bf16, int B, int N, int H, int d, int causal,
+                           int impl, jen1_stream_t stream);
+
 /* Introspection for tests / benchmarks. */
 int64_t jen1_engine_launch_count(void* handle);        /* kernels launched (or replayed) so far */
 int64_t jen1_engine_weight_bytes(void* handle);        /* device bytes of packed weights streamed per step */

@@ -43,6 +43,8 @@ SIGNATURES = {
     "jen1_sample_begin": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                     C.c_float, C.c_int, C.c_float, C.c_int, C.c_int, C.c_void_p]),
     "jen1_sample_step": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "jen1_attention_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_int, C.c_void_p]),
     "jen1_engine_launch_count": (C.c_int64, [C.c_void_p]),
     "jen1_engine_weight_bytes": (C.c_int64, [C.c_void_p]),
     "jen1_engine_umma_launch_count": (C.c_int64, [C.c_void_p]),

@@ -1,0 +1,540 @@
+// Key-tiled tcgen05 / TMEM attention with online softmax for bf16 storage on sm_100a (reference jen1/model/blocks.py:355-380
+// AttentionBase.forward, causal mask :304-319) -- the general-length companion of attn_umma.cu (which holds a whole head's
+// keys in one TMEM accumulator, <= 256 keys, the model's own shapes).  One CTA = (batch row, head, 128-query tile); the
+// keys stream through in tiles of 128:
+//
+//   loaders (warps 5-7)   K_j, V_j tiles -> 2-stage shared-memory ring with cp.async (K-major 128-byte-swizzled rows; V is
+//                         consumed as an MN-major operand straight from its [key][channel] layout)
+//   MMA issuer (warp 4)   S_j = Q K_j^T  -> TMEM buffer j & 1 (2 x 128 columns);  O_j = P_j V_j -> TMEM buffer 2 + (j & 1).
+//                         S_{j+1} is issued BEFORE P_j V_j, so the tensor core computes the next logits while the softmax
+//                         warps are busy with the current ones
+//   softmax (warps 0-3)   thread == query row (TMEM lane): running max m and sum l in base 2 (online softmax), P_j = 2^(s-m)
+//                         rounded to bf16 into a swizzled A tile; the partial product O_j comes back from TMEM and is folded
+//                         into register accumulators  o = o * 2^(m_old - m_new) + O_j  -- no read-modify-write of TMEM and no
+//                         separate correction pass
+//
+// Five mbarrier pipelines connect them (kv_full/kv_empty, s_full/s_empty, p_full, o_full/o_empty).  Causal tiles that lie
+// completely above the diagonal are skipped.  Keys beyond the key count are zero-filled and excluded from the softmax.
+#include <cuda.h>
+#include <float.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace jen1 {
+
+namespace {
+
+constexpr int kFaThreads = 384;  // warps 0-3 softmax A, 4 MMA issuer, 5-7 loaders, 8-11 softmax B
+constexpr int kFaLoaders = 96;   // warps 5-7
+constexpr int kBN = 128;         // keys per tile
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// TMA: one [1][128 rows][64 channels] box of the packed [B][N][ld] bf16 tensor -> a 16 KB K-major tile in the 128-byte
+// swizzle the UMMA descriptors expect; rows beyond N arrive as zeros
+__device__ __forceinline__ void tma_load_tile(void* dst, const CUtensorMap* tm, int c0, int row0, int b, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(row0), "r"(b), "r"(smem_u32(bar))
+      : "memory");
+}
+// suspending wait (hardware time-limited sleep) for the warps whose waits are long: keeps them off the issue slots
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// 64 consecutive accumulator columns of this thread's TMEM lane in ONE load (one wait instead of four)
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
+  uint32_t r[64];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,"
+      "%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%64];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]),
+        "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]),
+        "=r"(r[46]), "=r"(r[47]), "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]),
+        "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
+}
+// 2^x with the single-instruction hardware approximation (2 ulp; the result is rounded to bf16 right away)
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+// DMAX: head-dim capacity of the register accumulators (64 or 128)
+template <int DMAX>
+__global__ void __launch_bounds__(kFaThreads, 1) attn_flash_kernel(const __grid_constant__ AttnParams p,
+                                                                   const __grid_constant__ CUtensorMap tmap, const int use_tma) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int i0 = blockIdx.x * 128, h = blockIdx.y, r = blockIdx.z;
+  const int d = p.d, M = p.M, N = p.N;
+  const int DB = (d + 63) >> 6;                       // 64-channel blocks of the head dim
+  const int sh = d == 16 ? 1 : (d == 32 ? 2 : (d == 64 ? 3 : 4));
+  const int cpr = 1 << sh;                            // 16-byte chunks per head row
+  const uint32_t tile_bytes = (uint32_t)DB * 128u * 128u;  // one Q / K / V tile
+  const int NS = d <= 64 ? 4 : 2;                     // K / V ring depth (what fits next to Q and P)
+  uint8_t* Qs = smem;
+  uint8_t* Ks = Qs + tile_bytes;                      // [NS stages]
+  uint8_t* Vs = Ks + NS * tile_bytes;                 // [NS stages]
+  uint8_t* Ps = Vs + NS * tile_bytes;                 // [2 key blocks][128 queries][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Ps + 2 * 128 * 128);
+  uint64_t* q_full = bars;           // 1: producers of Q (all threads)
+  uint64_t* kv_full = bars + 1;      // [4] loaders -> MMA
+  uint64_t* kv_empty = bars + 5;     // [4] MMA (commit) -> loaders
+  uint64_t* s_full = bars + 9;       // [2] MMA (commit) -> softmax
+  uint64_t* s_empty = bars + 11;     // [2] softmax -> MMA
+  uint64_t* p_full = bars + 13;      // softmax -> MMA
+  uint64_t* o_full = bars + 14;      // [2] MMA (commit) -> softmax
+  uint64_t* o_empty = bars + 16;     // [2] softmax -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  float* xbuf = reinterpret_cast<float*>(bars + 20);  // [2 parities][2 halves][128 rows]: row-max / row-sum exchange
+
+  if (tid == 128) {
+    mbar_init(q_full, use_tma ? 1 : kFaThreads);
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(&kv_full[s], use_tma ? 1 : kFaLoaders);
+      mbar_init(&kv_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], 256);
+      mbar_init(&o_full[s], 1);
+      mbar_init(&o_empty[s], 256);
+    }
+    mbar_init(p_full, 256);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  // key tiles this query tile needs (causal: tiles completely above the diagonal are skipped)
+  int nt = (M + kBN - 1) / kBN;
+  if (p.causal) {
+    const int last_key = min(M - 1, i0 + 127 + (M - N));
+    nt = min(nt, last_key / kBN + 1);
+  }
+
+  // ---- Q tile (once): TMA (head dims that are multiples of 64) or all threads with cp.async; chunks beyond the head
+  //      dim inside the last 64-channel block read as zero
+  if (use_tma) {
+    if (tid == 160) {
+      mbar_expect_tx(q_full, tile_bytes);
+      for (int db = 0; db < DB; ++db) tma_load_tile(Qs + (size_t)db * 128 * 128, &tmap, p.q_off + h * d + db * 64, i0, r, q_full);
+    }
+  } else {
+    const int nqr = min(128, N - i0);
+    const bf16* qsrc = (const bf16*)p.q + ((size_t)r * N + i0) * p.q_ld + p.q_off + h * d;
+    for (int i = tid; i < (nqr << sh); i += kFaThreads) {
+      const int rw = i >> sh, part = i & (cpr - 1);
+      cp_async16(Qs + ((uint32_t)(part >> 3) * 128u + (uint32_t)rw) * 128u + (uint32_t)(((part & 7) ^ (rw & 7)) * 16),
+                 qsrc + (size_t)rw * p.q_ld + part * 8);
+    }
+    for (int i = (nqr << sh) + tid; i < (128 << sh); i += kFaThreads) {  // query rows beyond N: zeros (never stored)
+      const int rw = i >> sh, part = i & (cpr - 1);
+      *reinterpret_cast<uint4*>(Qs + ((uint32_t)(part >> 3) * 128u + (uint32_t)rw) * 128u + (uint32_t)(((part & 7) ^ (rw & 7)) * 16)) =
+          make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (cpr < 8) {
+      const int zc = 8 - cpr;
+      for (int it = tid; it < 128 * zc; it += kFaThreads) {
+        const int rw = it / zc, ch = cpr + (it - rw * zc);
+        *reinterpret_cast<uint4*>(Qs + (uint32_t)rw * 128u + (uint32_t)((ch ^ (rw & 7)) * 16)) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_all;" ::: "memory");
+    fence_async_smem();
+    mbar_arrive(q_full);
+  }
+
+  if (warp >= 5 && warp < 8) {
+    // ======================================================================== K / V loaders
+    if (use_tma) {  // one thread: 2 * DB bulk tensor copies per key tile, completion counted in bytes on kv_full
+      if (tid == 160) {
+        for (int j = 0; j < nt; ++j) {
+          const int s = j % NS;
+          if (j >= NS) mbar_wait_sleep(&kv_empty[s], (uint32_t)((j / NS - 1) & 1));
+          mbar_expect_tx(&kv_full[s], 2 * tile_bytes);
+          for (int db = 0; db < DB; ++db) {
+            tma_load_tile(Ks + (size_t)s * tile_bytes + (size_t)db * 128 * 128, &tmap, p.k_off + h * d + db * 64, j * kBN, r, &kv_full[s]);
+            tma_load_tile(Vs + (size_t)s * tile_bytes + (size_t)db * 128 * 128, &tmap, p.v_off + h * d + db * 64, j * kBN, r, &kv_full[s]);
+          }
+        }
+      }
+      __syncwarp();
+    } else {
+    const int lt = tid - 160;
+    const bf16* kbase = (const bf16*)p.kv + (size_t)r * N * p.kv_ld + h * d;  // self-attention layout: key rows r * N + j
+    for (int j = 0; j < nt; ++j) {
+      const int s = j % NS;
+      if (j >= NS) mbar_wait_sleep(&kv_empty[s], (uint32_t)((j / NS - 1) & 1));
+      uint8_t* kt = Ks + (size_t)s * tile_bytes;
+      uint8_t* vt = Vs + (size_t)s * tile_bytes;
+      const int j0 = j * kBN;
+      for (int i = lt; i < (kBN << (sh + 1)); i += kFaLoaders) {
+        const int v = i >= (kBN << sh) ? 1 : 0;
+        const int q = i - (v ? (kBN << sh) : 0);
+        const int rw = q >> sh, part = q & (cpr - 1);
+        uint8_t* dst = (v ? vt : kt) + ((uint32_t)(part >> 3) * 128u + (uint32_t)rw) * 128u + (uint32_t)(((part & 7) ^ (rw & 7)) * 16);
+        if (j0 + rw < M)
+          cp_async16(dst, kbase + (size_t)(j0 + rw) * p.kv_ld + (v ? p.v_off : p.k_off) + part * 8);
+        else
+          *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+      }
+      if (cpr < 8 && j < NS) {  // zero chunks beyond the head dim: once per stage (never overwritten afterwards)
+        const int zc = 8 - cpr;
+        for (int it = lt; it < 2 * kBN * zc; it += kFaLoaders) {
+          const int v = it >= kBN * zc ? 1 : 0;
+          const int q = it - (v ? kBN * zc : 0);
+          const int rw = q / zc, ch = cpr + (q - rw * zc);
+          *reinterpret_cast<uint4*>((v ? vt : kt) + (uint32_t)rw * 128u + (uint32_t)((ch ^ (rw & 7)) * 16)) = make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
+      asm volatile("cp.async.commit_group;\n\tcp.async.wait_all;" ::: "memory");
+      fence_async_smem();
+      mbar_arrive(&kv_full[s]);
+    }
+    }
+  } else if (warp == 4) {
+    // ======================================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBN >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(d >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t q_addr = smem_u32(Qs), p_addr = smem_u32(Ps);
+      auto issue_s = [&](int j) {
+        const int s = j & 1, ks = j % NS;
+        mbar_wait_sleep(&kv_full[ks], (uint32_t)((j / NS) & 1));
+        if (j >= 2) mbar_wait(&s_empty[s], (uint32_t)(((j >> 1) - 1) & 1));  // softmax has read S_{j-2}
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(Ks + (size_t)ks * tile_bytes);
+        uint32_t acc = 0;
+        for (int db = 0; db < DB; ++db) {
+          const int kmax = min(4, (d - db * 64) / 16);
+          for (int kk = 0; kk < kmax; ++kk) {
+            const uint64_t ad = make_desc_sw128(q_addr + (uint32_t)db * 128u * 128u + (uint32_t)kk * 32u, 16u, 1024u);
+            const uint64_t bd = make_desc_sw128(k_addr + (uint32_t)db * 128u * 128u + (uint32_t)kk * 32u, 16u, 1024u);
+            umma_bf16(tmem_base + (uint32_t)(s * 128), ad, bd, idesc_s, acc);
+            acc = 1;
+          }
+        }
+        umma_commit(&s_full[s]);
+      };
+      auto issue_o = [&](int j) {
+        const int s = j & 1;
+        mbar_wait_sleep(p_full, (uint32_t)(j & 1));                            // P_j written
+        if (j >= 2) mbar_wait(&o_empty[s], (uint32_t)(((j >> 1) - 1) & 1));    // softmax has read O_{j-2}
+        tc_fence_after();
+        const int ks = j % NS;
+        const uint32_t v_addr = smem_u32(Vs + (size_t)ks * tile_bytes);
+        uint32_t acc = 0;
+        for (int k16 = 0; k16 < kBN / 16; ++k16) {
+          const uint64_t ad = make_desc_sw128(p_addr + (uint32_t)(k16 >> 2) * 128u * 128u + (uint32_t)(k16 & 3) * 32u, 16u, 1024u);
+          const uint64_t bd = make_desc_sw128(v_addr + (uint32_t)k16 * 2048u, 128u * 128u, 1024u);
+          umma_bf16(tmem_base + (uint32_t)(256 + s * 128), ad, bd, idesc_o, acc);
+          acc = 1;
+        }
+        umma_commit(&o_full[s]);
+        umma_commit(&kv_empty[ks]);  // K_j and V_j are free once S_j and O_j are complete
+      };
+      mbar_wait(q_full, 0);
+      tc_fence_after();
+      for (int j = 0; j < nt; ++j) {
+        issue_s(j);
+        if (j > 0) issue_o(j - 1);
+      }
+      issue_o(nt - 1);
+    }
+    __syncwarp();
+  } else {
+    // ======================================================================== online softmax + accumulation
+    // Two warpgroups share every row: `half` 0 (warps 0-3) owns key columns [0, 64) of each tile and output channels
+    // [0, d/2), half 1 (warps 8-11) the other halves.  The row maximum is exchanged through shared memory (one named
+    // barrier per tile); the running sum is kept per half and combined at the end.  Each thread: 64 logits in
+    // registers (ONE TMEM load per tile), 64 exponentials, one 64-key block of the P row, d/2 accumulators.
+    const int half = warp >> 3;                       // 0 / 1
+    const int rowi = (warp & 3) * 32 + lane;          // query row of this thread == TMEM lane
+    const int i = i0 + rowi;
+    const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const float sc = p.scale * 1.4426950408889634f;   // base-2 softmax
+    const int jmax = p.causal ? i + (M - N) : M - 1;  // last key this query may see
+    constexpr int DH = DMAX / 2;
+    const int dc = d >= 64 ? d / 2 : (half == 0 ? d : 0);  // output channels folded by this thread: [half * dc, +dc)
+    float m = -FLT_MAX, l = 0.f;
+    float o[DH];
+#pragma unroll
+    for (int e = 0; e < DH; ++e) o[e] = 0.f;
+    uint8_t* prow = Ps + (size_t)half * 128 * 128 + (size_t)rowi * 128;
+    for (int j = 0; j < nt; ++j) {
+      const int s = j & 1, j0 = j * kBN + half * 64;
+      mbar_wait(&s_full[s], (uint32_t)((j >> 1) & 1));
+      tc_fence_after();
+      float v[64];
+      tmem_ld64(trow + (uint32_t)(s * 128 + half * 64), v);
+      tc_fence_before();
+      mbar_arrive(&s_empty[s]);  // the logits are in registers: the TMEM buffer may be overwritten
+      const int kmaxv = min(jmax, M - 1) - j0;  // last valid key of this thread's 64 (may be < 0)
+      const bool edge = kmaxv < 63;
+      float mx = -FLT_MAX;
+      if (!edge) {
+#pragma unroll
+        for (int q = 0; q < 64; ++q) mx = fmaxf(mx, v[q]);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 64; ++q)
+          if (q <= kmaxv) mx = fmaxf(mx, v[q]);
+      }
+      mx = (mx == -FLT_MAX) ? mx : mx * sc;  // sc > 0: max commutes with the scaling
+      float* xb = xbuf + (size_t)(j & 1) * 256;
+      xb[half * 128 + rowi] = mx;
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      mx = fmaxf(fmaxf(mx, xb[(half ^ 1) * 128 + rowi]), m);
+      const float alpha = ex2_fast(m - mx);
+      m = mx;
+      float sum = 0.f;
+      if (j > 0) mbar_wait(&o_full[(j - 1) & 1], (uint32_t)(((j - 1) >> 1) & 1));  // P V_{j-1} done: the P tile is free
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {  // 8 keys = one 16-byte chunk of the P row
+        float e[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float pj = ex2_fast(fmaf(v[c * 8 + q], sc, -mx));
+          if (edge && c * 8 + q > kmaxv) pj = 0.0f;
+          sum += pj;  // (the bf16 rounding of P happens in pack2; the row sum keeps the unrounded terms)
+          e[q] = pj;
+        }
+        *reinterpret_cast<uint4*>(prow + ((c ^ (rowi & 7)) * 16)) = make_uint4(pack2(e[0], e[1]), pack2(e[2], e[3]), pack2(e[4], e[5]), pack2(e[6], e[7]));
+      }
+      fence_async_smem();
+      mbar_arrive(p_full);
+      // fold the PREVIOUS tile's partial product into the accumulators (its MMA ran while this tile's logits were being
+      // exponentiated): o_{j-1} = o_{j-2} * alpha_{j-1} + O_{j-1}, then expressed at this tile's maximum (* alpha_j)
+      if (j > 0) {
+        const int so = (j - 1) & 1;
+        tc_fence_after();
+        const uint32_t to = trow + (uint32_t)(256 + so * 128 + half * dc);
+        if (dc == 64) {
+          if constexpr (DH >= 64) {
+            float w[64];
+            tmem_ld64(to, w);
+#pragma unroll
+            for (int q = 0; q < 64; ++q) o[q] = (o[q] + w[q]) * alpha;
+          }
+        } else {
+#pragma unroll
+          for (int c0 = 0; c0 < DH; c0 += 16) {
+            if (c0 < dc) {  // dc is a multiple of 16 here except d = 16 split... (d >= 64: dc = 32; d < 64: dc = d or 0)
+              float w[16];
+              tmem_ld16(to + (uint32_t)c0, w);
+#pragma unroll
+              for (int q = 0; q < 16; ++q) o[c0 + q] = (o[c0 + q] + w[q]) * alpha;
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&o_empty[so]);
+      }
+      l = l * alpha + sum;
+    }
+    {  // last tile's partial product; the two halves of the row sum are combined through shared memory
+      const int so = (nt - 1) & 1;
+      float* xb = xbuf + (size_t)(nt & 1) * 256;
+      xb[half * 128 + rowi] = l;
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      const float inv = 1.0f / (xb[rowi] + xb[128 + rowi]);
+      mbar_wait(&o_full[so], (uint32_t)(((nt - 1) >> 1) & 1));
+      tc_fence_after();
+      const uint32_t to = trow + (uint32_t)(256 + so * 128 + half * dc);
+      bf16* orow = (bf16*)p.out + ((size_t)r * N + (i < N ? i : 0)) * p.C + h * d + half * dc;
+#pragma unroll
+      for (int c0 = 0; c0 < DH; c0 += 16) {
+        if (c0 < dc) {
+          float w[16];
+          tmem_ld16(to + (uint32_t)c0, w);
+          if (i < N) {
+            *reinterpret_cast<uint4*>(orow + c0) =
+                make_uint4(pack2((o[c0] + w[0]) * inv, (o[c0 + 1] + w[1]) * inv), pack2((o[c0 + 2] + w[2]) * inv, (o[c0 + 3] + w[3]) * inv),
+                           pack2((o[c0 + 4] + w[4]) * inv, (o[c0 + 5] + w[5]) * inv), pack2((o[c0 + 6] + w[6]) * inv, (o[c0 + 7] + w[7]) * inv));
+            *reinterpret_cast<uint4*>(orow + c0 + 8) =
+                make_uint4(pack2((o[c0 + 8] + w[8]) * inv, (o[c0 + 9] + w[9]) * inv), pack2((o[c0 + 10] + w[10]) * inv, (o[c0 + 11] + w[11]) * inv),
+                           pack2((o[c0 + 12] + w[12]) * inv, (o[c0 + 13] + w[13]) * inv), pack2((o[c0 + 14] + w[14]) * inv, (o[c0 + 15] + w[15]) * inv));
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+}  // namespace
+
+bool attn_flash_supported(const AttnParams& p) {
+  const int d = p.d;
+  if (p.cross) return false;  // the context caches have <= 129 rows: attn_umma.cu's single-tile kernel covers them
+  if (!(d == 16 || d == 32 || d == 64 || d == 128)) return false;
+  if (p.M < 1 || p.N < 1 || p.M != p.N) return false;  // self-attention: keys are the rows of the same tensor
+  if ((p.q_ld & 7) || (p.q_off & 7) || (p.C & 7) || (p.kv_ld & 7) || (p.k_off & 7) || (p.v_off & 7)) return false;
+  return true;
+}
+
+static size_t attn_flash_smem(int d) {
+  const int DB = (d + 63) / 64, NS = d <= 64 ? 4 : 2;
+  return (size_t)(1 + 2 * NS) * DB * 128 * 128 + 2 * 128 * 128 + 160 + 2 * 2 * 128 * 4 + 1024;
+}
+
+cudaError_t attn_flash_init() {
+  cudaError_t e = cudaFuncSetAttribute(attn_flash_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_flash_smem(64));
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(attn_flash_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_flash_smem(128));
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(f);
+    (void)cudaGetLastError();
+  }
+  return fn;
+}
+
+cudaError_t launch_attention_flash(const AttnParams& p, bool pdl, cudaStream_t stream) {
+  if (!attn_flash_supported(p)) return cudaErrorInvalidValue;
+  // TMA staging when q / k / v live in one packed tensor and the head dim fills whole 64-channel blocks
+  CUtensorMap tm;
+  memset(&tm, 0, sizeof(tm));
+  int use_tma = 0;
+  if (p.d % 64 == 0 && p.q == p.kv && p.q_ld == p.kv_ld && encode_tiled_fn() != nullptr) {
+    const cuuint64_t dims[3] = {(cuuint64_t)p.kv_ld, (cuuint64_t)p.N, (cuuint64_t)p.B2};
+    const cuuint64_t strides[2] = {(cuuint64_t)p.kv_ld * 2, (cuuint64_t)p.N * p.kv_ld * 2};
+    const cuuint32_t box[3] = {64, 128, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    if (encode_tiled_fn()(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(p.kv), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+      use_tma = 1;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((p.N + 127) / 128, p.H, p.B2);
+  cfg.blockDim = dim3(kFaThreads);
+  cfg.dynamicSmemBytes = attn_flash_smem(p.d <= 64 ? 64 : 128);
+  cfg.stream = stream;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = pdl ? 1 : 0;
+  if (p.d <= 64) return cudaLaunchKernelEx(&cfg, attn_flash_kernel<64>, p, tm, use_tma);
+  return cudaLaunchKernelEx(&cfg, attn_flash_kernel<128>, p, tm, use_tma);
+}
+
+}  // namespace jen1

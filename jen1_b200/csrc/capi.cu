@@ -125,6 +125,16 @@ int64_t jen1_engine_umma_launch_count(void* h) { return h ? E(h)->umma_launch_co
 int64_t jen1_engine_umma_attn_launch_count(void* h) { return h ? E(h)->umma_attn_launch_count() : 0; }
 int64_t jen1_engine_fused_transformer_launch_count(void* h) { return h ? E(h)->fused_tr_launch_count() : 0; }
 
+int jen1_attention_forward(void* h, const void* qkv_bf16, void* out_bf16, int B, int N, int H, int d, int causal, int impl,
+                           jen1_stream_t stream) {
+  if (!h || !qkv_bf16 || !out_bf16) return 1;
+  try {
+    return E(h)->attention(qkv_bf16, out_bf16, B, N, H, d, causal, impl, (cudaStream_t)stream);
+  } catch (...) {
+    return 99;
+  }
+}
+
 int jen1_engine_debug_tensor(void* h, const char* name, float* host_out, int64_t capacity, int64_t* shape3) {
   if (!h || !name || !host_out || !shape3) return 1;
   try {

@@ -290,7 +290,8 @@ int Engine::finalize() {
     if (use_umma_ && conv_umma_init() != cudaSuccess) return fail("tcgen05 path initialisation failed");
     // shared-memory opt-ins of the attention kernels are per device as well (one engine per GPU in one process)
     if (attention_init() != cudaSuccess) return fail("attention kernel initialisation failed");
-    if (use_umma_ && attn_umma_init() != cudaSuccess) return fail("tcgen05 attention initialisation failed");
+    if (use_umma_ && (attn_umma_init() != cudaSuccess || attn_flash_init() != cudaSuccess))
+      return fail("tcgen05 attention initialisation failed");
     const char* ftr = getenv("JEN1_FUSED_TR");  // "1": run every Transformer1d as ONE fused launch (tr_umma.cu)
     use_fused_tr_ = ftr && strcmp(ftr, "1") == 0;
     if (use_umma_ && use_fused_tr_ && tr_umma_init() != cudaSuccess) return fail("fused transformer initialisation failed");
@@ -778,6 +779,9 @@ Act Engine::attention_core(const Act& q, const Act* kvself, const DAttn* cross, 
   cudaError_t e;
   if (use_umma_ && use_umma_attn_ && attn_umma_supported(p)) {
     e = launch_attention_umma(p, use_pdl_, st_);
+    ++umma_attn_launches_;
+  } else if (use_umma_ && use_umma_attn_ && attn_flash_supported(p)) {  // more than 256 keys: key-tiled online softmax
+    e = launch_attention_flash(p, use_pdl_, st_);
     ++umma_attn_launches_;
   } else {
     e = (dtype_ == JEN1_DTYPE_F32) ? launch_attention<float>(p, st_) : launch_attention<bf16>(p, st_);
@@ -1513,6 +1517,55 @@ int Engine::sample_step(int step, float* x, const float* noise, const uint8_t* d
     if (e && atoi(e) == step) dump_timeline(st);
   }
   return 0;
+}
+
+// ============================================================================================ attention operator
+// Stand-alone AttentionBase.forward (reference blocks.py:355-380) on a packed bf16 [B][N][3 * H * d] (q | k | v) tensor:
+// the kernels' own entry point for parity tests and the large-N tensor-pipe evidence.  impl: 0 = tcgen05 (single-tile
+// kernel up to 256 keys, key-tiled online-softmax kernel beyond), 1 = fp32-FMA core, 2 = force the key-tiled kernel.
+int Engine::attention(const void* qkv, void* out, int B, int N, int H, int d, int causal, int impl, cudaStream_t st) {
+  ok_ = true;
+  if (!finalized_) return fail("engine not finalized");
+  if (dtype_ != JEN1_DTYPE_BF16) return fail("attention operator: bf16 engines only");
+  if (B < 1 || N < 1 || H < 1 || d < 1) return fail("attention operator: bad shape");
+  cudaSetDevice(device_);
+  AttnParams p;
+  memset(&p, 0, sizeof(p));
+  const int C = H * d;
+  p.q = qkv;
+  p.q_ld = 3 * C;
+  p.q_off = 0;
+  p.B2 = B;
+  p.Bc = B;
+  p.N = N;
+  p.M = N;
+  p.H = H;
+  p.d = d;
+  p.C = C;
+  p.scale = (float)std::pow((double)d, -0.5);
+  p.causal = causal ? 1 : 0;
+  p.kv = qkv;
+  p.kv_ld = 3 * C;
+  p.k_off = C;
+  p.v_off = 2 * C;
+  p.cond_row = d_ctl_->cond_row;
+  p.out = out;
+  cudaError_t e;
+  if (impl == 1) {
+    if (d > 128 || (d & 7)) return fail("attention operator: head dim must be a multiple of 8, <= 128");
+    e = launch_attention<bf16>(p, st);
+  } else if (impl == 2 || !attn_umma_supported(p)) {
+    if (!use_umma_ || !attn_flash_supported(p)) return fail("attention operator: shape not supported by the tcgen05 kernels");
+    e = launch_attention_flash(p, false, st);
+    ++umma_attn_launches_;
+  } else {
+    if (!use_umma_) return fail("attention operator: tcgen05 path unavailable");
+    e = launch_attention_umma(p, false, st);
+    ++umma_attn_launches_;
+  }
+  ++launches_;
+  ck(e, "attention operator launch");
+  return ok_ ? 0 : 1;
 }
 
 // ============================================================================================ debug

@@ -101,6 +101,7 @@ class Engine {
                    int scale_cfg, float phi, int objective, int use_graph, cudaStream_t st);
   int sample_step(int step, float* x, const float* noise, const uint8_t* drop, cudaStream_t st);
   int debug_tensor(const char* name, float* host_out, int64_t capacity, int64_t* shape3);
+  int attention(const void* qkv, void* out, int B, int N, int H, int d, int causal, int impl, cudaStream_t st);
 
   const char* last_error() const { return err_.c_str(); }
   int64_t launch_count() const { return launches_; }

@@ -84,6 +84,10 @@ cudaError_t attention_init();   // per-device function attributes (call after cu
 cudaError_t attn_umma_init();
 // tcgen05 / TMEM implementation for bf16 storage (attn_umma.cu): head dim in {16, 32, 64, 128}, up to 256 keys
 bool attn_umma_supported(const AttnParams& p);
+// key-tiled online-softmax tcgen05 attention for any self-attention length (attn_flash.cu)
+bool attn_flash_supported(const AttnParams& p);
+cudaError_t attn_flash_init();
+cudaError_t launch_attention_flash(const AttnParams& p, bool pdl, cudaStream_t stream);
 cudaError_t launch_attention_umma(const AttnParams& p, bool pdl, cudaStream_t stream);
 
 // ---- fused Transformer1d (tr_umma.cu): one launch per transformer, a thread-block cluster per batch row walks the op list

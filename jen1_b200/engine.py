@@ -179,6 +179,18 @@ class Engine:
             dptr = C.c_void_p(drop.data_ptr())
         self._ck(self.lib.jen1_sample_step(self._h, int(step), C.c_void_p(x.data_ptr()), nptr, dptr, self._stream()))
 
+    def attention(self, qkv: torch.Tensor, heads: int, causal: bool = False, impl: str = "tcgen05") -> torch.Tensor:
+        """The attention core alone (reference blocks.py:355-380) on a packed bf16 [B, N, 3*C] (q | k | v) tensor."""
+        assert qkv.dtype == torch.bfloat16 and qkv.is_contiguous() and qkv.device == self.device and qkv.dim() == 3
+        B, N, C3 = qkv.shape
+        ch = C3 // 3
+        assert ch * 3 == C3 and ch % heads == 0
+        out = torch.empty((B, N, ch), device=self.device, dtype=torch.bfloat16)
+        self._ck(self.lib.jen1_attention_forward(self._h, C.c_void_p(qkv.data_ptr()), C.c_void_p(out.data_ptr()), B, N, heads,
+                                                 ch // heads, int(bool(causal)), {"tcgen05": 0, "fma": 1, "flash": 2}[impl],
+                                                 self._stream()))
+        return out
+
     # ------------------------------------------------------------------------------------------------
     def launch_count(self) -> int:
         return int(self.lib.jen1_engine_launch_count(self._h))
