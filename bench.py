@@ -16,7 +16,7 @@ GPU) -- the configuration the north-star's targets are quoted on; it fits one GP
   * `value`  : K steps timed with CUDA events on the launching stream, everything resident in HBM.
   * `e2e`    : the same metric through the public API -- `GaussianDiffusion.sample(model, shape, conditioning)`
                with the conditioning in pinned HOST memory (H2D inside the timed region) and the finished latent
-               read back to the host (D2H inside), K sampler steps per call; median of 5 calls.
+               read back to the host (D2H inside), K sampler steps per call; median of 7 calls.
   * `roofline`: whole-step HBM roofline (one CUDA-graph launch = one step): algorithmic bytes (jen1_b200.workload)
                / event-timed step duration vs MEASURED_PEAKS.json.
   * `cpu_baseline`: the reference's CPU path on this box's host cores (baseline/_ref when installed, else the oracle
@@ -518,9 +518,13 @@ def run_ours(args, wl, scaling):
 
     e2e = None
     if not args.no_e2e:
+        import gc
         e2e_call()  # warm (graph capture for this shape, allocator)
+        e2e_call()
         reps = []
-        for _ in range(5):
+        gc.collect()
+        gc.disable()  # a generational collection in the middle of a call is host time the GPU queue cannot hide
+        for _ in range(7):
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize(dev)
@@ -531,6 +535,7 @@ def run_ours(args, wl, scaling):
             if world > 1:
                 dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
             reps.append(t_e.item())
+        gc.enable()
         e_ms_step = sorted(reps)[len(reps) // 2] / Se
         h2d = (emb_p.numel() * 4 + mask_p.numel() + cc_p.numel() * 4)
         d2h = out_h.numel() * 4

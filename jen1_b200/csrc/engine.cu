@@ -1078,6 +1078,7 @@ bool Engine::pack_inputs(const float* x, int B, int T, Act* xpk, bool with_cc, c
 // ============================================================================================ caches
 int Engine::set_timesteps(const int64_t* t_host, int n, cudaStream_t st) {
   ok_ = true;
+  szone_ = nullptr;  // no statistics zone outside a forward
   if (!finalized_) return fail("engine not finalized");
   if (n < 1) return fail("set_timesteps: n must be >= 1");
   cudaSetDevice(device_);
@@ -1157,6 +1158,7 @@ int Engine::set_timesteps(const int64_t* t_host, int n, cudaStream_t st) {
 
 int Engine::set_context(const float* emb, const float* mask, int B, int S, cudaStream_t st) {
   ok_ = true;
+  szone_ = nullptr;
   if (!finalized_) return fail("engine not finalized");
   if (B < 1 || B > 128) return fail("set_context: batch must be in [1, 128]");
   if (S < 1 || S > d_.context_embedding_max_length) return fail("set_context: context length exceeds context_embedding_max_length");

@@ -230,7 +230,9 @@ class GaussianDiffusion:
         use_cfg = self.embedding_scale != 1.0
         # CUDA graphs cannot be captured on the legacy default stream: run the loop on a side stream
         cur = torch.cuda.current_stream(device)
-        side = torch.cuda.Stream(device)
+        side = model.__dict__.get("_side_stream")
+        if side is None or side.device != device:
+            side = model.__dict__["_side_stream"] = torch.cuda.Stream(device)  # one capture / replay stream per model
         side.wait_stream(cur)
         with torch.cuda.device(device), torch.cuda.stream(side):
             eng.sample_begin(self.ddim_coefficients(), conditioning["input_concat_cond"], B, T, causal,

@@ -25,7 +25,7 @@ KEYS = ["launch__grid_size", "launch__cluster_dim_z", "launch__block_size", "lau
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "smsp__inst_executed.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "smsp__average_warp_latency_per_inst_issued.ratio"]
-STEP_KERNELS = ("conv_umma_kernel", "attn_umma_kernel", "sampler_kernel", "pack_ncl_kernel", "attention_kernel")
+STEP_KERNELS = ("conv_umma_kernel", "attn_umma_kernel", "tr_umma_kernel", "sampler_kernel", "pack_ncl_kernel", "attention_kernel")
 
 
 def step_facts(path, steps):
@@ -81,12 +81,16 @@ def main(tag, label, steps=5):
                 if k in h:
                     i = h.index(k)
                     out.append("%-66s %-16s %s" % (k, rows[1][i], "  ".join(r[i][:40] for r in rows[2:])))
-        hot = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_lines.py"), os.path.join(G, rep), "1", "25"],
+            st = {k[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")]: rows[2][h.index(k)]
+                  for k in h if k.startswith("smsp__average_warps_issue_stalled_") and k.endswith("_per_issue_active.ratio")}
+            top = sorted(st.items(), key=lambda kv: -float(kv[1] or 0))[:8]
+            out.append("stall reasons (warps per issue-active cycle, first launch): " + ", ".join("%s %.2f" % (k, float(v)) for k, v in top))
+        hot = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_lines.py"), os.path.join(G, rep), "0", "25"],
                              capture_output=True, text=True).stdout
-        out.append("\n# source lines ranked by warp-stall samples (samples, warp-instructions executed, file:line)")
+        out.append("\n# SASS instructions ranked by warp-stall samples (samples, executions, instruction) -- first captured launch")
         out.append(hot)
         open(os.path.join(P, "%s_%s.txt" % (label, name)), "w").write("\n".join(out))
-        shutil.copy(os.path.join(G, rep), os.path.join(P, "%s_%s.ncu-rep" % (label, name)))
+        # (the binary .ncu-rep stays in gpurun_out/: only the text digest is committed)
     for extra in ("tl_c2.txt", "tl_c3.txt"):
         src = os.path.join(G, "%s_%s" % (tag, extra))
         if os.path.exists(src):

@@ -5,5 +5,5 @@ TAG=$1; T=$2; B=$3; OP=$4; CNT=${5:-2}
 O=gpurun_out
 mkdir -p $O
 SKIP=$((234 + OP))
-JEN1_TIMELINE= timeout 400 ncu --set full --clock-control none --import-source on -k regex:conv_umma -s $SKIP -c $CNT -o $O/${TAG} -f python scripts/timeline_plain.py $T $B > $O/${TAG}.log 2>&1
+JEN1_TIMELINE= timeout 400 ncu --set full --clock-control none --import-source on -k regex:conv_umma -s $SKIP -c $CNT -o $O/${TAG} -f python scripts/timeline.py --plain $T $B > $O/${TAG}.log 2>&1
 tail -3 $O/${TAG}.log

@@ -1,9 +1,16 @@
 #!/usr/bin/env python
-"""Print per-op phase clocks of the tcgen05 conv kernel for one UNet evaluation (JEN1_TIMELINE debugging aid)."""
+"""Print per-op phase clocks of the tcgen05 conv kernel for one UNet evaluation (JEN1_TIMELINE debugging aid).
+
+    python scripts/timeline.py [--plain] [T = 1515] [B = 1]
+"""
 import os
 import sys
-os.environ["JEN1_TIMELINE"] = "1"
-os.environ["JEN1_TRACE"] = "1"
+PLAIN = "--plain" in sys.argv  # no in-kernel clocks / plan trace: the bare two-evaluation workload for ncu captures
+if PLAIN:
+    sys.argv.remove("--plain")
+else:
+    os.environ["JEN1_TIMELINE"] = "1"
+    os.environ["JEN1_TRACE"] = "1"
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
