@@ -42,3 +42,20 @@ def test_sharded_sampling_matches_unsharded(dtype, tol):
     got = torch.cat(parts, 0)
     err = ((got - whole).norm() / whole.norm()).item()
     assert err < tol, err
+
+
+def test_nccl_gather_of_sharded_latents_across_gpus():
+    """The optional NCCL/NVLink gather of finished latents (jen1_b200/sharding.py:gather_latents) on real GPUs: torchrun
+    with one rank per GPU, uneven shards, gathered result == unsharded run (scripts/multigpu_check.py).  Needs >= 2 GPUs."""
+    import os
+    import subprocess
+    import sys
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(min(n, 4)), "--master-addr",
+           "127.0.0.1", "--master-port", "29531", os.path.join(root, "scripts", "multigpu_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "rel-L2 vs unsharded run" in r.stdout
