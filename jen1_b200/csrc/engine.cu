@@ -1342,9 +1342,9 @@ void Engine::dump_timeline(cudaStream_t st) {
       const long long t0 = t[0];
       for (int oi = 0; oi < TR_MAX_OPS && t[oi * 8] != 0; ++oi) {
         const long long* o = t + oi * 8;
-        fprintf(stderr, "[jen1-trtl] tr%02d op%02d start %.2f wait %.2f staged %.2f acc %.2f body %.2f fence %.2f\n", k, oi,
+        fprintf(stderr, "[jen1-trtl] tr%02d op%02d start %.2f wait %.2f staged %.2f acc %.2f body %.2f fence %.2f | mma: panel seen %.2f issued %.2f\n", k, oi,
                 (o[0] - t0) / 1965.0, (o[1] - t0) / 1965.0, (o[2] - t0) / 1965.0, (o[3] - t0) / 1965.0, (o[4] - t0) / 1965.0,
-                (o[5] - t0) / 1965.0);
+                (o[5] - t0) / 1965.0, o[6] ? (o[6] - t0) / 1965.0 : 0.0, o[7] ? (o[7] - t0) / 1965.0 : 0.0);
       }
     }
   }

@@ -119,7 +119,7 @@ struct TrOp {
 };
 struct TrParams {
   int B2, N, C, H, d, Bc, causal, n_ops, CS;
-  int NT, panel_bytes, smem_bytes, work_bytes, kvx_bytes, prestage, cross_op;  // filled by launch_tr_umma
+  int NT, panel_bytes, smem_bytes, work_bytes, kvx_bytes, prestage, cross_op, stages;  // filled by launch_tr_umma
   float scale, gn_eps;
   const long long* gn_stats;        // [Bx][32][2] fixed-point statistics of the input x (GroupNorm(32))
   const float *gn_gamma, *gn_beta;

@@ -37,8 +37,7 @@ namespace {
 constexpr int kThreads = 192;
 constexpr int kProd = 128;
 constexpr int kABytes = 128 * 64 * 2;
-constexpr int kStages = 5;
-constexpr int kRingBytes = kStages * kABytes;
+constexpr int kMinStages = 4, kMaxStages = 8;  // weight ring depth (runtime: what fits next to the work region)
 constexpr int kTmemCols = 256;
 constexpr int kSfgBytes = 4 * 32 * 2 * 4;  // per-warp GroupNorm fine-group sums of one M tile
 
@@ -191,7 +190,8 @@ __global__ void __launch_bounds__(kThreads, 1) tr_umma_kernel(const __grid_const
 
   // ---- shared memory carve-up: [weight ring][work region: panel | staging | stat cells  /  attention tiles][barriers]
   uint8_t* ring = smem;
-  uint8_t* work = smem + kRingBytes;
+  const int kStages = P.stages;
+  uint8_t* work = smem + (size_t)kStages * kABytes;
   uint8_t* panel = work;                                           // [K/64 blocks][NT rows][128 B]
   float* stage = reinterpret_cast<float*>(work + P.panel_bytes);   // [NT][128] fp32
   float* sfg = stage + (size_t)NT * 128;                           // [4 warps][32 fine groups][2]
@@ -201,8 +201,8 @@ __global__ void __launch_bounds__(kThreads, 1) tr_umma_kernel(const __grid_const
   uint8_t* kvx = work + P.work_bytes;                              // [K tile][V tile] of head `crank` (prestage only)
   const uint32_t kvx_half = (uint32_t)P.kvx_bytes >> 1;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P.smem_bytes - 256);
-  uint64_t* a_full = bars;            // [kStages]
-  uint64_t* a_empty = bars + 8;       // [kStages]
+  uint64_t* a_full = bars;            // [kMaxStages]
+  uint64_t* a_empty = bars + 8;       // [kMaxStages]
   uint64_t* panel_full = bars + 16;   // producers -> MMA (GEMM panel or attention tiles staged), 128 arrivals
   uint64_t* acc_full = bars + 17;     // MMA -> epilogue (tcgen05.commit)
   uint64_t* acc_empty = bars + 18;    // epilogue -> MMA (accumulator drained), 128 arrivals
@@ -274,6 +274,7 @@ __global__ void __launch_bounds__(kThreads, 1) tr_umma_kernel(const __grid_const
           mbar_wait(panel_full, n_panel & 1);
           ++n_panel;
           tc_fence_after();
+          if (P.timeline && crank == 0 && row == 0) P.timeline[oi * 8 + 6] = clock64();
           const uint32_t pbase = smem_u32(panel);
           for (int mt = crank; mt < mtiles; mt += CS) {
             if (n_acc_use > 0) {  // the previous accumulator contents have been read out
@@ -299,6 +300,7 @@ __global__ void __launch_bounds__(kThreads, 1) tr_umma_kernel(const __grid_const
             }
             umma_commit(acc_full);
             ++n_acc_use;
+            if (P.timeline && crank == 0 && row == 0 && mt == crank) P.timeline[oi * 8 + 7] = clock64();
           }
         } else {
           // attention: heads crank, crank + CS, ...
@@ -751,7 +753,7 @@ static size_t tr_kvx_bytes(int C, int H, int M) {  // K + V tiles of one head fo
   const int d = C / H, KP = (M + 15) / 16 * 16, DB = (d + 63) / 64;
   return 2 * (((size_t)DB * KP * 128 + 1023) / 1024 * 1024);
 }
-size_t tr_umma_smem_bytes(int N, int C, int H, int M) { return (size_t)kRingBytes + tr_work_bytes(N, C, H, M) + 256; }
+size_t tr_umma_smem_bytes(int N, int C, int H, int M) { return (size_t)kMinStages * kABytes + tr_work_bytes(N, C, H, M) + 256; }
 
 cudaError_t tr_umma_init() {
   cudaError_t e = cudaFuncSetAttribute(tr_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -769,9 +771,14 @@ cudaError_t launch_tr_umma(const TrParams& p_in, bool pdl, cudaStream_t stream) 
   for (int i = 0; i < p.n_ops; ++i)
     if (p.ops[i].type == TR_ATTN && p.ops[i].M > Mx) Mx = p.ops[i].M;
   p.work_bytes = (int)tr_work_bytes(p.N, p.C, p.H, Mx);
-  p.smem_bytes = (int)tr_umma_smem_bytes(p.N, p.C, p.H, Mx);
-  if (p.smem_bytes > 227 * 1024) return cudaErrorInvalidValue;
-  // cross-attention K / V tiles staged at kernel start when there is exactly one cross-attention op and room for them
+  const size_t limit = (size_t)227 * 1024;
+  if ((size_t)kMinStages * kABytes + p.work_bytes + 256 > limit) return cudaErrorInvalidValue;
+  // Shared memory budget, in order of what the op chain gains most from: (1) a weight ring deep enough to hold one whole
+  // M tile of the next op (C / 64 blobs: the stream then never stalls a tile on L2 latency), up to 8 stages; (2) the
+  // cross-attention K / V tiles staged at kernel start (only with exactly one cross-attention op); (3) more ring stages.
+  int stages = kMinStages;
+  const int want = p.C / 64 < kMaxStages ? (p.C / 64 > kMinStages ? p.C / 64 : kMinStages) : kMaxStages;
+  while (stages < want && (size_t)(stages + 1) * kABytes + p.work_bytes + 256 <= limit) ++stages;
   p.prestage = 0;
   p.kvx_bytes = 0;
   p.cross_op = -1;
@@ -783,12 +790,14 @@ cudaError_t launch_tr_umma(const TrParams& p_in, bool pdl, cudaStream_t stream) 
     }
   if (ncross == 1) {
     const size_t kvx = tr_kvx_bytes(p.C, p.H, p.ops[p.cross_op].M);
-    if ((size_t)p.smem_bytes + kvx <= (size_t)227 * 1024) {
+    if ((size_t)stages * kABytes + p.work_bytes + 256 + kvx <= limit) {
       p.prestage = 1;
       p.kvx_bytes = (int)kvx;
-      p.smem_bytes += (int)kvx;
     }
   }
+  while (stages < kMaxStages && (size_t)(stages + 1) * kABytes + p.work_bytes + 256 + p.kvx_bytes <= limit) ++stages;
+  p.stages = stages;
+  p.smem_bytes = (int)((size_t)stages * kABytes + p.work_bytes + 256 + p.kvx_bytes);
   // Cluster size: 16 CTAs per row when all rows' clusters can be resident at once, else 8 (a second wave of clusters
   // doubles the launch's duration; co-residency of 16-CTA clusters is limited by the SMs per GPC).
   if (p.CS == 16) {
