@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_C", "libjen1_b200.so")
+# JEN1_B200_LIB: A/B a variant build (scripts/build_variant.py) without touching the in-tree library
+LIB_PATH = os.environ.get("JEN1_B200_LIB") or os.path.join(_HERE, "_C", "libjen1_b200.so")
 MAX_LEVELS = 16
 
 DTYPE_F32, DTYPE_BF16 = 0, 1
