@@ -16,6 +16,7 @@
  *                                       jen1/model/model.py:299-376  |
  *   GaussianDiffusion.ddim_sample loop body                           | jen1_sample_begin / jen1_sample_step
  *                                       jen1/diffusion/gdm/gdm.py:202-222 |
+ *   self.audio_encoder.decoder(sample_embs)        generation.py:130  | jen1_codec_create / _load_tensor / _decode
  *
  * Conventions: every function returns 0 on success or a non-zero code; the message is available from
  * jen1_last_error(handle).  Nothing throws or aborts across the ABI.  A handle is bound to one CUDA device and
@@ -107,6 +108,39 @@ int jen1_sample_step(void* handle, int step, float* x, const float* noise, const
  * 1: fp32-FMA core (the strict-mode kernel), 2: force the key-tiled kernel.  bf16 engines only. */
 int jen1_attention_forward(void* handle, const void* qkv_bf16, void* out_bf16, int B, int N, int H, int d, int causal,
                            int impl, jen1_stream_t stream);
+
+/* ---- Encodec (SEANet) decoder: latent -> audio, the step after the sampling loop.
+ * Replaces `self.audio_encoder.decoder(sample_embs)` (reference generation.py:130; audio_encoder =
+ * EncodecModel.encodec_model_48khz(), generation.py:34, pip encodec==0.1.1).  The description mirrors the SEANetDecoder
+ * constructor arguments of that model (encodec/model.py encodec_model_48khz, encodec/modules/seanet.py). */
+#define JEN1_CODEC_MAX_RATIOS 8
+typedef struct Jen1CodecDesc {
+  int32_t channels;              /* audio channels (2) */
+  int32_t dimension;             /* latent channels (128) */
+  int32_t n_filters;             /* 32 */
+  int32_t n_ratios;
+  int32_t ratios[JEN1_CODEC_MAX_RATIOS]; /* decoder order (8, 5, 4, 2) */
+  int32_t kernel_size;           /* 7 */
+  int32_t last_kernel_size;      /* 7 */
+  int32_t residual_kernel_size;  /* 3 */
+  int32_t compress;              /* 2 */
+  int32_t lstm_layers;           /* 2 */
+  float eps;                     /* GroupNorm epsilon (1e-5) */
+} Jen1CodecDesc;
+int jen1_codec_create(const Jen1CodecDesc* desc, int device, void** out_handle);
+void jen1_codec_destroy(void* handle);
+const char* jen1_codec_last_error(void* handle);
+/* One tensor of the decoder's state_dict (fp32 host memory; names as in the pip package: model.N.conv.conv.weight ...). */
+int jen1_codec_load_tensor(void* handle, const char* name, const float* host_data, const int64_t* shape, int ndim);
+int jen1_codec_finalize(void* handle);
+size_t jen1_codec_workspace_bytes(void* handle, int B, int T);
+int jen1_codec_reserve(void* handle, int B, int T);
+/* latent: DEVICE fp32 [B][dimension][T]; audio: DEVICE fp32 [B][channels][T * hop]. */
+int jen1_codec_decode(void* handle, const float* latent, float* audio, int B, int T, jen1_stream_t stream);
+int64_t jen1_codec_launch_count(void* handle);
+int64_t jen1_codec_weight_bytes(void* handle);
+int jen1_codec_hop(void* handle);          /* samples per latent frame (320) */
+int jen1_codec_lstm_cluster(void* handle); /* CTAs per sequence of the LSTM cluster kernel */
 
 /* Introspection for tests / benchmarks. */
 int64_t jen1_engine_launch_count(void* handle);        /* kernels launched (or replayed) so far */

@@ -28,6 +28,14 @@ class Jen1ModelDesc(C.Structure):
     ]
 
 
+class Jen1CodecDesc(C.Structure):
+    _fields_ = [
+        ("channels", C.c_int32), ("dimension", C.c_int32), ("n_filters", C.c_int32), ("n_ratios", C.c_int32),
+        ("ratios", C.c_int32 * 8), ("kernel_size", C.c_int32), ("last_kernel_size", C.c_int32),
+        ("residual_kernel_size", C.c_int32), ("compress", C.c_int32), ("lstm_layers", C.c_int32), ("eps", C.c_float),
+    ]
+
+
 # every symbol include/jen1_b200.h declares: name -> (restype, argtypes)
 SIGNATURES = {
     "jen1_engine_create": (C.c_int, [C.POINTER(Jen1ModelDesc), C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
@@ -52,6 +60,18 @@ SIGNATURES = {
     "jen1_engine_umma_attn_launch_count": (C.c_int64, [C.c_void_p]),
     "jen1_engine_fused_transformer_launch_count": (C.c_int64, [C.c_void_p]),
     "jen1_engine_debug_tensor": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
+    "jen1_codec_create": (C.c_int, [C.POINTER(Jen1CodecDesc), C.c_int, C.POINTER(C.c_void_p)]),
+    "jen1_codec_destroy": (None, [C.c_void_p]),
+    "jen1_codec_last_error": (C.c_char_p, [C.c_void_p]),
+    "jen1_codec_load_tensor": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int]),
+    "jen1_codec_finalize": (C.c_int, [C.c_void_p]),
+    "jen1_codec_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
+    "jen1_codec_reserve": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "jen1_codec_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "jen1_codec_launch_count": (C.c_int64, [C.c_void_p]),
+    "jen1_codec_weight_bytes": (C.c_int64, [C.c_void_p]),
+    "jen1_codec_hop": (C.c_int, [C.c_void_p]),
+    "jen1_codec_lstm_cluster": (C.c_int, [C.c_void_p]),
 }
 
 _lib = None

@@ -1,13 +1,16 @@
 // extern "C" boundary of the engine (include/jen1_b200.h).  Plain pointers and sizes only; no exceptions cross.
 #include <new>
 
+#include "codec.h"
 #include "engine.h"
 
+using jen1::CodecDecoder;
 using jen1::Engine;
 
 namespace {
 thread_local char g_create_error[256] = "";
 inline Engine* E(void* h) { return reinterpret_cast<Engine*>(h); }
+inline CodecDecoder* K(void* h) { return reinterpret_cast<CodecDecoder*>(h); }
 }  // namespace
 
 extern "C" {
@@ -144,4 +147,58 @@ int jen1_engine_debug_tensor(void* h, const char* name, float* host_out, int64_t
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------- Encodec decoder
+int jen1_codec_create(const Jen1CodecDesc* desc, int device, void** out_handle) {
+  if (!desc || !out_handle) return 1;
+  *out_handle = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    snprintf(g_create_error, sizeof g_create_error, "no CUDA device %d (the codec engine has no CPU fallback)", device);
+    return 2;
+  }
+  CodecDecoder* k = new (std::nothrow) CodecDecoder(*desc, device);
+  if (!k) return 4;
+  *out_handle = k;
+  return 0;
+}
+void jen1_codec_destroy(void* h) { delete K(h); }
+const char* jen1_codec_last_error(void* h) { return h ? K(h)->last_error() : g_create_error; }
+int jen1_codec_load_tensor(void* h, const char* name, const float* host_data, const int64_t* shape, int ndim) {
+  if (!h || !name || !host_data || !shape) return 1;
+  try {
+    return K(h)->load_tensor(name, host_data, shape, ndim);
+  } catch (...) {
+    return 99;
+  }
+}
+int jen1_codec_finalize(void* h) {
+  if (!h) return 1;
+  try {
+    return K(h)->finalize();
+  } catch (...) {
+    return 99;
+  }
+}
+size_t jen1_codec_workspace_bytes(void* h, int B, int T) { return h ? K(h)->workspace_bytes(B, T) : 0; }
+int jen1_codec_reserve(void* h, int B, int T) {
+  if (!h) return 1;
+  try {
+    return K(h)->reserve(B, T);
+  } catch (...) {
+    return 99;
+  }
+}
+int jen1_codec_decode(void* h, const float* latent, float* audio, int B, int T, jen1_stream_t stream) {
+  if (!h) return 1;
+  try {
+    return K(h)->decode(latent, audio, B, T, reinterpret_cast<cudaStream_t>(stream));
+  } catch (...) {
+    return 99;
+  }
+}
+int64_t jen1_codec_launch_count(void* h) { return h ? K(h)->launch_count() : 0; }
+int64_t jen1_codec_weight_bytes(void* h) { return h ? K(h)->weight_bytes() : 0; }
+int jen1_codec_hop(void* h) { return h ? K(h)->hop() : 0; }
+int jen1_codec_lstm_cluster(void* h) { return h ? K(h)->lstm_cluster() : 0; }
 }  // extern "C"

@@ -1,0 +1,609 @@
+// Encodec (SEANet) decoder: latent [B][128][T] -> audio [B][2][T*hop]  (SURVEY.md section 8 row f1).
+//
+// Reference: generation.py:130 `self.audio_encoder.decoder(sample_embs)` with the 48 kHz model of pip encodec==0.1.1
+// (generation.py:34; the package is not vendored -- the algorithm restated here is encodec/modules/seanet.py
+// SEANetDecoder, conv.py SConv1d / SConvTranspose1d / pad1d / unpad1d, lstm.py SLSTM, norm.py; see
+// jen1_b200/codec_config.py for the layer list and oracle/codec_oracle.py for the CPU restatement).
+//
+// Data layout: channels-last fp32 [B][L][C].  Every conv output is kept RAW (before its GroupNorm(1, C)) together with
+// fixed-point (sum, sumsq) accumulators written by the producing kernel's epilogue (common.cuh); the consumer applies
+// GroupNorm + ELU + reflect padding while it loads its operand tile, so no normalisation / activation / padding pass
+// ever touches HBM:
+//   * SConv1d            = tap-GEMM, reflect index mapping in the prologue (conv_generic.cu PAD_REFLECT)
+//   * SConvTranspose1d   = stride-r phases x 2 taps; the UNTRIMMED output is stored (GroupNorm statistics cover it, as
+//                          encodec normalises before unpad1d) and consumers read the trimmed window (ConvSeg.row0/Lstore)
+//   * SEANetResnetBlock  = three tap-GEMMs; "shortcut + block" is never materialised: the next layer's prologue adds the
+//                          two normalised tensors (ConvParams.sum2)
+//   * SLSTM              = W_ih x_t for all t as one k=1 tap-GEMM, then a persistent thread-block CLUSTER per sequence:
+//                          W_hh lives in shared memory (fp16, sliced over the cluster's CTAs), h_t is broadcast over
+//                          distributed shared memory, one cluster barrier per time step; the skip connection is folded
+//                          into the next layer's prologue (sum2 with a plain second source).
+// All convs run on the fp32-FMA tap-GEMM (conv_generic.cu): this first version is correctness-first.
+#include "codec.h"
+
+#include <cuda_fp16.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace jen1 {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------ LSTM recurrence
+struct LstmParams {
+  const float* gx;    // [B][T][4H] = W_ih x_t + b_ih + b_hh (gate order i, f, g, o)
+  const uint4* whh;   // [CS][H/8][R] 8 fp16 each: columns 8*k8 .. 8*k8+7 of local row lr = g*U + u  (R = 4U)
+  float* hout;        // [B][T][H]
+  int T, H, CS, U;
+};
+
+__device__ __forceinline__ uint32_t lstm_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void lstm_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void lstm_st_remote(uint32_t local_addr, uint32_t rank, float4 v) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_addr), "r"(rank));
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ra), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// One cluster of CS CTAs per sequence; CTA `r` owns hidden units [r*U, (r+1)*U).  256 threads: thread (row = tid % R,
+// half = tid / R) accumulates half of the H columns of gate row `row`; the U "unit" threads then combine the gates.
+__global__ void __launch_bounds__(256) lstm_cluster_kernel(const LstmParams P) {
+  extern __shared__ __align__(16) uint8_t lsm[];
+  const int H = P.H, U = P.U, R = 4 * U, CS = P.CS;
+  uint4* W = reinterpret_cast<uint4*>(lsm);                                    // [H/8][R]
+  float* hbuf = reinterpret_cast<float*>(lsm + (size_t)(H / 8) * R * 16);      // [2][H]
+  float* part = hbuf + 2 * H;                                                  // [2][R]
+  float* hnew = part + 2 * R;                                                  // [U]
+  const int tid = threadIdx.x;
+  const int r = (int)lstm_cluster_rank();
+  const int b = blockIdx.x / CS;
+
+  const uint4* wsrc = P.whh + (size_t)r * (H / 8) * R;
+  for (int i = tid; i < (H / 8) * R; i += 256) W[i] = wsrc[i];
+  for (int i = tid; i < 2 * H; i += 256) hbuf[i] = 0.0f;
+  lstm_cluster_sync();  // every CTA's buffers are initialised before anybody writes into them remotely
+
+  const int row = tid % R, half = tid / R;
+  const bool mv = tid < 2 * R;
+  const int k_lo = half * (H / 16), k_hi = k_lo + H / 16;
+  const float* gxb = P.gx + (size_t)b * P.T * 4 * H + r * U + tid;  // unit threads: tid < U
+  float c = 0.0f;
+  float gi = 0.f, gf = 0.f, gg = 0.f, go = 0.f;
+  if (tid < U && P.T > 0) {
+    gi = __ldcg(gxb);
+    gf = __ldcg(gxb + H);
+    gg = __ldcg(gxb + 2 * H);
+    go = __ldcg(gxb + 3 * H);
+  }
+  for (int t = 0; t < P.T; ++t) {
+    const float* hc = hbuf + (t & 1) * H;
+    float ni = 0.f, nf = 0.f, ng = 0.f, no = 0.f;
+    if (tid < U && t + 1 < P.T) {  // next step's input gates: in flight during this step's matvec
+      const float* g = gxb + (size_t)(t + 1) * 4 * H;
+      ni = __ldcg(g);
+      nf = __ldcg(g + H);
+      ng = __ldcg(g + 2 * H);
+      no = __ldcg(g + 3 * H);
+    }
+    if (mv) {
+      float a0 = 0.f, a1 = 0.f;
+      for (int k8 = k_lo; k8 < k_hi; ++k8) {
+        const uint4 w = W[(size_t)k8 * R + row];
+        const float4 h0 = *reinterpret_cast<const float4*>(hc + k8 * 8);
+        const float4 h1 = *reinterpret_cast<const float4*>(hc + k8 * 8 + 4);
+        const float2 w0 = __half22float2(*reinterpret_cast<const __half2*>(&w.x));
+        const float2 w1 = __half22float2(*reinterpret_cast<const __half2*>(&w.y));
+        const float2 w2 = __half22float2(*reinterpret_cast<const __half2*>(&w.z));
+        const float2 w3 = __half22float2(*reinterpret_cast<const __half2*>(&w.w));
+        a0 = fmaf(w0.x, h0.x, a0);
+        a1 = fmaf(w0.y, h0.y, a1);
+        a0 = fmaf(w1.x, h0.z, a0);
+        a1 = fmaf(w1.y, h0.w, a1);
+        a0 = fmaf(w2.x, h1.x, a0);
+        a1 = fmaf(w2.y, h1.y, a1);
+        a0 = fmaf(w3.x, h1.z, a0);
+        a1 = fmaf(w3.y, h1.w, a1);
+      }
+      part[half * R + row] = a0 + a1;
+    }
+    __syncthreads();
+    if (tid < U) {
+      const float pi = (part[tid] + part[R + tid]) + gi;
+      const float pf = (part[U + tid] + part[R + U + tid]) + gf;
+      const float pg = (part[2 * U + tid] + part[R + 2 * U + tid]) + gg;
+      const float po = (part[3 * U + tid] + part[R + 3 * U + tid]) + go;
+      c = sigmoid_f(pf) * c + sigmoid_f(pi) * tanhf(pg);
+      const float h = sigmoid_f(po) * tanhf(c);
+      hnew[tid] = h;
+      P.hout[((size_t)b * P.T + t) * H + r * U + tid] = h;
+      gi = ni;
+      gf = nf;
+      gg = ng;
+      go = no;
+    }
+    __syncthreads();
+    // broadcast this CTA's U new hidden values into every CTA's next-step buffer (16 bytes per remote store)
+    if (tid < CS * (U / 4)) {
+      const int dst = tid / (U / 4), q = tid - dst * (U / 4);
+      const float4 v = *reinterpret_cast<const float4*>(hnew + q * 4);
+      float* nxt = hbuf + ((t + 1) & 1) * H + r * U + q * 4;
+      lstm_st_remote((uint32_t)__cvta_generic_to_shared(nxt), (uint32_t)dst, v);
+    }
+    lstm_cluster_sync();  // all reads of hbuf[t&1] are done and all of hbuf[(t+1)&1] has landed
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ final GroupNorm
+// audio[b][c][l] = gamma[c] * (raw[b][l][c] - mean_b) * rstd_b + beta[c]   (GroupNorm(1, C) of the last conv, NCL fp32 out)
+__global__ void final_norm_kernel(const float* __restrict__ raw, const long long* __restrict__ stats, int FG,
+                                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int C, int L,
+                                  float* __restrict__ out) {
+  const int b = blockIdx.y;
+  double a = 0.0, q = 0.0;
+  for (int f = 0; f < FG; ++f) {
+    a += stat_get_d(stats[((size_t)b * FG + f) * 2]);
+    q += stat_get_d(stats[((size_t)b * FG + f) * 2 + 1]);
+  }
+  const double n = (double)C * (double)L;
+  const double mean = a / n;
+  double var = q / n - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float mu = (float)mean, rstd = (float)(1.0 / sqrt(var + (double)eps));
+  for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < L; l += gridDim.x * blockDim.x)
+    for (int c = 0; c < C; ++c)
+      out[((size_t)b * C + c) * L + l] = gamma[c] * ((raw[((size_t)b * L + l) * C + c] - mu) * rstd) + beta[c];
+}
+
+int pick_cluster(int H) {
+  // largest power-of-two cluster (<= 16) whose per-CTA W_hh slice (4U x H fp16) fits shared memory, with U % 4 == 0
+  for (int cs = 16; cs >= 1; cs >>= 1) {
+    if (H % cs) continue;
+    const int U = H / cs;
+    if (U % 4 || 8 * U > 256) continue;
+    if ((size_t)4 * U * H * 2 > 160 * 1024) continue;
+    return cs;
+  }
+  return 0;
+}
+
+}  // namespace
+
+// ================================================================================================== CodecDecoder
+CodecDecoder::CodecDecoder(const Jen1CodecDesc& d, int device) : d_(d), device_(device) {}
+
+CodecDecoder::~CodecDecoder() {
+  cudaSetDevice(device_);
+  for (void* p : owned_) cudaFree(p);
+  if (arena_) cudaFree(arena_);
+}
+
+int CodecDecoder::fail(const std::string& m) {
+  err_ = m;
+  return 1;
+}
+
+bool CodecDecoder::ck(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return true;
+  err_ = std::string(what) + ": " + cudaGetErrorString(e);
+  (void)cudaGetLastError();
+  return false;
+}
+
+int CodecDecoder::load_tensor(const char* name, const float* data, const int64_t* shape, int ndim) {
+  if (finalized_) return fail("load_tensor after finalize");
+  if (!name || !data || ndim < 1 || ndim > 3) return fail("load_tensor: bad arguments");
+  HostTensor t;
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) {
+    t.shape.push_back(shape[i]);
+    n *= (size_t)shape[i];
+  }
+  t.data.assign(data, data + n);
+  host_[name] = std::move(t);
+  return 0;
+}
+
+const CodecDecoder::HostTensor* CodecDecoder::get(const std::string& name, std::initializer_list<int64_t> shape) {
+  auto it = host_.find(name);
+  if (it == host_.end()) {
+    fail("missing tensor " + name);
+    return nullptr;
+  }
+  if (it->second.shape != std::vector<int64_t>(shape)) {
+    fail("tensor " + name + " has the wrong shape");
+    return nullptr;
+  }
+  return &it->second;
+}
+
+float* CodecDecoder::upload(const std::vector<float>& v) {
+  float* p = nullptr;
+  if (!ck(cudaMalloc((void**)&p, v.size() * sizeof(float)), "cudaMalloc(weights)")) return nullptr;
+  owned_.push_back(p);
+  if (!ck(cudaMemcpy(p, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice), "upload")) return nullptr;
+  weight_bytes_ += (int64_t)v.size() * 4;
+  return p;
+}
+
+// Conv1d weight [Cout][Cin][k] -> tap-major [k][Cin][Cout]
+bool CodecDecoder::make_conv(const std::string& prefix, const char* conv, const char* norm, int cin, int cout, int k,
+                             bool transposed, ConvW* out) {
+  const HostTensor* w = transposed ? get(prefix + conv + ".weight", {cin, cout, k}) : get(prefix + conv + ".weight", {cout, cin, k});
+  const HostTensor* bs = get(prefix + conv + ".bias", {cout});
+  const HostTensor* g = get(prefix + norm + ".weight", {cout});
+  const HostTensor* be = get(prefix + norm + ".bias", {cout});
+  if (!w || !bs || !g || !be) return false;
+  std::vector<float> packed((size_t)k * cin * cout);
+  for (int j = 0; j < k; ++j)
+    for (int c = 0; c < cin; ++c)
+      for (int n = 0; n < cout; ++n)
+        packed[((size_t)j * cin + c) * cout + n] =
+            transposed ? w->data[((size_t)c * cout + n) * k + j] : w->data[((size_t)n * cin + c) * k + j];
+  out->w = upload(packed);
+  out->bias = upload(bs->data);
+  out->gamma = upload(g->data);
+  out->beta = upload(be->data);
+  out->cin = cin;
+  out->cout = cout;
+  out->k = k;
+  return out->w && out->bias && out->gamma && out->beta;
+}
+
+int CodecDecoder::finalize() {
+  if (finalized_) return 0;
+  if (cudaSetDevice(device_) != cudaSuccess) return fail("no CUDA device " + std::to_string(device_) + " (this library has no CPU path)");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device_ >= ndev) return fail("no CUDA device (this library has no CPU path)");
+  if (d_.n_ratios < 1 || d_.n_ratios > 8 || d_.lstm_layers < 0 || d_.lstm_layers > 4) return fail("bad decoder description");
+  H_ = d_.n_filters << d_.n_ratios;
+  hop_ = 1;
+  for (int i = 0; i < d_.n_ratios; ++i) hop_ *= d_.ratios[i];
+  if (H_ % 16) return fail("hidden size must be a multiple of 16");
+  if (!make_conv("model.0", ".conv.conv", ".conv.norm", d_.dimension, H_, d_.kernel_size, false, &first_)) return 1;
+  // ---- LSTM
+  CS_ = pick_cluster(H_);
+  if (d_.lstm_layers > 0 && CS_ == 0) return fail("LSTM hidden size does not fit the cluster kernel");
+  U_ = CS_ ? H_ / CS_ : 0;
+  for (int l = 0; l < d_.lstm_layers; ++l) {
+    const std::string p = "model.1.lstm.";
+    const std::string s = "_l" + std::to_string(l);
+    const HostTensor* wih = get(p + "weight_ih" + s, {4 * H_, H_});
+    const HostTensor* whh = get(p + "weight_hh" + s, {4 * H_, H_});
+    const HostTensor* bih = get(p + "bias_ih" + s, {4 * H_});
+    const HostTensor* bhh = get(p + "bias_hh" + s, {4 * H_});
+    if (!wih || !whh || !bih || !bhh) return 1;
+    LstmW L;
+    std::vector<float> wt((size_t)H_ * 4 * H_), bsum((size_t)4 * H_);
+    for (int n = 0; n < 4 * H_; ++n) {
+      bsum[n] = bih->data[n] + bhh->data[n];
+      for (int c = 0; c < H_; ++c) wt[(size_t)c * 4 * H_ + n] = wih->data[(size_t)n * H_ + c];
+    }
+    L.wih = upload(wt);
+    L.bias = upload(bsum);
+    const int R = 4 * U_;
+    std::vector<__half> pk((size_t)CS_ * (H_ / 8) * R * 8);
+    for (int r = 0; r < CS_; ++r)
+      for (int k8 = 0; k8 < H_ / 8; ++k8)
+        for (int lr = 0; lr < R; ++lr) {
+          const int g = lr / U_, u = lr % U_;
+          const int grow = g * H_ + r * U_ + u;
+          for (int e = 0; e < 8; ++e)
+            pk[(((size_t)r * (H_ / 8) + k8) * R + lr) * 8 + e] = __float2half_rn(whh->data[(size_t)grow * H_ + k8 * 8 + e]);
+        }
+    void* dp = nullptr;
+    if (!ck(cudaMalloc(&dp, pk.size() * sizeof(__half)), "cudaMalloc(W_hh)")) return 1;
+    owned_.push_back(dp);
+    if (!ck(cudaMemcpy(dp, pk.data(), pk.size() * sizeof(__half), cudaMemcpyHostToDevice), "upload W_hh")) return 1;
+    weight_bytes_ += (int64_t)pk.size() * 2;
+    L.whh = reinterpret_cast<const uint4*>(dp);
+    if (!L.wih || !L.bias) return 1;
+    lstm_.push_back(L);
+  }
+  // ---- upsampling stages
+  int idx = 2, c = H_;
+  for (int i = 0; i < d_.n_ratios; ++i) {
+    const int r = d_.ratios[i];
+    Stage S;
+    S.ratio = r;
+    const std::string pt = "model." + std::to_string(idx + 1), pr = "model." + std::to_string(idx + 2);
+    const int hid = (c / 2) / d_.compress;
+    if (!make_conv(pt, ".convtr.convtr", ".convtr.norm", c, c / 2, 2 * r, true, &S.up)) return 1;
+    if (!make_conv(pr + ".block.1", ".conv.conv", ".conv.norm", c / 2, hid, d_.residual_kernel_size, false, &S.res1)) return 1;
+    if (!make_conv(pr + ".block.3", ".conv.conv", ".conv.norm", hid, c / 2, 1, false, &S.res2)) return 1;
+    if (!make_conv(pr + ".shortcut", ".conv.conv", ".conv.norm", c / 2, c / 2, 1, false, &S.shortcut)) return 1;
+    stages_.push_back(S);
+    idx += 3;
+    c /= 2;
+  }
+  if (!make_conv("model." + std::to_string(idx + 1), ".conv.conv", ".conv.norm", c, d_.channels, d_.last_kernel_size, false, &last_))
+    return 1;
+  if (CS_ > 0) {
+    const size_t smem = lstm_smem();
+    if (!ck(cudaFuncSetAttribute(lstm_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "lstm smem attribute"))
+      return 1;
+    if (CS_ > 8 &&
+        !ck(cudaFuncSetAttribute(lstm_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1), "lstm cluster attribute"))
+      return 1;
+  }
+  host_.clear();
+  finalized_ = true;
+  return 0;
+}
+
+size_t CodecDecoder::lstm_smem() const {
+  const int R = 4 * U_;
+  return (size_t)(H_ / 8) * R * 16 + (size_t)2 * H_ * 4 + (size_t)2 * R * 4 + (size_t)U_ * 4 + 16;
+}
+
+// ---- workspace: a bump arena sized by a dry run of the same walk (nothing is reused: 2 GB per 30 s sample)
+float* CodecDecoder::falloc(size_t n) {
+  const size_t bytes = (n * sizeof(float) + 255) & ~(size_t)255;
+  float* p = dry_ ? nullptr : reinterpret_cast<float*>(arena_ + off_);
+  off_ += bytes;
+  return p;
+}
+long long* CodecDecoder::salloc(int B, int FG) {
+  const size_t bytes = ((size_t)B * FG * 2 * sizeof(long long) + 255) & ~(size_t)255;
+  long long* p = dry_ ? nullptr : reinterpret_cast<long long*>(arena_ + soff_);
+  soff_ += bytes;
+  return p;
+}
+
+size_t CodecDecoder::workspace_bytes(int B, int T) {
+  dry_ = true;
+  off_ = 0;
+  soff_ = 0;
+  walk(nullptr, nullptr, B, T, nullptr);
+  dry_ = false;
+  stats_bytes_need_ = soff_;
+  return off_ + soff_ + 4096;
+}
+
+int CodecDecoder::reserve(int B, int T) {
+  if (!finalized_) return fail("reserve before finalize");
+  if (B < 1 || T < 1) return fail("reserve: bad shape");
+  cudaSetDevice(device_);
+  const size_t need = workspace_bytes(B, T);
+  if (need > arena_bytes_) {
+    if (arena_) cudaFree(arena_);
+    arena_ = nullptr;
+    arena_bytes_ = 0;
+    if (!ck(cudaMalloc((void**)&arena_, need), "cudaMalloc(codec workspace)")) return 1;
+    arena_bytes_ = need;
+  }
+  return 0;
+}
+
+CodecDecoder::Act CodecDecoder::conv(const Act& in, const Act* in2, int act, const ConvW& W, int pad_left, bool reflect,
+                                     bool want_stats, cudaStream_t st) {
+  Act o;
+  o.C = W.cout;
+  o.L = in.L;
+  o.Lstore = in.L;
+  o.row0 = 0;
+  o.FG = W.cout >= 64 ? W.cout / 64 : 1;
+  o.gamma = W.gamma;
+  o.beta = W.beta;
+  o.ptr = falloc((size_t)B_ * o.Lstore * o.C);
+  o.stats = want_stats ? salloc(B_, o.FG) : nullptr;
+  if (dry_) return o;
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+  fill_src(p, in, in2, act);
+  ConvSeg& S = p.seg[0];
+  S.w = W.w;
+  S.ntaps = W.k;
+  S.in_stride = 1;
+  S.shift0 = -pad_left;
+  S.shift_step = 1;
+  S.wtap0 = 0;
+  S.wtap_phase = 0;
+  S.wtap_step = 1;
+  p.pad_mode = reflect ? PAD_REFLECT : PAD_ZERO;
+  const int max_pad = pad_left > (W.k - 1 - pad_left) ? pad_left : (W.k - 1 - pad_left);
+  p.Lext = (reflect && in.L <= max_pad) ? max_pad + 1 : 0;  // encodec pad1d: zero-extend a too-short signal first
+  p.B = B_;
+  p.Lm = in.L;
+  p.nphase = 1;
+  p.out_stride = 1;
+  p.Lout = o.Lstore;
+  p.Cout = W.cout;
+  p.bias = W.bias;
+  p.out = o.ptr;
+  p.stats_out = o.stats;
+  p.FGo = o.FG;
+  if (!ck(launch_conv_generic<float, float, float>(p, st), "codec conv launch")) ok_ = false;
+  ++launches_;
+  return o;
+}
+
+CodecDecoder::Act CodecDecoder::convtr(const Act& in, const Act* in2, int act, const ConvW& W, int r, cudaStream_t st) {
+  // out[m*r + z] = W[z] x[m] + W[z + r] x[m - 1], m in [0, L]: (L + 1) * r untrimmed rows; trim r - r/2 left, r/2 right
+  Act o;
+  o.C = W.cout;
+  o.Lstore = (in.L + 1) * r;
+  o.row0 = r - r / 2;
+  o.L = in.L * r;
+  o.FG = W.cout >= 64 ? W.cout / 64 : 1;
+  o.gamma = W.gamma;
+  o.beta = W.beta;
+  o.ptr = falloc((size_t)B_ * o.Lstore * o.C);
+  o.stats = salloc(B_, o.FG);
+  if (dry_) return o;
+  ConvParams p;
+  memset(&p, 0, sizeof(p));
+  fill_src(p, in, in2, act);
+  ConvSeg& S = p.seg[0];
+  S.w = W.w;
+  S.ntaps = 2;
+  S.in_stride = 1;
+  S.shift0 = 0;
+  S.shift_step = -1;
+  S.wtap0 = 0;
+  S.wtap_phase = 1;
+  S.wtap_step = r;
+  p.pad_mode = PAD_ZERO;
+  p.B = B_;
+  p.Lm = in.L + 1;
+  p.nphase = r;
+  p.out_stride = r;
+  p.out_off0 = 0;
+  p.out_off_phase = 1;
+  p.Lout = o.Lstore;
+  p.Cout = W.cout;
+  p.bias = W.bias;
+  p.out = o.ptr;
+  p.stats_out = o.stats;
+  p.FGo = o.FG;
+  if (!ck(launch_conv_generic<float, float, float>(p, st), "codec convtr launch")) ok_ = false;
+  ++launches_;
+  return o;
+}
+
+// prologue of seg 0: value(in) [+ value(in2)], then `act`.  value(x) = GroupNorm(1, C)(x.raw) when x carries statistics
+void CodecDecoder::fill_src(ConvParams& p, const Act& in, const Act* in2, int act) {
+  ConvSeg& S = p.seg[0];
+  p.nseg = 1;
+  p.mode = PRO_AFFINE;
+  p.act = act;
+  p.eps = d_.eps;
+  S.Cin = in.C;
+  S.L = in.L;
+  S.Lstore = in.Lstore;
+  S.row0 = in.row0;
+  S.s[0].ptr = in.ptr;
+  S.s[0].stats = in.stats;
+  S.s[0].C = in.C;
+  S.s[0].FG = in.FG;
+  S.s[0].bmod = B_;
+  S.s[0].scale = 1.0f;
+  p.gamma = in.gamma;
+  p.beta = in.beta;
+  if (in2) {
+    p.sum2 = 1;
+    S.s[1].ptr = in2->ptr;
+    S.s[1].stats = in2->stats;
+    S.s[1].C = in2->C;
+    S.s[1].FG = in2->FG;
+    S.s[1].bmod = B_;
+    S.s[1].scale = 1.0f;
+    p.gamma2 = in2->gamma;
+    p.beta2 = in2->beta;
+  } else {
+    p.G = in.stats ? 1 : 0;
+  }
+}
+
+void CodecDecoder::walk(const float* latent, float* audio, int B, int T, cudaStream_t st) {
+  B_ = B;
+  // ---- latent [B][D][T] -> channels-last
+  Act x;
+  x.C = d_.dimension;
+  x.L = x.Lstore = T;
+  x.ptr = falloc((size_t)B * T * x.C);
+  if (!dry_) {
+    if (!ck(launch_pack_ncl<float>(latent, x.ptr, nullptr, B, x.C, x.C, T, st), "codec pack")) ok_ = false;
+    ++launches_;
+  }
+  const int k0 = d_.kernel_size;
+  Act y0 = conv(x, nullptr, ACT_NONE, first_, (k0 - 1) - (k0 - 1) / 2, true, true, st);
+  // ---- SLSTM: value = lstm(GN(y0)) + GN(y0); the sum is taken by the next layer's prologue
+  Act cur = y0;
+  Act hseq;
+  bool have_h = false;
+  for (size_t l = 0; l < lstm_.size(); ++l) {
+    ConvW W;
+    W.w = lstm_[l].wih;
+    W.bias = lstm_[l].bias;
+    W.gamma = W.beta = nullptr;
+    W.cin = H_;
+    W.cout = 4 * H_;
+    W.k = 1;
+    Act gx = conv(cur, nullptr, ACT_NONE, W, 0, false, false, st);
+    Act h;
+    h.C = H_;
+    h.L = h.Lstore = T;
+    h.ptr = falloc((size_t)B * T * H_);
+    if (!dry_) {
+      LstmParams P;
+      P.gx = gx.ptr;
+      P.whh = lstm_[l].whh;
+      P.hout = h.ptr;
+      P.T = T;
+      P.H = H_;
+      P.CS = CS_;
+      P.U = U_;
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3((unsigned)(B * CS_));
+      cfg.blockDim = dim3(256);
+      cfg.dynamicSmemBytes = lstm_smem();
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = (unsigned)CS_;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      // (function attributes are per process: another decoder instance may have set a smaller limit)
+      cudaFuncSetAttribute(lstm_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lstm_smem());
+      if (!ck(cudaLaunchKernelEx(&cfg, lstm_cluster_kernel, P), "lstm launch")) ok_ = false;
+      ++launches_;
+    }
+    cur = h;
+    hseq = h;
+    have_h = true;
+  }
+  // ---- upsampling stages
+  Act a = y0;               // first operand of the running value
+  Act a2 = hseq;            // optional second operand (value = GN(a) + value(a2))
+  bool two = have_h;
+  for (const Stage& S : stages_) {
+    Act up = convtr(a, two ? &a2 : nullptr, ACT_ELU, S.up, S.ratio, st);
+    const int kr = S.res1.k;
+    Act r1 = conv(up, nullptr, ACT_ELU, S.res1, (kr - 1) - (kr - 1) / 2, true, true, st);
+    Act r2 = conv(r1, nullptr, ACT_ELU, S.res2, 0, true, true, st);
+    Act sc = conv(up, nullptr, ACT_NONE, S.shortcut, 0, true, true, st);
+    a = sc;
+    a2 = r2;
+    two = true;
+  }
+  const int kl = d_.last_kernel_size;
+  Act fin = conv(a, two ? &a2 : nullptr, ACT_ELU, last_, (kl - 1) - (kl - 1) / 2, true, true, st);
+  if (!dry_) {
+    dim3 grid((unsigned)std::min<long long>(((long long)fin.L + 255) / 256, 4096), (unsigned)B);
+    final_norm_kernel<<<grid, 256, 0, st>>>(fin.ptr, fin.stats, fin.FG, fin.gamma, fin.beta, d_.eps, fin.C, fin.L, audio);
+    if (!ck(cudaGetLastError(), "final norm launch")) ok_ = false;
+    ++launches_;
+  }
+}
+
+int CodecDecoder::decode(const float* latent, float* audio, int B, int T, cudaStream_t st) {
+  if (!finalized_) return fail("decode before finalize");
+  if (!latent || !audio || B < 1 || T < 1) return fail("decode: bad arguments");
+  cudaSetDevice(device_);
+  if (reserve(B, T)) return 1;
+  ok_ = true;
+  off_ = 0;
+  // statistics zone at the tail of the arena: one memset per decode
+  const size_t act_bytes = arena_bytes_ - stats_bytes_need_ - 2048;
+  soff_ = act_bytes & ~(size_t)255;
+  if (!ck(cudaMemsetAsync(arena_ + soff_, 0, stats_bytes_need_, st), "codec statistics memset")) return 1;
+  walk(latent, audio, B, T, st);
+  return ok_ ? 0 : 1;
+}
+
+}  // namespace jen1

@@ -1,0 +1,92 @@
+// Encodec (SEANet) decoder engine -- see codec.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <initializer_list>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/jen1_b200.h"
+#include "conv_params.h"
+
+namespace jen1 {
+
+class CodecDecoder {
+ public:
+  CodecDecoder(const Jen1CodecDesc& d, int device);
+  ~CodecDecoder();
+
+  int load_tensor(const char* name, const float* data, const int64_t* shape, int ndim);
+  int finalize();
+  size_t workspace_bytes(int B, int T);
+  int reserve(int B, int T);
+  int decode(const float* latent, float* audio, int B, int T, cudaStream_t st);
+
+  const char* last_error() const { return err_.c_str(); }
+  int64_t launch_count() const { return launches_; }
+  int64_t weight_bytes() const { return weight_bytes_; }
+  int hop() const { return hop_; }
+  int lstm_cluster() const { return CS_; }
+
+ private:
+  struct HostTensor {
+    std::vector<int64_t> shape;
+    std::vector<float> data;
+  };
+  struct ConvW {  // tap-major fp32 weights [k][Cin][Cout] + bias + the GroupNorm(1, Cout) affine applied by consumers
+    const float* w = nullptr;
+    const float* bias = nullptr;
+    const float* gamma = nullptr;
+    const float* beta = nullptr;
+    int cin = 0, cout = 0, k = 0;
+  };
+  struct LstmW {
+    const float* wih = nullptr;   // [H][4H] (transposed for the k=1 tap-GEMM)
+    const float* bias = nullptr;  // b_ih + b_hh
+    const uint4* whh = nullptr;   // fp16, packed per cluster rank (codec.cu LstmParams)
+  };
+  struct Stage {
+    int ratio = 1;
+    ConvW up, res1, res2, shortcut;
+  };
+  // an activation: raw values + (optionally) the statistics / affine of the GroupNorm its consumers must apply
+  struct Act {
+    float* ptr = nullptr;
+    long long* stats = nullptr;
+    const float* gamma = nullptr;
+    const float* beta = nullptr;
+    int C = 0, L = 0, Lstore = 0, row0 = 0, FG = 1;
+  };
+
+  int fail(const std::string& m);
+  bool ck(cudaError_t e, const char* what);
+  const HostTensor* get(const std::string& name, std::initializer_list<int64_t> shape);
+  float* upload(const std::vector<float>& v);
+  bool make_conv(const std::string& prefix, const char* conv, const char* norm, int cin, int cout, int k, bool transposed,
+                 ConvW* out);
+  size_t lstm_smem() const;
+  float* falloc(size_t n);
+  long long* salloc(int B, int FG);
+  void fill_src(ConvParams& p, const Act& in, const Act* in2, int act);
+  Act conv(const Act& in, const Act* in2, int act, const ConvW& W, int pad_left, bool reflect, bool want_stats, cudaStream_t st);
+  Act convtr(const Act& in, const Act* in2, int act, const ConvW& W, int r, cudaStream_t st);
+  void walk(const float* latent, float* audio, int B, int T, cudaStream_t st);
+
+  Jen1CodecDesc d_;
+  int device_;
+  bool finalized_ = false, dry_ = false, ok_ = true;
+  std::string err_;
+  std::map<std::string, HostTensor> host_;
+  std::vector<void*> owned_;
+  ConvW first_, last_;
+  std::vector<LstmW> lstm_;
+  std::vector<Stage> stages_;
+  int H_ = 0, hop_ = 1, CS_ = 0, U_ = 0, B_ = 0;
+  uint8_t* arena_ = nullptr;
+  size_t arena_bytes_ = 0, off_ = 0, soff_ = 0, stats_bytes_need_ = 0;
+  int64_t launches_ = 0, weight_bytes_ = 0;
+};
+
+}  // namespace jen1

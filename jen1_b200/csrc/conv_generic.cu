@@ -17,7 +17,7 @@ constexpr int LDA = TM + 4, LDB = TN + 4;
 
 template <typename TA, typename TW, typename TO>
 __global__ void __launch_bounds__(NT) conv_generic_kernel(const ConvParams p) {
-  extern __shared__ float dsm[];  // coefA[Cin0] | coefS[Cin0]
+  extern __shared__ float dsm[];  // coefA[Cin0] | coefS[Cin0] | (sum2) coefA2[Cin0]
   __shared__ __align__(16) float As[2][TK][LDA];
   __shared__ __align__(16) float Bs[2][TK][LDB];
   __shared__ double fine[2][32][2];
@@ -33,9 +33,50 @@ __global__ void __launch_bounds__(NT) conv_generic_kernel(const ConvParams p) {
   const int Ct = s0.Cin;
   float* coefA = dsm;
   float* coefS = dsm + Ct;
+  float* coefA2 = dsm + 2 * Ct;
+  const int gn_rows = s0.Lstore > 0 ? s0.Lstore : s0.L;
 
   // ------------------------------------------------------------------ prologue coefficients
-  if (p.mode == PRO_AFFINE) {
+  if (p.mode == PRO_AFFINE && p.sum2) {
+    // value = GN1(src0) + GN1(src1): one (mean, rstd) per source from all of its fine groups
+    if (tid < 2) {
+      const ConvSrc& sr = s0.s[tid];
+      double a = 0.0, q = 0.0;
+      float mean = 0.f, rstd = 1.f;
+      if (sr.stats) {
+        for (int fg = 0; fg < sr.FG; ++fg) {
+          const long long* st = sr.stats + ((size_t)(b % sr.bmod) * sr.FG + fg) * 2;
+          a += stat_get_d(st[0]);
+          q += stat_get_d(st[1]);
+        }
+        const double n = (double)sr.C * (double)gn_rows;
+        const double m = a / n;
+        double var = q / n - m * m;
+        if (var < 0.0) var = 0.0;
+        mean = (float)m;
+        rstd = (float)(1.0 / sqrt(var + (double)p.eps));
+      }
+      gmean[tid] = mean;
+      grstd[tid] = rstd;
+    }
+    __syncthreads();
+    for (int c = tid; c < Ct; c += NT) {
+      float a0 = s0.s[0].scale, a1 = s0.s[1].scale, sh = 0.f;
+      if (s0.s[0].stats) {
+        const float ga = p.gamma[c] * grstd[0];
+        a0 *= ga;
+        sh += p.beta[c] - gmean[0] * ga;
+      }
+      if (s0.s[1].stats) {
+        const float ga = p.gamma2[c] * grstd[1];
+        a1 *= ga;
+        sh += p.beta2[c] - gmean[1] * ga;
+      }
+      coefA[c] = a0;
+      coefA2[c] = a1;
+      coefS[c] = sh;
+    }
+  } else if (p.mode == PRO_AFFINE) {
     if (p.G > 0) {
       if (tid < 64) {  // the producers' fixed-point accumulators (order-independent => deterministic)
         const int sI = tid >> 5, fg = tid & 31;
@@ -70,7 +111,7 @@ __global__ void __launch_bounds__(NT) conv_generic_kernel(const ConvParams p) {
           }
           off += sr.C;
         }
-        const double n = (double)(p.gn_real_c > 0 ? p.gn_real_c / p.G : cpg) * (double)s0.L;
+        const double n = (double)(p.gn_real_c > 0 ? p.gn_real_c / p.G : cpg) * (double)gn_rows;
         const double mean = a / n;
         double var = q / n - mean * mean;
         if (var < 0.0) var = 0.0;
@@ -151,27 +192,35 @@ __global__ void __launch_bounds__(NT) conv_generic_kernel(const ConvParams p) {
     const int shift = S.shift0 + tap * S.shift_step;
     const int wt = S.wtap0 + z * S.wtap_phase + tap * S.wtap_step;
     const int c = kc + a_c;
-    const bool second = c >= S.s[0].C;
+    const bool sum2 = sg == 0 && p.sum2;
+    const bool second = !sum2 && c >= S.s[0].C;
     const ConvSrc& sr = second ? S.s[1] : S.s[0];
     const int cc = second ? c - S.s[0].C : c;
-    const TA* base = (const TA*)sr.ptr + (size_t)(b % sr.bmod) * S.L * sr.C + cc;
-    float ca = 0.f, cs = 0.f;
+    const int lstore = S.Lstore > 0 ? S.Lstore : S.L;
+    const TA* base = (const TA*)sr.ptr + ((size_t)(b % sr.bmod) * lstore + S.row0) * sr.C + cc;
+    const TA* base2 = sum2 ? (const TA*)S.s[1].ptr + ((size_t)(b % S.s[1].bmod) * lstore + S.row0) * S.s[1].C + cc : nullptr;
+    float ca = 0.f, cs = 0.f, ca2 = 0.f;
     if (sg == 0 && p.mode == PRO_AFFINE && c < S.Cin) {
       ca = coefA[c];
       cs = coefS[c];
+      if (sum2) ca2 = coefA2[c];
     }
+    const int lext = p.Lext > 0 ? p.Lext : S.L;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int r = a_r + 16 * i;
       const int m = m0 + r;
-      const int irow = m * S.in_stride + shift;
+      int irow = m * S.in_stride + shift;
+      if (sg == 0 && p.pad_mode == PAD_REFLECT) irow = irow < 0 ? -irow : (irow >= lext ? 2 * lext - 2 - irow : irow);
       float v = 0.0f;
       if (m < p.Lm && irow >= 0 && irow < S.L && c < S.Cin) {
         const float raw = ldf(base + (size_t)irow * sr.C);
         if (sg == 0) {
           if (p.mode == PRO_AFFINE) {
             v = fmaf(ca, raw, cs);
+            if (sum2) v = fmaf(ca2, ldf(base2 + (size_t)irow * sr.C), v);
             if (p.act == ACT_SILU) v = silu_f(v);
+            if (p.act == ACT_ELU) v = v > 0.0f ? v : expm1f(v);
           } else {
             v = (raw - rmu[r]) * rrs[r];
           }
@@ -326,7 +375,7 @@ __global__ void __launch_bounds__(NT) conv_generic_kernel(const ConvParams p) {
 template <typename TA, typename TW, typename TO>
 cudaError_t launch_conv_generic(const ConvParams& p, cudaStream_t stream) {
   dim3 grid((p.Lm + TM - 1) / TM, (p.Cout + TN - 1) / TN, p.B * p.nphase);
-  size_t dsm = (size_t)2 * p.seg[0].Cin * sizeof(float);
+  size_t dsm = (size_t)(p.sum2 ? 3 : 2) * p.seg[0].Cin * sizeof(float);
   conv_generic_kernel<TA, TW, TO><<<grid, NT, dsm, stream>>>(p);
   return cudaGetLastError();
 }

@@ -40,10 +40,15 @@ struct ConvSeg {
   int in_stride;
   int shift0, shift_step;             // shift(j)  = shift0 + j*shift_step
   int wtap0, wtap_phase, wtap_step;   // wtap(z,j) = wtap0 + z*wtap_phase + j*wtap_step
+  // ---- window into a longer stored tensor (generic kernel only; the Encodec decoder reads the trimmed middle of an
+  //      untrimmed transposed-conv output): logical row i lives at stored row row0 + i of Lstore rows per batch.
+  //      Lstore == 0 means Lstore = L, row0 = 0.  GroupNorm statistics always cover the Lstore stored rows.
+  int row0, Lstore;
 };
 
 enum { PRO_AFFINE = 0, PRO_ROWNORM = 1 };
-enum { ACT_NONE = 0, ACT_SILU = 1, ACT_GELU = 2 };
+enum { ACT_NONE = 0, ACT_SILU = 1, ACT_GELU = 2, ACT_ELU = 3 };
+enum { PAD_ZERO = 0, PAD_REFLECT = 1 };
 
 struct ConvParams {
   ConvSeg seg[2];
@@ -60,6 +65,12 @@ struct ConvParams {
   int film_stride;
   const int* cond_row; // [B] table row per batch row (device)
   int act;             // ACT_NONE / ACT_SILU applied after the affine
+  // ---- generic kernel only (Encodec decoder, csrc/codec.cu)
+  int pad_mode;        // PAD_REFLECT: rows outside [0, L) mirror (of the signal zero-extended to Lext rows when L is
+  int Lext;            //              shorter than the padding, as encodec's pad1d does); Lext == 0 means L
+  int sum2;            // seg[0] = prologue(s[0]) + prologue(s[1]) (same C; GroupNorm(1) each with its own affine and
+  const float* gamma2; //              statistics; a source without statistics is taken as is) instead of a channel concat
+  const float* beta2;
   const float* rowpart;  // PRO_ROWNORM: [Bsrc][L][rp_nct][2] per-row partial (sum, sumsq) of seg[0].s[0]
   int rp_nct;
   float ln_eps;

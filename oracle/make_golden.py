@@ -106,8 +106,44 @@ def make_conditioner_golden():
     print("  %-28s %8.1f KB" % ("conditioners.pt", os.path.getsize(os.path.join(GOLD, "conditioners.pt")) / 1024))
 
 
+def make_codec_golden():
+    """Encodec-48k decoder: the pip package the reference imports (generation.py:9,34) is absent offline; the pin is the
+    Hugging Face port of the same SEANet decoder, 48 kHz configuration, seeded random weights (never stored: they are
+    regenerated from the seed by jen1_b200.codec_config.random_state_dict)."""
+    from transformers import EncodecConfig
+    from transformers.models.encodec.modeling_encodec import EncodecDecoder
+    from jen1_b200.codec_config import CodecDesc, random_state_dict as codec_sd, to_hf_names
+    desc = CodecDesc()
+    cfg = EncodecConfig(sampling_rate=48000, audio_channels=desc.channels, normalize=True, chunk_length_s=1.0, overlap=0.01,
+                        hidden_size=desc.dimension, num_filters=desc.n_filters, num_residual_layers=1,
+                        upsampling_ratios=list(desc.ratios), norm_type="time_group_norm", kernel_size=desc.kernel_size,
+                        last_kernel_size=desc.last_kernel_size, residual_kernel_size=desc.residual_kernel_size,
+                        dilation_growth_rate=2, use_causal_conv=False, pad_mode="reflect", compress=desc.compress,
+                        num_lstm_layers=desc.lstm_layers, trim_right_ratio=1.0, use_conv_shortcut=True)
+    dec = EncodecDecoder(cfg).eval()
+    sd = codec_sd(desc, 11)
+    missing, unexpected = dec.load_state_dict(to_hf_names(sd), strict=True)
+    cases = {}
+    for name, B, T, seed in (("b2_t20", 2, 20, 5), ("b1_t3", 1, 3, 6), ("b3_t33", 3, 33, 7)):
+        g = torch.Generator().manual_seed(seed)
+        z = torch.randn(B, desc.dimension, T, generator=g)
+        with torch.no_grad():
+            taps, x = {}, z
+            for i, layer in enumerate(dec.layers):
+                x = layer(x)
+                if name == "b2_t20" and i in (0, 1, 3, 4, 15):
+                    taps["model.%d" % i] = x[:, :, :32].clone()  # head of every stage kind (conv, lstm, convtr, res, last)
+            cases[name] = dict(z=z, out=x.clone(), taps=taps)
+        print("  codec %-8s out %s  |out| max %.3f" % (name, tuple(x.shape), x.abs().max().item()))
+    torch.save(dict(weight_seed=11, cases=cases), os.path.join(GOLD, "codec_decoder.pt"))
+    print("  %-28s %8.1f KB" % ("codec_decoder.pt", os.path.getsize(os.path.join(GOLD, "codec_decoder.pt")) / 1024))
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "codec":
+        make_codec_golden()
+        return
     ref_import.install_shims()
     if len(sys.argv) > 1 and sys.argv[1] == "c2":
         make_config2_golden()

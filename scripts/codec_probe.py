@@ -1,0 +1,16 @@
+import os, sys, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from jen1_b200.codec import EncodecDecoder
+from jen1_b200.codec_config import CodecDesc, random_state_dict
+desc = CodecDesc()
+dec = EncodecDecoder(desc, "cuda:0").load_state_dict(random_state_dict(desc, 11))
+for T in [int(a) for a in sys.argv[1:]]:
+    z = torch.randn(1, 128, T, device="cuda")
+    try:
+        out = dec(z); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); out = dec(z); e1.record(); torch.cuda.synchronize()
+        print("T", T, "ok %.2f ms" % e0.elapsed_time(e1), "ws %.2f GB" % (dec.workspace_bytes(1, T) / 1e9), flush=True)
+    except Exception as e:
+        print("T", T, "FAIL", str(e)[:200], flush=True)
+        break
