@@ -458,6 +458,49 @@ def _device_timed(model, dif, desc, wl, dev, rank, world, K, W, clock_index=None
     return dev_ms, launches, lps, clk
 
 
+def codec_decode_leg(B, T, dev, cpu=True):
+    """the Encodec-48k decoder engine on the finished latents of this workload (once per
+    generate(), after the sampling loop -- NOT part of `value`), next to the CPU oracle on a bounded sample."""
+    import torch
+    from jen1_b200.codec import EncodecDecoder
+    from jen1_b200.codec_config import CodecDesc, random_state_dict as codec_sd
+    cdesc = CodecDesc()
+    csd = codec_sd(cdesc, 11)
+    dec = EncodecDecoder(cdesc, dev).load_state_dict(csd)
+    z = torch.randn(B, cdesc.dimension, T, generator=torch.Generator().manual_seed(3)).to(dev)
+    for _ in range(2):
+        out = dec(z)
+    torch.cuda.synchronize(dev)
+    n0 = dec.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    e0.record()
+    for _ in range(reps):
+        out = dec(z)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / reps
+    leg = {"ms_per_decode": ms, "audio_seconds": B * T / 150.0, "samples_per_s": B * T * cdesc.hop / (ms / 1e3),
+           "launches_per_decode": (dec.launch_count() - n0) // reps, "lstm_cluster_ctas": dec.lstm_cluster(),
+           "workspace_gb": dec.workspace_bytes(B, T) / 1e9,
+           "what": "EncodecDecoder(latent [%d,128,%d]) -> audio [%d,2,%d] fp32, device-timed, latent resident; seeded "
+                   "random-init weights (the pip checkpoint is unreachable offline)" % (B, T, B, T * cdesc.hop)}
+    if cpu:
+        from oracle.codec_oracle import decoder_forward
+        Ts = max(32, T // 16)
+        zc = z[:1, :, :Ts].cpu()
+        with torch.no_grad():
+            decoder_forward(cdesc, csd, zc[:, :, :16])
+            t0 = time.perf_counter()
+            ref = decoder_forward(cdesc, csd, zc)
+            dt = time.perf_counter() - t0
+        got = dec(zc.to(dev)).cpu()
+        leg["cpu_oracle"] = {"ms_per_decode_scaled": dt * 1e3 * (B * T) / Ts, "cores": torch.get_num_threads(),
+                             "sample": "oracle/codec_oracle.py on 1 x %d frames (%.1f s of CPU), scaled by frames" % (Ts, dt),
+                             "parity_rel_l2": ((got - ref).norm() / ref.norm()).item()}
+    return leg
+
+
 def run_ours(args, wl, scaling):
     import torch
     import torch.distributed as dist
@@ -570,6 +613,9 @@ def run_ours(args, wl, scaling):
         f_ms = (time.perf_counter() - t0) * 1e3 / n_f
         extra["unet_forward_path"] = {"ms_per_call": f_ms, "value": B * T / (f_ms / 1e3), "unit": UNIT, "calls": n_f,
                                       "what": "UNetCFG1d.__call__ -> jen1_unet_forward per step (no sampler fusion), wall clock"}
+
+    if world == 1 and not args.quick:
+        extra["codec_decode"] = codec_decode_leg(B, T, dev, cpu=not args.no_cpu_baseline)
 
     if rank == 0:
         pk = _peaks()

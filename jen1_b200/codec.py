@@ -95,3 +95,21 @@ class EncodecDecoder:
         return out
 
     forward = __call__
+
+
+class EncodecCodec:
+    """The `codec` object `jen1_b200.generation.Jen1` expects, with the decode side on the B200 engine:
+    `decode_latent(latent) -> [B, channels, samples]` (reference generation.py:130).  The encoder side
+    (`encode_latent`, reference generation.py:145-150: Encodec encoder + RVQ encode/decode) is not built -- prompts that
+    need it pass `init_latent=` instead."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], desc: Optional[CodecDesc] = None, device="cuda:0"):
+        self.decoder = EncodecDecoder(desc, device).load_state_dict(state_dict)
+        self.channels = self.decoder.desc.channels
+        self.hop = self.decoder.desc.hop
+
+    def decode_latent(self, latent: torch.Tensor) -> torch.Tensor:
+        return self.decoder(latent)
+
+    def encode_latent(self, audio: torch.Tensor) -> torch.Tensor:
+        raise RuntimeError("jen1_b200: the Encodec ENCODER is not part of this build (pass init_latent= instead)")

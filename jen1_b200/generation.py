@@ -12,8 +12,9 @@ each deviation is listed in DESIGN.md:
   * `use_gdm=False` selects the reference's VDM sampler, which is non-functional; GDM/DDIM is always used;
   * per-sample masks / latents keep their batch dimension (generation.py:173-180 drops it);
   * Encodec (pip `encodec`, not installed, weights unreachable) is an injectable `codec` object with
-    `encode_latent(audio)->[B,128,T]`, `decode_latent(latent)->[B,2,samples]`; without one the facade works in
-    the latent domain (`init_latent=` in, latents out).
+    `encode_latent(audio)->[B,128,T]`, `decode_latent(latent)->[B,2,samples]`; `codec_state_dict=` (the Encodec model's
+    or its decoder's state_dict) builds the B200 decoder engine (jen1_b200/codec.py) for the decode side; without either
+    the facade works in the latent domain (`init_latent=` in, latents out).
 """
 from __future__ import annotations
 
@@ -81,7 +82,8 @@ class Jen1:
                  cross_attn_cond_ids: Sequence[str] = ("prompt",), global_cond_ids: Sequence[str] = (),
                  input_concat_ids: Sequence[str] = ("masked_input", "mask"), *, desc: Optional[UNetDesc] = None,
                  diffusion: Optional[DiffusionDesc] = None, conditioner: Optional[MultiConditioner] = None,
-                 codec=None, state_dict: Optional[Dict[str, torch.Tensor]] = None, dtype: str = "bf16",
+                 codec=None, codec_state_dict: Optional[Dict[str, torch.Tensor]] = None,
+                 state_dict: Optional[Dict[str, torch.Tensor]] = None, dtype: str = "bf16",
                  random_init_seed: Optional[int] = None, rng_device=None, use_cuda_graph: bool = True):
         self.ckpt_path, self.device, self.sample_rate = ckpt_path, torch.device(device), sample_rate
         self.cross_attn_cond_ids = list(cross_attn_cond_ids)
@@ -92,6 +94,9 @@ class Jen1:
         self.dcfg = diffusion or DiffusionDesc()
         self.conditioner = conditioner or MultiConditioner(
             {"prompt": RandomTextConditioner(self.desc.context_embedding_features, self.desc.context_embedding_max_length)})
+        if codec is None and codec_state_dict is not None:
+            from .codec import EncodecCodec
+            codec = EncodecCodec(codec_state_dict, device=self.device)
         self.codec = codec
         self.rng_device, self.use_cuda_graph = rng_device, use_cuda_graph
         if state_dict is None:

@@ -35,6 +35,22 @@ def test_desc_struct_layout_matches_header():
     assert ctypes.sizeof(_lib.Jen1ModelDesc) == 4 * (4 + 17 + 16 + 16 + 17 + 8)
 
 
+def test_codec_desc_struct_layout_matches_header():
+    # 4 + 8 + 5 int32 fields + one float
+    assert ctypes.sizeof(_lib.Jen1CodecDesc) == 4 * (4 + 8 + 5 + 1)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_codec_fails_loudly_without_cuda(lib):
+    from jen1_b200.codec import EncodecDecoder
+    with pytest.raises(RuntimeError, match="CUDA"):
+        EncodecDecoder(device="cpu")
+    d = _lib.Jen1CodecDesc()
+    h = ctypes.c_void_p()
+    assert lib.jen1_codec_create(ctypes.byref(d), 0, ctypes.byref(h)) != 0
+    assert b"no CUDA device" in lib.jen1_codec_last_error(None)
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
 def test_engine_fails_loudly_without_cuda(lib):
     from jen1_b200.engine import Engine, EngineError

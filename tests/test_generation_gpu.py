@@ -71,3 +71,21 @@ def test_continuation_is_causal(jen):
     cond["masked_input"], cond["mask"] = full * mask, mask
     causal = dif.sample(model, (B, C, T), jen.get_conditioning(cond), causal=True, init_data=full)
     assert torch.equal(out, causal) and not torch.equal(out, noncausal)
+
+
+def test_generate_decodes_through_the_codec_engine():
+    """With a codec attached, generate() returns audio: the sampled latent goes through the B200 Encodec-decoder engine
+    (reference generation.py:128-131), and equals decoding the latent-domain result of the same seed."""
+    from jen1_b200.codec import EncodecCodec
+    from jen1_b200.codec_config import CodecDesc, random_state_dict as codec_sd
+    from jen1_b200.generation import Jen1
+    desc = tiny_desc()
+    cdesc = CodecDesc(channels=2, dimension=desc.in_channels, n_filters=4, ratios=(4, 2))
+    codec = EncodecCodec(codec_sd(cdesc, 5), cdesc, DEV)
+    jen = Jen1(None, device=DEV, desc=desc, state_dict=random_state_dict(desc, 7), dtype="fp32", codec=codec)
+    secs, B = 0.5, 2
+    T = latent_frames(secs)
+    audio = jen.generate(["a", "b"], seed=3, steps=10, batch_size=B, seconds=secs, use_gdm=True)
+    lat = jen.generate(["a", "b"], seed=3, steps=10, batch_size=B, seconds=secs, use_gdm=True, return_latents=True)
+    assert audio.shape == (B, 2, T * cdesc.hop) and torch.isfinite(audio).all()
+    assert torch.equal(audio, codec.decode_latent(lat))
