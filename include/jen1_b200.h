@@ -127,7 +127,10 @@ typedef struct Jen1CodecDesc {
   int32_t lstm_layers;           /* 2 */
   float eps;                     /* GroupNorm epsilon (1e-5) */
 } Jen1CodecDesc;
-int jen1_codec_create(const Jen1CodecDesc* desc, int device, void** out_handle);
+enum { JEN1_CODEC_FP32 = 0, JEN1_CODEC_TF32 = 1 };
+/* precision: JEN1_CODEC_TF32 = convs on the TF32 tensor-core kernel (fp32 storage and accumulation), JEN1_CODEC_FP32 =
+ * strict mode (fp32 FMA everywhere except the recurrent LSTM weights, which are fp16 in shared memory in both modes). */
+int jen1_codec_create(const Jen1CodecDesc* desc, int device, int precision, void** out_handle);
 void jen1_codec_destroy(void* handle);
 const char* jen1_codec_last_error(void* handle);
 /* One tensor of the decoder's state_dict (fp32 host memory; names as in the pip package: model.N.conv.conv.weight ...). */
@@ -138,6 +141,7 @@ int jen1_codec_reserve(void* handle, int B, int T);
 /* latent: DEVICE fp32 [B][dimension][T]; audio: DEVICE fp32 [B][channels][T * hop]. */
 int jen1_codec_decode(void* handle, const float* latent, float* audio, int B, int T, jen1_stream_t stream);
 int64_t jen1_codec_launch_count(void* handle);
+int64_t jen1_codec_tf32_launch_count(void* handle); /* how many of them were the TF32 tensor-core tap-GEMM */
 int64_t jen1_codec_weight_bytes(void* handle);
 int jen1_codec_hop(void* handle);          /* samples per latent frame (320) */
 int jen1_codec_lstm_cluster(void* handle); /* CTAs per sequence of the LSTM cluster kernel */

@@ -15,7 +15,11 @@ from .codec_config import CodecDesc, canonical_state_dict
 
 
 class EncodecDecoder:
-    def __init__(self, desc: Optional[CodecDesc] = None, device="cuda:0"):
+    def __init__(self, desc: Optional[CodecDesc] = None, device="cuda:0", precision: str = "tf32"):
+        """precision: "tf32" (convs on the TF32 tensor-core tap-GEMM, fp32 storage / accumulation) or "fp32" (strict)."""
+        if precision not in ("tf32", "fp32"):
+            raise ValueError("precision must be 'tf32' or 'fp32'")
+        self.precision = precision
         self.desc = desc or CodecDesc()
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -31,7 +35,7 @@ class EncodecDecoder:
         d.eps = float(self.desc.eps)
         h = C.c_void_p()
         index = self.device.index if self.device.index is not None else torch.cuda.current_device()
-        rc = lib.jen1_codec_create(C.byref(d), int(index), C.byref(h))
+        rc = lib.jen1_codec_create(C.byref(d), int(index), 1 if precision == "tf32" else 0, C.byref(h))
         if rc != 0:
             raise RuntimeError("jen1_codec_create failed (%d): %s" % (rc, (lib.jen1_codec_last_error(None) or b"").decode()))
         self._lib, self._h, self._finalized = lib, h, False
@@ -71,6 +75,9 @@ class EncodecDecoder:
     def launch_count(self) -> int:
         return int(self._lib.jen1_codec_launch_count(self._h))
 
+    def tf32_launch_count(self) -> int:
+        return int(self._lib.jen1_codec_tf32_launch_count(self._h))
+
     def lstm_cluster(self) -> int:
         return int(self._lib.jen1_codec_lstm_cluster(self._h))
 
@@ -103,8 +110,9 @@ class EncodecCodec:
     (`encode_latent`, reference generation.py:145-150: Encodec encoder + RVQ encode/decode) is not built -- prompts that
     need it pass `init_latent=` instead."""
 
-    def __init__(self, state_dict: Dict[str, torch.Tensor], desc: Optional[CodecDesc] = None, device="cuda:0"):
-        self.decoder = EncodecDecoder(desc, device).load_state_dict(state_dict)
+    def __init__(self, state_dict: Dict[str, torch.Tensor], desc: Optional[CodecDesc] = None, device="cuda:0",
+                 precision: str = "tf32"):
+        self.decoder = EncodecDecoder(desc, device, precision).load_state_dict(state_dict)
         self.channels = self.decoder.desc.channels
         self.hop = self.decoder.desc.hop
 

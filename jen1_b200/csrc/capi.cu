@@ -149,7 +149,7 @@ int jen1_engine_debug_tensor(void* h, const char* name, float* host_out, int64_t
 
 
 // ---------------------------------------------------------------------------------------------- Encodec decoder
-int jen1_codec_create(const Jen1CodecDesc* desc, int device, void** out_handle) {
+int jen1_codec_create(const Jen1CodecDesc* desc, int device, int precision, void** out_handle) {
   if (!desc || !out_handle) return 1;
   *out_handle = nullptr;
   int ndev = 0;
@@ -157,7 +157,8 @@ int jen1_codec_create(const Jen1CodecDesc* desc, int device, void** out_handle) 
     snprintf(g_create_error, sizeof g_create_error, "no CUDA device %d (the codec engine has no CPU fallback)", device);
     return 2;
   }
-  CodecDecoder* k = new (std::nothrow) CodecDecoder(*desc, device);
+  if (precision != JEN1_CODEC_FP32 && precision != JEN1_CODEC_TF32) return 3;
+  CodecDecoder* k = new (std::nothrow) CodecDecoder(*desc, device, precision == JEN1_CODEC_FP32);
   if (!k) return 4;
   *out_handle = k;
   return 0;
@@ -199,6 +200,7 @@ int jen1_codec_decode(void* h, const float* latent, float* audio, int B, int T, 
 }
 int64_t jen1_codec_launch_count(void* h) { return h ? K(h)->launch_count() : 0; }
 int64_t jen1_codec_weight_bytes(void* h) { return h ? K(h)->weight_bytes() : 0; }
+int64_t jen1_codec_tf32_launch_count(void* h) { return h ? K(h)->tf32_launch_count() : 0; }
 int jen1_codec_hop(void* h) { return h ? K(h)->hop() : 0; }
 int jen1_codec_lstm_cluster(void* h) { return h ? K(h)->lstm_cluster() : 0; }
 }  // extern "C"

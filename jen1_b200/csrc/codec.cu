@@ -18,7 +18,8 @@
 //                          W_hh lives in shared memory (fp16, sliced over the cluster's CTAs), h_t is broadcast over
 //                          distributed shared memory, one cluster barrier per time step; the skip connection is folded
 //                          into the next layer's prologue (sum2 with a plain second source).
-// All convs run on the fp32-FMA tap-GEMM (conv_generic.cu): this first version is correctness-first.
+// Convs run on the TF32 tensor-core tap-GEMM (conv_tf32.cu; mma.sync m16n8k8, fp32 accumulation) or, in strict mode and
+// for the LSTM input projection, on the fp32-FMA tap-GEMM (conv_generic.cu); the last 32 -> 2 conv has its own kernel.
 #include "codec.h"
 
 #include <cuda_fp16.h>
@@ -166,6 +167,128 @@ __global__ void final_norm_kernel(const float* __restrict__ raw, const long long
       out[((size_t)b * C + c) * L + l] = gamma[c] * ((raw[((size_t)b * L + l) * C + c] - mu) * rstd) + beta[c];
 }
 
+// ------------------------------------------------------------------------------------------------ narrow-output conv
+// The last SConv1d (32 -> 2 channels, k7) would waste 62 of the tap-GEMM's 64 tile columns.  One thread per output row:
+// the CTA stages rows [m0 - pad, m0 + 256 + k - 1 - pad) of value = ELU(GN(a) + GN(b)) (reflect mapping) in shared
+// memory once (row stride Cin + 1: conflict-free), the weights sit next to them, each thread runs the k*Cin*Cout MACs.
+struct NarrowParams {
+  const float* a;
+  const float* b;          // second operand of the sum (or nullptr)
+  const long long* sa;     // statistics of a / b (nullptr: take as is)
+  const long long* sb;
+  int FGa, FGb;
+  const float *ga, *ba, *gb, *bb;  // GroupNorm affines of a / b
+  const float* w;          // [k][Cin][Cout]
+  const float* bias;
+  float* out;              // raw [B][L][Cout]
+  long long* stats_out;    // [B][1][2]
+  int L, Lstore, row0, Cin, Cout, k, pad_left;
+  float eps;
+};
+constexpr int NR_ROWS = 256;
+
+__global__ void __launch_bounds__(NR_ROWS) narrow_conv_kernel(const NarrowParams P) {
+  extern __shared__ float nsm[];
+  const int Cin = P.Cin, ld = Cin + 1, rows = NR_ROWS + P.k - 1;
+  float* tile = nsm;                         // [rows][ld]
+  float* wsm = tile + (size_t)rows * ld;     // [k][Cin][Cout]
+  float* coef = wsm + P.k * Cin * P.Cout;    // [3][Cin]: a0, a1, shift
+  __shared__ float mr[2][2];
+  __shared__ float red[NR_ROWS / 32][2];
+  const int tid = threadIdx.x, b = blockIdx.y, m0 = blockIdx.x * NR_ROWS;
+  if (tid < 2) {
+    const long long* st = tid ? P.sb : P.sa;
+    const int FG = tid ? P.FGb : P.FGa;
+    float mean = 0.f, rstd = 1.f;
+    if (st) {
+      double a = 0.0, q = 0.0;
+      for (int f = 0; f < FG; ++f) {
+        a += stat_get_d(st[((size_t)b * FG + f) * 2]);
+        q += stat_get_d(st[((size_t)b * FG + f) * 2 + 1]);
+      }
+      const double n = (double)Cin * (double)P.Lstore;
+      const double m = a / n;
+      double var = q / n - m * m;
+      if (var < 0.0) var = 0.0;
+      mean = (float)m;
+      rstd = (float)(1.0 / sqrt(var + (double)P.eps));
+    }
+    mr[tid][0] = mean;
+    mr[tid][1] = rstd;
+  }
+  for (int i = tid; i < P.k * Cin * P.Cout; i += NR_ROWS) wsm[i] = P.w[i];
+  __syncthreads();
+  for (int c = tid; c < Cin; c += NR_ROWS) {
+    float a0 = 1.f, a1 = P.b ? 1.f : 0.f, sh = 0.f;
+    if (P.sa) {
+      a0 = P.ga[c] * mr[0][1];
+      sh += P.ba[c] - mr[0][0] * a0;
+    }
+    if (P.b && P.sb) {
+      a1 = P.gb[c] * mr[1][1];
+      sh += P.bb[c] - mr[1][0] * a1;
+    }
+    coef[c] = a0;
+    coef[Cin + c] = a1;
+    coef[2 * Cin + c] = sh;
+  }
+  __syncthreads();
+  const size_t base = ((size_t)b * P.Lstore + P.row0) * Cin;
+  for (int i = tid; i < rows * Cin; i += NR_ROWS) {
+    const int r = i / Cin, c = i - r * Cin;
+    int ir = m0 + r - P.pad_left;
+    ir = ir < 0 ? -ir : (ir >= P.L ? 2 * P.L - 2 - ir : ir);  // reflect (L > pad here: the audio-rate layers)
+    float v = 0.f;
+    if (ir >= 0 && ir < P.L) {
+      v = fmaf(coef[c], P.a[base + (size_t)ir * Cin + c], coef[2 * Cin + c]);
+      if (P.b) v = fmaf(coef[Cin + c], P.b[base + (size_t)ir * Cin + c], v);
+      v = v > 0.0f ? v : __expf(v) - 1.0f;
+    }
+    tile[r * ld + c] = v;
+  }
+  __syncthreads();
+  const int m = m0 + tid;
+  float s = 0.f, q = 0.f;
+  if (m < P.L) {
+    float acc[4];
+#pragma unroll
+    for (int n = 0; n < 4; ++n) acc[n] = (P.bias && n < P.Cout) ? P.bias[n] : 0.f;
+    for (int j = 0; j < P.k; ++j) {
+      const float* trow = tile + (tid + j) * ld;
+      const float* wj = wsm + j * Cin * P.Cout;
+      for (int c = 0; c < Cin; ++c) {
+        const float x = trow[c];
+#pragma unroll
+        for (int n = 0; n < 4; ++n)
+          if (n < P.Cout) acc[n] = fmaf(x, wj[c * P.Cout + n], acc[n]);
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < 4; ++n)
+      if (n < P.Cout) {
+        P.out[((size_t)b * P.L + m) * P.Cout + n] = acc[n];
+        s += acc[n];
+        q += acc[n] * acc[n];
+      }
+  }
+  s = warp_sum(s);
+  q = warp_sum(q);
+  if ((tid & 31) == 0) {
+    red[tid >> 5][0] = s;
+    red[tid >> 5][1] = q;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float a = 0.f, qq = 0.f;
+    for (int w = 0; w < NR_ROWS / 32; ++w) {
+      a += red[w][0];
+      qq += red[w][1];
+    }
+    stat_add(P.stats_out + (size_t)b * 2, a);
+    stat_add(P.stats_out + (size_t)b * 2 + 1, qq);
+  }
+}
+
 int pick_cluster(int H) {
   // largest power-of-two cluster (<= 16) whose per-CTA W_hh slice (4U x H fp16) fits shared memory, with U % 4 == 0
   for (int cs = 16; cs >= 1; cs >>= 1) {
@@ -181,7 +304,7 @@ int pick_cluster(int H) {
 }  // namespace
 
 // ================================================================================================== CodecDecoder
-CodecDecoder::CodecDecoder(const Jen1CodecDesc& d, int device) : d_(d), device_(device) {}
+CodecDecoder::CodecDecoder(const Jen1CodecDesc& d, int device, int strict) : d_(d), device_(device), strict_(strict != 0) {}
 
 CodecDecoder::~CodecDecoder() {
   cudaSetDevice(device_);
@@ -237,7 +360,6 @@ float* CodecDecoder::upload(const std::vector<float>& v) {
   return p;
 }
 
-// Conv1d weight [Cout][Cin][k] -> tap-major [k][Cin][Cout]
 bool CodecDecoder::make_conv(const std::string& prefix, const char* conv, const char* norm, int cin, int cout, int k,
                              bool transposed, ConvW* out) {
   const HostTensor* w = transposed ? get(prefix + conv + ".weight", {cin, cout, k}) : get(prefix + conv + ".weight", {cout, cin, k});
@@ -246,13 +368,24 @@ bool CodecDecoder::make_conv(const std::string& prefix, const char* conv, const 
   const HostTensor* be = get(prefix + norm + ".bias", {cout});
   if (!w || !bs || !g || !be) return false;
   std::vector<float> packed((size_t)k * cin * cout);
-  for (int j = 0; j < k; ++j)
-    for (int c = 0; c < cin; ++c)
-      for (int n = 0; n < cout; ++n)
-        packed[((size_t)j * cin + c) * cout + n] =
-            transposed ? w->data[((size_t)c * cout + n) * k + j] : w->data[((size_t)n * cin + c) * k + j];
+  std::vector<float> bias = bs->data;
+  if (transposed) {  // ConvTranspose1d [Cin][Cout][k = 2r] -> [tap j][Cin][(z, n)] = w[c][n][z + j*r]  (see convtr())
+    const int r = k / 2;
+    bias.resize((size_t)r * cout);
+    for (int z = 0; z < r; ++z)
+      for (int n = 0; n < cout; ++n) bias[(size_t)z * cout + n] = bs->data[n];
+    for (int j = 0; j < 2; ++j)
+      for (int c = 0; c < cin; ++c)
+        for (int z = 0; z < r; ++z)
+          for (int n = 0; n < cout; ++n)
+            packed[((size_t)j * cin + c) * r * cout + (size_t)z * cout + n] = w->data[((size_t)c * cout + n) * k + z + j * r];
+  } else {  // Conv1d [Cout][Cin][k] -> tap-major [k][Cin][Cout]
+    for (int j = 0; j < k; ++j)
+      for (int c = 0; c < cin; ++c)
+        for (int n = 0; n < cout; ++n) packed[((size_t)j * cin + c) * cout + n] = w->data[((size_t)n * cin + c) * k + j];
+  }
   out->w = upload(packed);
-  out->bias = upload(bs->data);
+  out->bias = upload(bias);
   out->gamma = upload(g->data);
   out->beta = upload(be->data);
   out->cin = cin;
@@ -386,6 +519,16 @@ int CodecDecoder::reserve(int B, int T) {
   return 0;
 }
 
+// TF32 tensor-core tap-GEMM by default; fp32 FMA in strict mode (and for the LSTM input projection, whose result feeds
+// 4 545 recurrent steps)
+cudaError_t CodecDecoder::launch_conv(const ConvParams& p, cudaStream_t st) {
+  if (!strict_ && !force_fp32_ && conv_tf32_supported(p)) {
+    ++tf32_launches_;
+    return launch_conv_tf32(p, st);
+  }
+  return launch_conv_generic<float, float, float>(p, st);
+}
+
 CodecDecoder::Act CodecDecoder::conv(const Act& in, const Act* in2, int act, const ConvW& W, int pad_left, bool reflect,
                                      bool want_stats, cudaStream_t st) {
   Act o;
@@ -424,19 +567,22 @@ CodecDecoder::Act CodecDecoder::conv(const Act& in, const Act* in2, int act, con
   p.out = o.ptr;
   p.stats_out = o.stats;
   p.FGo = o.FG;
-  if (!ck(launch_conv_generic<float, float, float>(p, st), "codec conv launch")) ok_ = false;
+  if (!ck(launch_conv(p, st), "codec conv launch")) ok_ = false;
   ++launches_;
   return o;
 }
 
 CodecDecoder::Act CodecDecoder::convtr(const Act& in, const Act* in2, int act, const ConvW& W, int r, cudaStream_t st) {
-  // out[m*r + z] = W[z] x[m] + W[z + r] x[m - 1], m in [0, L]: (L + 1) * r untrimmed rows; trim r - r/2 left, r/2 right
+  // out[m*r + z][n] = W[z] x[m] + W[z + r] x[m - 1], m in [0, L]: (L + 1) * r untrimmed rows; trim r - r/2 left, r/2 right.
+  // Row m of the [L + 1][r * Cout] matrix of a k = 2 conv with r * Cout "virtual" output channels (z, n) IS rows
+  // m*r .. m*r + r - 1 of the output: one tap-GEMM with full-width N tiles, the input transformed once for all phases.
+  const int cv = r * W.cout;
   Act o;
   o.C = W.cout;
   o.Lstore = (in.L + 1) * r;
   o.row0 = r - r / 2;
   o.L = in.L * r;
-  o.FG = W.cout >= 64 ? W.cout / 64 : 1;
+  o.FG = cv >= 64 ? cv / 64 : 1;
   o.gamma = W.gamma;
   o.beta = W.beta;
   o.ptr = falloc((size_t)B_ * o.Lstore * o.C);
@@ -446,28 +592,73 @@ CodecDecoder::Act CodecDecoder::convtr(const Act& in, const Act* in2, int act, c
   memset(&p, 0, sizeof(p));
   fill_src(p, in, in2, act);
   ConvSeg& S = p.seg[0];
-  S.w = W.w;
+  S.w = W.w;  // packed [2][Cin][r * Cout] (make_conv, transposed)
   S.ntaps = 2;
   S.in_stride = 1;
   S.shift0 = 0;
   S.shift_step = -1;
   S.wtap0 = 0;
-  S.wtap_phase = 1;
-  S.wtap_step = r;
+  S.wtap_phase = 0;
+  S.wtap_step = 1;
   p.pad_mode = PAD_ZERO;
   p.B = B_;
   p.Lm = in.L + 1;
-  p.nphase = r;
-  p.out_stride = r;
-  p.out_off0 = 0;
-  p.out_off_phase = 1;
-  p.Lout = o.Lstore;
-  p.Cout = W.cout;
+  p.nphase = 1;
+  p.out_stride = 1;
+  p.Lout = in.L + 1;
+  p.Cout = cv;
   p.bias = W.bias;
   p.out = o.ptr;
   p.stats_out = o.stats;
   p.FGo = o.FG;
-  if (!ck(launch_conv_generic<float, float, float>(p, st), "codec convtr launch")) ok_ = false;
+  if (!ck(launch_conv(p, st), "codec convtr launch")) ok_ = false;
+  ++launches_;
+  return o;
+}
+
+// the narrow last conv (ELU prologue, reflect padding); falls back to the tap-GEMM for shapes the narrow kernel does not take
+CodecDecoder::Act CodecDecoder::last_conv(const Act& in, const Act* in2, const ConvW& W, int pad_left, cudaStream_t st) {
+  const int max_pad = pad_left > (W.k - 1 - pad_left) ? pad_left : (W.k - 1 - pad_left);
+  const size_t smem = ((size_t)(NR_ROWS + W.k - 1) * (in.C + 1) + (size_t)W.k * in.C * W.cout + 3 * (size_t)in.C) * sizeof(float);
+  if (W.cout > 4 || in.L <= max_pad || smem > 46 * 1024) return conv(in, in2, ACT_ELU, W, pad_left, true, true, st);
+  Act o;
+  o.C = W.cout;
+  o.L = o.Lstore = in.L;
+  o.FG = 1;
+  o.gamma = W.gamma;
+  o.beta = W.beta;
+  o.ptr = falloc((size_t)B_ * o.L * o.C);
+  o.stats = salloc(B_, 1);
+  if (dry_) return o;
+  NarrowParams P;
+  memset(&P, 0, sizeof(P));
+  P.a = in.ptr;
+  P.sa = in.stats;
+  P.FGa = in.FG;
+  P.ga = in.gamma;
+  P.ba = in.beta;
+  if (in2) {
+    P.b = in2->ptr;
+    P.sb = in2->stats;
+    P.FGb = in2->FG;
+    P.gb = in2->gamma;
+    P.bb = in2->beta;
+  }
+  P.w = W.w;
+  P.bias = W.bias;
+  P.out = o.ptr;
+  P.stats_out = o.stats;
+  P.L = in.L;
+  P.Lstore = in.Lstore;
+  P.row0 = in.row0;
+  P.Cin = in.C;
+  P.Cout = W.cout;
+  P.k = W.k;
+  P.pad_left = pad_left;
+  P.eps = d_.eps;
+  dim3 grid((unsigned)((in.L + NR_ROWS - 1) / NR_ROWS), (unsigned)B_);
+  narrow_conv_kernel<<<grid, NR_ROWS, smem, st>>>(P);
+  if (!ck(cudaGetLastError(), "narrow conv launch")) ok_ = false;
   ++launches_;
   return o;
 }
@@ -531,7 +722,9 @@ void CodecDecoder::walk(const float* latent, float* audio, int B, int T, cudaStr
     W.cin = H_;
     W.cout = 4 * H_;
     W.k = 1;
+    force_fp32_ = true;  // the input projection feeds T recurrent steps: keep it in fp32
     Act gx = conv(cur, nullptr, ACT_NONE, W, 0, false, false, st);
+    force_fp32_ = false;
     Act h;
     h.C = H_;
     h.L = h.Lstore = T;
@@ -582,7 +775,7 @@ void CodecDecoder::walk(const float* latent, float* audio, int B, int T, cudaStr
     two = true;
   }
   const int kl = d_.last_kernel_size;
-  Act fin = conv(a, two ? &a2 : nullptr, ACT_ELU, last_, (kl - 1) - (kl - 1) / 2, true, true, st);
+  Act fin = last_conv(a, two ? &a2 : nullptr, last_, (kl - 1) - (kl - 1) / 2, st);
   if (!dry_) {
     dim3 grid((unsigned)std::min<long long>(((long long)fin.L + 255) / 256, 4096), (unsigned)B);
     final_norm_kernel<<<grid, 256, 0, st>>>(fin.ptr, fin.stats, fin.FG, fin.gamma, fin.beta, d_.eps, fin.C, fin.L, audio);

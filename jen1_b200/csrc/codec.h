@@ -15,7 +15,7 @@ namespace jen1 {
 
 class CodecDecoder {
  public:
-  CodecDecoder(const Jen1CodecDesc& d, int device);
+  CodecDecoder(const Jen1CodecDesc& d, int device, int strict);
   ~CodecDecoder();
 
   int load_tensor(const char* name, const float* data, const int64_t* shape, int ndim);
@@ -29,6 +29,7 @@ class CodecDecoder {
   int64_t weight_bytes() const { return weight_bytes_; }
   int hop() const { return hop_; }
   int lstm_cluster() const { return CS_; }
+  int64_t tf32_launch_count() const { return tf32_launches_; }
 
  private:
   struct HostTensor {
@@ -70,13 +71,15 @@ class CodecDecoder {
   float* falloc(size_t n);
   long long* salloc(int B, int FG);
   void fill_src(ConvParams& p, const Act& in, const Act* in2, int act);
+  cudaError_t launch_conv(const ConvParams& p, cudaStream_t st);
   Act conv(const Act& in, const Act* in2, int act, const ConvW& W, int pad_left, bool reflect, bool want_stats, cudaStream_t st);
   Act convtr(const Act& in, const Act* in2, int act, const ConvW& W, int r, cudaStream_t st);
+  Act last_conv(const Act& in, const Act* in2, const ConvW& W, int pad_left, cudaStream_t st);
   void walk(const float* latent, float* audio, int B, int T, cudaStream_t st);
 
   Jen1CodecDesc d_;
   int device_;
-  bool finalized_ = false, dry_ = false, ok_ = true;
+  bool finalized_ = false, dry_ = false, ok_ = true, strict_ = false, force_fp32_ = false;
   std::string err_;
   std::map<std::string, HostTensor> host_;
   std::vector<void*> owned_;
@@ -86,7 +89,7 @@ class CodecDecoder {
   int H_ = 0, hop_ = 1, CS_ = 0, U_ = 0, B_ = 0;
   uint8_t* arena_ = nullptr;
   size_t arena_bytes_ = 0, off_ = 0, soff_ = 0, stats_bytes_need_ = 0;
-  int64_t launches_ = 0, weight_bytes_ = 0;
+  int64_t launches_ = 0, weight_bytes_ = 0, tf32_launches_ = 0;
 };
 
 }  // namespace jen1

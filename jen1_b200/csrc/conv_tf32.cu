@@ -1,0 +1,255 @@
+// TF32 tensor-core variant of the fused tap-GEMM for the Encodec decoder stack (csrc/codec.cu).
+//
+// Same operator and parameter block as conv_generic.cu (conv_params.h), restricted to what the decoder needs: fp32
+// channels-last storage, one K segment, PRO_AFFINE prologue (GroupNorm(1) apply, optional sum of two normalised
+// sources, ELU, zero or reflect padding, windowed source), bias epilogue, fixed-point GroupNorm statistics of the output.
+// The decoder's layers are long and thin (up to 1.45 M rows of 16-256 channels): too narrow for the 128-lane tcgen05
+// tile of conv_umma.cu without repacking, and FMA-bound on the fp32 kernel.  Here the CTA tile is 64 rows x 64 output
+// channels, the operand tiles are rounded to TF32 when they are staged in shared memory, and 8 warps (4 x 2) run
+// mma.sync m16n8k8 with fp32 accumulation.  Rounding both operands to TF32 (10-bit mantissa) costs about 1e-3 relative
+// error per layer; the fp32-FMA kernel stays available as the decoder's strict mode.
+#include "common.cuh"
+#include "conv_params.h"
+
+namespace jen1 {
+
+namespace {
+constexpr int TM = 64, TN = 64, TK = 16, NT = 256;
+constexpr int LDK = TK + 4;  // A tile [m][k], row stride 20: fragment loads (20*g + t) and the staging stores are conflict-free
+constexpr int LDB = TN + 8;  // B tile [k][n], row stride 72: fragment loads (8*t + g) hit 32 distinct banks
+
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+}  // namespace
+
+__global__ void __launch_bounds__(NT) conv_tf32_kernel(const ConvParams p) {
+  extern __shared__ float dsm[];  // coefA[Cin] | coefS[Cin] | coefA2[Cin]
+  __shared__ __align__(16) float As[2][TM][LDK];
+  __shared__ __align__(16) float Bs[2][TK][LDB];
+  __shared__ float gmean[2], grstd[2];
+  __shared__ float cpart[4][TN][2];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.z;
+  const int n0 = blockIdx.x * TN;  // N tiles fastest: the CTAs that share an input tile run together (L2 reuse)
+  const int m0 = blockIdx.y * TM;
+  const ConvSeg& S = p.seg[0];
+  const int Ct = S.Cin;
+  float* coefA = dsm;
+  float* coefS = dsm + Ct;
+  float* coefA2 = dsm + 2 * Ct;
+  const int lstore = S.Lstore > 0 ? S.Lstore : S.L;
+
+  // ------------------------------------------------------------------ prologue coefficients (GroupNorm(1) per source)
+  if (tid < 2) {
+    const ConvSrc& sr = S.s[tid];
+    float mean = 0.f, rstd = 1.f;
+    if (sr.C > 0 && sr.stats) {
+      double a = 0.0, q = 0.0;
+      for (int fg = 0; fg < sr.FG; ++fg) {
+        const long long* st = sr.stats + ((size_t)(b % sr.bmod) * sr.FG + fg) * 2;
+        a += stat_get_d(st[0]);
+        q += stat_get_d(st[1]);
+      }
+      const double n = (double)sr.C * (double)lstore;
+      const double m = a / n;
+      double var = q / n - m * m;
+      if (var < 0.0) var = 0.0;
+      mean = (float)m;
+      rstd = (float)(1.0 / sqrt(var + (double)p.eps));
+    }
+    gmean[tid] = mean;
+    grstd[tid] = rstd;
+  }
+  __syncthreads();
+  for (int c = tid; c < Ct; c += NT) {
+    float a0 = S.s[0].scale, a1 = p.sum2 ? S.s[1].scale : 0.f, sh = 0.f;
+    if (S.s[0].stats) {
+      const float ga = p.gamma[c] * grstd[0];
+      a0 *= ga;
+      sh += p.beta[c] - gmean[0] * ga;
+    }
+    if (p.sum2 && S.s[1].stats) {
+      const float ga = p.gamma2[c] * grstd[1];
+      a1 *= ga;
+      sh += p.beta2[c] - gmean[1] * ga;
+    }
+    coefA[c] = a0;
+    coefA2[c] = a1;
+    coefS[c] = sh;
+  }
+  __syncthreads();
+
+  // ------------------------------------------------------------------ main loop
+  const int nk = (Ct + TK - 1) / TK;
+  const int total = S.ntaps * nk;
+  const int a_c = tid & 15, a_r = tid >> 4;
+  const int b_n = tid & 63, b_k = tid >> 6;
+  const int lext = p.Lext > 0 ? p.Lext : S.L;
+  const float* src0 = (const float*)S.s[0].ptr + ((size_t)(b % S.s[0].bmod) * lstore + S.row0) * Ct;
+  const float* src1 = p.sum2 ? (const float*)S.s[1].ptr + ((size_t)(b % S.s[1].bmod) * lstore + S.row0) * Ct : nullptr;
+
+  float ra[4], rb[4];
+  auto fetch = [&](int it) {
+    const int tap = it / nk, kc = (it - tap * nk) * TK;
+    const int shift = S.shift0 + tap * S.shift_step;
+    const int wt = S.wtap0 + tap * S.wtap_step;
+    const int c = kc + a_c;
+    float ca = 0.f, cs = 0.f, ca2 = 0.f;
+    if (c < Ct) {
+      ca = coefA[c];
+      cs = coefS[c];
+      ca2 = coefA2[c];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = m0 + a_r + 16 * i;
+      int irow = m * S.in_stride + shift;
+      if (p.pad_mode == PAD_REFLECT) irow = irow < 0 ? -irow : (irow >= lext ? 2 * lext - 2 - irow : irow);
+      float v = 0.0f;
+      if (m < p.Lm && irow >= 0 && irow < S.L && c < Ct) {
+        v = fmaf(ca, __ldg(src0 + (size_t)irow * Ct + c), cs);
+        if (src1) v = fmaf(ca2, __ldg(src1 + (size_t)irow * Ct + c), v);
+        if (p.act == ACT_ELU) v = v > 0.0f ? v : __expf(v) - 1.0f;
+      }
+      ra[i] = to_tf32(v);
+    }
+    const int n = n0 + b_n;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int kk = kc + b_k + 4 * i;
+      rb[i] = (kk < Ct && n < p.Cout) ? to_tf32(__ldg((const float*)S.w + ((size_t)wt * Ct + kk) * p.Cout + n)) : 0.0f;
+    }
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) As[buf][a_r + 16 * i][a_c] = ra[i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) Bs[buf][b_k + 4 * i][b_n] = rb[i];
+  };
+
+  const int wm = warp & 3, wn = warp >> 2;  // warp tile: rows wm*16 .. +15, columns wn*32 .. +31
+  const int g = lane >> 2, t = lane & 3;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+
+  fetch(0);
+  stash(0);
+  __syncthreads();
+  for (int it = 0; it < total; ++it) {
+    const int buf = it & 1;
+    if (it + 1 < total) fetch(it + 1);
+#pragma unroll
+    for (int ks = 0; ks < TK; ks += 8) {
+      uint32_t af[4];
+      af[0] = __float_as_uint(As[buf][wm * 16 + g][ks + t]);
+      af[1] = __float_as_uint(As[buf][wm * 16 + g + 8][ks + t]);
+      af[2] = __float_as_uint(As[buf][wm * 16 + g][ks + t + 4]);
+      af[3] = __float_as_uint(As[buf][wm * 16 + g + 8][ks + t + 4]);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        uint32_t bf[2];
+        bf[0] = __float_as_uint(Bs[buf][ks + t][wn * 32 + nt * 8 + g]);
+        bf[1] = __float_as_uint(Bs[buf][ks + t + 4][wn * 32 + nt * 8 + g]);
+        mma_tf32(acc[nt], af, bf);
+      }
+    }
+    if (it + 1 < total) stash(buf ^ 1);
+    __syncthreads();
+  }
+
+  // ------------------------------------------------------------------ epilogue
+  // thread owns rows {wm*16 + g, +8} x columns {wn*32 + nt*8 + 2t, +1}: acc[nt][0..1] row g, acc[nt][2..3] row g + 8
+  float cS[4][2], cQ[4][2];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) cS[nt][0] = cS[nt][1] = cQ[nt][0] = cQ[nt][1] = 0.f;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int m = m0 + wm * 16 + g + 8 * h;
+    const int o = m * p.out_stride + p.out_off0;
+    const bool rv = (m < p.Lm) && (o >= 0) && (o < p.Lout);
+    float* op = (float*)p.out + ((size_t)b * p.Lout + o) * p.Cout;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int n = n0 + wn * 32 + nt * 8 + 2 * t;
+      float x0 = 0.f, x1 = 0.f;
+      if (rv && n < p.Cout) x0 = acc[nt][2 * h] + (p.bias ? p.bias[n] : 0.f);
+      if (rv && n + 1 < p.Cout) x1 = acc[nt][2 * h + 1] + (p.bias ? p.bias[n + 1] : 0.f);
+      if (rv) {
+        if (n + 1 < p.Cout && (p.Cout & 1) == 0) {
+          *reinterpret_cast<float2*>(op + n) = make_float2(x0, x1);
+        } else {
+          if (n < p.Cout) op[n] = x0;
+          if (n + 1 < p.Cout) op[n + 1] = x1;
+        }
+      }
+      cS[nt][0] += x0;
+      cS[nt][1] += x1;
+      cQ[nt][0] += x0 * x0;
+      cQ[nt][1] += x1 * x1;
+    }
+  }
+  if (p.stats_out) {
+    // column sums over the warp's 16 rows (lanes with equal t), then over the 4 row-warps, then per fine group
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        float s = cS[nt][e], q = cQ[nt][e];
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+          s += __shfl_xor_sync(0xffffffffu, s, o);
+          q += __shfl_xor_sync(0xffffffffu, q, o);
+        }
+        if (g == 0) {
+          cpart[wm][wn * 32 + nt * 8 + 2 * t + e][0] = s;
+          cpart[wm][wn * 32 + nt * 8 + 2 * t + e][1] = q;
+        }
+      }
+    __syncthreads();
+    const int gs = p.Cout / p.FGo;  // host guarantees gs | 64 and gs <= 64
+    const int ngl = TN / gs;
+    if (tid < ngl) {
+      const int fg = n0 / gs + tid;
+      if (fg < p.FGo) {
+        float a = 0.f, q = 0.f;
+        for (int c = tid * gs; c < (tid + 1) * gs; ++c)
+          for (int w = 0; w < 4; ++w) {
+            a += cpart[w][c][0];
+            q += cpart[w][c][1];
+          }
+        long long* so = p.stats_out + ((size_t)b * p.FGo + fg) * 2;
+        stat_add(so, a);
+        stat_add(so + 1, q);
+      }
+    }
+  }
+}
+
+// Supported: fp32 storage, one segment, PRO_AFFINE, nphase 1, G <= 1 (or sum2), no FiLM / residual / LayerNorm partials.
+bool conv_tf32_supported(const ConvParams& p) {
+  return p.nseg == 1 && p.mode == PRO_AFFINE && p.nphase == 1 && p.film == nullptr && p.res == nullptr && p.out != nullptr &&
+         p.rowpart_out == nullptr && p.epi_act == ACT_NONE && (p.sum2 || p.seg[0].s[1].C == 0) && p.G <= 1 &&
+         (p.act == ACT_NONE || p.act == ACT_ELU) && (p.Lm + TM - 1) / TM <= 65535;
+}
+
+cudaError_t launch_conv_tf32(const ConvParams& p, cudaStream_t stream) {
+  dim3 grid((p.Cout + TN - 1) / TN, (p.Lm + TM - 1) / TM, p.B);
+  size_t dsm = (size_t)3 * p.seg[0].Cin * sizeof(float);
+  conv_tf32_kernel<<<grid, NT, dsm, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace jen1

@@ -16,6 +16,9 @@ typedef __nv_bfloat16 bf16;
 template <typename TA, typename TW, typename TO>
 cudaError_t launch_conv_generic(const ConvParams& p, cudaStream_t stream);
 int conv_generic_row_tile();
+// TF32 tensor-core variant for the Encodec decoder stack (conv_tf32.cu): fp32 storage, PRO_AFFINE prologue only
+bool conv_tf32_supported(const ConvParams& p);
+cudaError_t launch_conv_tf32(const ConvParams& p, cudaStream_t stream);
 int conv_generic_col_tile();
 
 // ---- tcgen05 / TMEM implementation for bf16 storage (conv_umma.cu): swap-AB implicit GEMM, weights streamed as

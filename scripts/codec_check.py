@@ -20,14 +20,15 @@ def main():
     g = torch.load(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "codec_decoder.pt"))
     desc = CodecDesc()
     sd = random_state_dict(desc, g["weight_seed"])
-    dec = EncodecDecoder(desc, "cuda:0").load_state_dict(sd)
-    print("lstm cluster", dec.lstm_cluster())
-    for name, c in g["cases"].items():
-        out = dec(c["z"].cuda()).cpu()
-        print("golden %-8s rel-L2 %.3e  max abs %.3e" % (name, rel(out, c["out"]), (out - c["out"]).abs().max().item()))
+    for prec in ("fp32", "tf32"):
+        dec = EncodecDecoder(desc, "cuda:0", prec).load_state_dict(sd)
+        print(prec, "lstm cluster", dec.lstm_cluster())
+        for name, c in g["cases"].items():
+            out = dec(c["z"].cuda()).cpu()
+            print("golden %-8s rel-L2 %.3e  max abs %.3e" % (name, rel(out, c["out"]), (out - c["out"]).abs().max().item()))
     td = tiny_codec_desc()
     tsd = random_state_dict(td, 3)
-    tdec = EncodecDecoder(td, "cuda:0").load_state_dict(tsd)
+    tdec = EncodecDecoder(td, "cuda:0", "tf32").load_state_dict(tsd)
     z = torch.randn(3, td.dimension, 37, generator=torch.Generator().manual_seed(1))
     with torch.no_grad():
         ref = decoder_forward(td, tsd, z)

@@ -3,7 +3,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from jen1_b200.codec import EncodecDecoder
 from jen1_b200.codec_config import CodecDesc, random_state_dict
 desc = CodecDesc()
-dec = EncodecDecoder(desc, "cuda:0").load_state_dict(random_state_dict(desc, 11))
+import os as _os
+dec = EncodecDecoder(desc, "cuda:0", _os.environ.get("CODEC_PREC", "tf32")).load_state_dict(random_state_dict(desc, 11))
 for T in [int(a) for a in sys.argv[1:]]:
     z = torch.randn(1, 128, T, device="cuda")
     try:

@@ -47,7 +47,7 @@ def test_codec_fails_loudly_without_cuda(lib):
         EncodecDecoder(device="cpu")
     d = _lib.Jen1CodecDesc()
     h = ctypes.c_void_p()
-    assert lib.jen1_codec_create(ctypes.byref(d), 0, ctypes.byref(h)) != 0
+    assert lib.jen1_codec_create(ctypes.byref(d), 0, 1, ctypes.byref(h)) != 0
     assert b"no CUDA device" in lib.jen1_codec_last_error(None)
 
 
