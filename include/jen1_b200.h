@@ -142,6 +142,7 @@ int jen1_codec_reserve(void* handle, int B, int T);
 int jen1_codec_decode(void* handle, const float* latent, float* audio, int B, int T, jen1_stream_t stream);
 int64_t jen1_codec_launch_count(void* handle);
 int64_t jen1_codec_tf32_launch_count(void* handle); /* how many of them were the TF32 tensor-core tap-GEMM */
+int64_t jen1_codec_lstm_tc_launch_count(void* handle); /* ... and the tensor-core LSTM cluster kernel */
 int64_t jen1_codec_weight_bytes(void* handle);
 int jen1_codec_hop(void* handle);          /* samples per latent frame (320) */
 int jen1_codec_lstm_cluster(void* handle); /* CTAs per sequence of the LSTM cluster kernel */

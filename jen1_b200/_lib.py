@@ -71,6 +71,7 @@ SIGNATURES = {
     "jen1_codec_launch_count": (C.c_int64, [C.c_void_p]),
     "jen1_codec_weight_bytes": (C.c_int64, [C.c_void_p]),
     "jen1_codec_tf32_launch_count": (C.c_int64, [C.c_void_p]),
+    "jen1_codec_lstm_tc_launch_count": (C.c_int64, [C.c_void_p]),
     "jen1_codec_hop": (C.c_int, [C.c_void_p]),
     "jen1_codec_lstm_cluster": (C.c_int, [C.c_void_p]),
 }

@@ -78,6 +78,9 @@ class EncodecDecoder:
     def tf32_launch_count(self) -> int:
         return int(self._lib.jen1_codec_tf32_launch_count(self._h))
 
+    def lstm_tc_launch_count(self) -> int:
+        return int(self._lib.jen1_codec_lstm_tc_launch_count(self._h))
+
     def lstm_cluster(self) -> int:
         return int(self._lib.jen1_codec_lstm_cluster(self._h))
 

@@ -201,6 +201,7 @@ int jen1_codec_decode(void* h, const float* latent, float* audio, int B, int T, 
 int64_t jen1_codec_launch_count(void* h) { return h ? K(h)->launch_count() : 0; }
 int64_t jen1_codec_weight_bytes(void* h) { return h ? K(h)->weight_bytes() : 0; }
 int64_t jen1_codec_tf32_launch_count(void* h) { return h ? K(h)->tf32_launch_count() : 0; }
+int64_t jen1_codec_lstm_tc_launch_count(void* h) { return h ? K(h)->lstm_tc_launch_count() : 0; }
 int jen1_codec_hop(void* h) { return h ? K(h)->hop() : 0; }
 int jen1_codec_lstm_cluster(void* h) { return h ? K(h)->lstm_cluster() : 0; }
 }  // extern "C"

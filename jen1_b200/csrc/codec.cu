@@ -26,6 +26,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -144,6 +145,186 @@ __global__ void __launch_bounds__(256) lstm_cluster_kernel(const LstmParams P) {
     }
     lstm_cluster_sync();  // all reads of hbuf[t&1] are done and all of hbuf[(t+1)&1] has landed
   }
+}
+
+
+// ------------------------------------------------------------------------------------------------ LSTM, tensor cores
+// Same cluster organisation, but the recurrent matvec runs on the tensor cores for up to 8 sequences at once:
+//   gates[R x 8] = W_hh slice [R x H] (fp16, REGISTER-resident mma A fragments, loaded once) x h_{t-1} [H x 8] (fp16 in
+//   shared memory, one column per batch row), fp32 accumulation, mma.sync m16n8k16.
+// One cluster therefore serves 8 batch rows (the smem kernel above needs a cluster per row), no weight byte moves after
+// the prologue, and the per-step critical path is: H/16 MMAs per warp (4 independent accumulators) -> gate math on
+// U x 8 threads -> 8-byte DSMEM broadcast of the new fp16 hidden values -> one cluster barrier.
+struct LstmTcParams {
+  const float* gx;   // [B][T][4H]
+  const float* whh;  // [4H][H] fp32 (PyTorch weight_hh layout)
+  float* hout;       // [B][T][H]
+  int T, CS, U, B;
+};
+
+__device__ __forceinline__ void mma_f16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+  __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return 2.0f * fast_sigmoid(2.0f * x) - 1.0f; }
+
+template <int KS, int U>  // KS = H / 16, U = hidden units per CTA (cluster size = H / U)
+__global__ void __launch_bounds__(256, 1) lstm_tc_kernel(const LstmTcParams P) {
+  extern __shared__ __align__(16) uint8_t lsm[];
+  constexpr int H = KS * 16, R = 4 * U, CS = H / U, ldg = R + 4;
+  // hidden state of step t: [source CTA][batch column][U (+ pad)] fp16 -- a source CTA's contribution is one contiguous
+  // chunk (one bulk copy per destination), the pad keeps the mma B-fragment loads bank-conflict free
+  constexpr int LDU = (U % 8 == 0) ? U + 8 : ((U + 7) / 8) * 8;
+  constexpr int CHUNK = 8 * LDU;  // halves per source CTA
+  constexpr uint32_t CHUNK_BYTES = CHUNK * 2;
+  __half* hs = reinterpret_cast<__half*>(lsm);                              // [2][CS][8][LDU]
+  __half* hnew = hs + 2 * CS * CHUNK;                                       // [2][8][LDU]
+  float* gsm = reinterpret_cast<float*>(hnew + 2 * CHUNK);                  // [8][ldg]
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(gsm + 8 * ldg);              // [2]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g_ = lane >> 2, t4 = lane & 3;
+  const int r = (int)lstm_cluster_rank();
+  const int b0 = (blockIdx.x / CS) * 8;
+  const int Bn = min(8, P.B - b0);
+  constexpr int nw = R / 16;
+
+  uint32_t a[KS][4];
+  const int lr0 = warp * 16 + g_, lr1 = lr0 + 8;
+  if (warp < nw) {
+    const float* w0 = P.whh + ((size_t)(lr0 / U) * H + r * U + (lr0 % U)) * H;
+    const float* w1 = P.whh + ((size_t)(lr1 / U) * H + r * U + (lr1 % U)) * H;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      const int c = ks * 16 + 2 * t4;
+      a[ks][0] = pack_h2(__ldg(w0 + c), __ldg(w0 + c + 1));
+      a[ks][1] = pack_h2(__ldg(w1 + c), __ldg(w1 + c + 1));
+      a[ks][2] = pack_h2(__ldg(w0 + c + 8), __ldg(w0 + c + 9));
+      a[ks][3] = pack_h2(__ldg(w1 + c + 8), __ldg(w1 + c + 9));
+    }
+  }
+  for (int i = tid; i < (2 * CS * CHUNK + 2 * CHUNK) / 2; i += 256) reinterpret_cast<uint32_t*>(hs)[i] = 0u;
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&mbar[i])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  lstm_cluster_sync();
+
+  // gate role: thread (n, u) finishes unit r*U + u of batch row b0 + n
+  const int gn = tid / U, gu = tid - gn * U;
+  const bool gate = gn < Bn;
+  const float* gxp = P.gx + ((size_t)(b0 + (gate ? gn : 0)) * P.T) * 4 * H + r * U + gu;
+  float* hop = P.hout + ((size_t)(b0 + (gate ? gn : 0)) * P.T) * H + r * U + gu;
+  float c = 0.0f, gi = 0.f, gf = 0.f, gg = 0.f, go = 0.f;
+  if (gate && P.T > 0) {
+    gi = __ldcg(gxp);
+    gf = __ldcg(gxp + H);
+    gg = __ldcg(gxp + 2 * H);
+    go = __ldcg(gxp + 3 * H);
+  }
+  for (int t = 0; t < P.T; ++t) {
+    const int pc = t & 1, pn = pc ^ 1;
+    const __half* cur = hs + (size_t)pc * CS * CHUNK;
+    const uint32_t bar_n = (uint32_t)__cvta_generic_to_shared(&mbar[pn]);
+    if (tid == 0)  // this step's CS incoming chunks complete the phase of the NEXT buffer's barrier
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_n), "r"(CS * CHUNK_BYTES) : "memory");
+    float ni = 0.f, nf = 0.f, ng = 0.f, no = 0.f;
+    if (gate && t + 1 < P.T) {
+      const float* g = gxp + (size_t)(t + 1) * 4 * H;
+      ni = __ldcg(g);
+      nf = __ldcg(g + H);
+      ng = __ldcg(g + 2 * H);
+      no = __ldcg(g + 3 * H);
+    }
+    if (warp < nw) {
+      float acc[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+      const __half* hb = cur + (size_t)g_ * LDU + 2 * t4;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        uint32_t bq0, bq1;
+        if constexpr (U >= 16) {  // k = ks*16 + 2*t4 (+8): source CTA and offset inside its chunk are compile-time
+          constexpr int dummy = 0;
+          (void)dummy;
+          const int o0 = ((ks * 16) / U) * CHUNK + (ks * 16) % U;
+          bq0 = *reinterpret_cast<const uint32_t*>(hb + o0);
+          bq1 = *reinterpret_cast<const uint32_t*>(hb + o0 + 8);
+        } else {
+          const int k0 = ks * 16 + 2 * t4, k1 = k0 + 8;
+          bq0 = *reinterpret_cast<const uint32_t*>(cur + (size_t)(k0 / U) * CHUNK + g_ * LDU + k0 % U);
+          bq1 = *reinterpret_cast<const uint32_t*>(cur + (size_t)(k1 / U) * CHUNK + g_ * LDU + k1 % U);
+        }
+        mma_f16(acc[ks & 3], a[ks], bq0, bq1);
+      }
+      float* g0 = gsm + (size_t)(2 * t4) * ldg;
+      g0[lr0] = (acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0]);
+      g0[ldg + lr0] = (acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1]);
+      g0[lr1] = (acc[0][2] + acc[1][2]) + (acc[2][2] + acc[3][2]);
+      g0[ldg + lr1] = (acc[0][3] + acc[1][3]) + (acc[2][3] + acc[3][3]);
+    }
+    __syncthreads();
+    __half* hn = hnew + (size_t)pc * CHUNK;
+    if (gate) {
+      const float* gs = gsm + (size_t)gn * ldg + gu;
+      const float pi = gs[0] + gi, pf = gs[U] + gf, pg = gs[2 * U] + gg, po = gs[3 * U] + go;
+      c = fast_sigmoid(pf) * c + fast_sigmoid(pi) * fast_tanh(pg);
+      const float h = fast_sigmoid(po) * fast_tanh(c);
+      hop[(size_t)t * H] = h;
+      hn[gn * LDU + gu] = __float2half_rn(h);
+      gi = ni;
+      gf = nf;
+      gg = ng;
+      go = no;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> readable by the bulk copies
+    __syncthreads();
+    if (tid < CS) {  // one bulk copy per destination CTA: this CTA's chunk of the next step's hidden state
+      const uint32_t dst_local = (uint32_t)__cvta_generic_to_shared(hs + ((size_t)pn * CS + r) * CHUNK);
+      uint32_t dst, rbar;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(dst) : "r"(dst_local), "r"((uint32_t)tid));
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(bar_n), "r"((uint32_t)tid));
+      asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                   "r"((uint32_t)__cvta_generic_to_shared(hn)), "r"(CHUNK_BYTES), "r"(rbar)
+                   : "memory");
+    }
+    {  // wait for all CS chunks of h_t (phase parity of this barrier's use number t / 2)
+      const uint32_t par = (uint32_t)((t >> 1) & 1);
+      uint32_t done = 0;
+      while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar_n), "r"(par)
+            : "memory");
+      }
+    }
+  }
+  lstm_cluster_sync();  // nobody leaves while a peer may still be copying into its shared memory
+}
+
+typedef void (*LstmTcFn)(const LstmTcParams);
+// instantiated shapes: the 48 kHz model (H = 512, 16 CTAs x 32 units) and the tiny test configuration (H = 16, 4 x 4)
+LstmTcFn lstm_tc_fn(int H, int U) {
+  if (H == 512 && U == 32) return lstm_tc_kernel<32, 32>;
+  if (H == 256 && U == 16) return lstm_tc_kernel<16, 16>;
+  if (H == 16 && U == 4) return lstm_tc_kernel<1, 4>;
+  return nullptr;
+}
+size_t lstm_tc_smem(int H, int U) {
+  const int CS = H / U, LDU = (U % 8 == 0) ? U + 8 : ((U + 7) / 8) * 8, CHUNK = 8 * LDU;
+  return (size_t)(2 * CS * CHUNK + 2 * CHUNK) * 2 + (size_t)8 * (4 * U + 4) * 4 + 16 + 16;
 }
 
 // ------------------------------------------------------------------------------------------------ final GroupNorm
@@ -304,7 +485,10 @@ int pick_cluster(int H) {
 }  // namespace
 
 // ================================================================================================== CodecDecoder
-CodecDecoder::CodecDecoder(const Jen1CodecDesc& d, int device, int strict) : d_(d), device_(device), strict_(strict != 0) {}
+CodecDecoder::CodecDecoder(const Jen1CodecDesc& d, int device, int strict) : d_(d), device_(device), strict_(strict != 0) {
+  const char* e = getenv("JEN1_LSTM");  // JEN1_LSTM=smem: the shared-memory-weights kernel (A/B partner of the tensor-core one)
+  lstm_smem_kernel_ = e && strcmp(e, "smem") == 0;
+}
 
 CodecDecoder::~CodecDecoder() {
   cudaSetDevice(device_);
@@ -425,6 +609,7 @@ int CodecDecoder::finalize() {
     }
     L.wih = upload(wt);
     L.bias = upload(bsum);
+    L.whh_f32 = upload(whh->data);
     const int R = 4 * U_;
     std::vector<__half> pk((size_t)CS_ * (H_ / 8) * R * 8);
     for (int r = 0; r < CS_; ++r)
@@ -730,6 +915,38 @@ void CodecDecoder::walk(const float* latent, float* audio, int B, int T, cudaStr
     h.L = h.Lstore = T;
     h.ptr = falloc((size_t)B * T * H_);
     if (!dry_) {
+      LstmTcFn tc = lstm_smem_kernel_ ? nullptr : lstm_tc_fn(H_, U_);
+      if (tc) {
+        LstmTcParams Q;
+        Q.gx = gx.ptr;
+        Q.whh = lstm_[l].whh_f32;
+        Q.hout = h.ptr;
+        Q.T = T;
+        Q.CS = CS_;
+        Q.U = U_;
+        Q.B = B;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)(((B + 7) / 8) * CS_));
+        cfg.blockDim = dim3(256);
+        cfg.dynamicSmemBytes = lstm_tc_smem(H_, U_);
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)CS_;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        if (CS_ > 8) cudaFuncSetAttribute(tc, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (!ck(cudaLaunchKernelEx(&cfg, tc, Q), "lstm (tensor core) launch")) ok_ = false;
+        ++launches_;
+        ++lstm_tc_launches_;
+        cur = h;
+        hseq = h;
+        have_h = true;
+        continue;
+      }
       LstmParams P;
       P.gx = gx.ptr;
       P.whh = lstm_[l].whh;

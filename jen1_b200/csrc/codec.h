@@ -30,6 +30,7 @@ class CodecDecoder {
   int hop() const { return hop_; }
   int lstm_cluster() const { return CS_; }
   int64_t tf32_launch_count() const { return tf32_launches_; }
+  int64_t lstm_tc_launch_count() const { return lstm_tc_launches_; }
 
  private:
   struct HostTensor {
@@ -47,6 +48,7 @@ class CodecDecoder {
     const float* wih = nullptr;   // [H][4H] (transposed for the k=1 tap-GEMM)
     const float* bias = nullptr;  // b_ih + b_hh
     const uint4* whh = nullptr;   // fp16, packed per cluster rank (codec.cu LstmParams)
+    const float* whh_f32 = nullptr;  // [4H][H] as loaded (the tensor-core kernel builds its register fragments from it)
   };
   struct Stage {
     int ratio = 1;
@@ -89,7 +91,8 @@ class CodecDecoder {
   int H_ = 0, hop_ = 1, CS_ = 0, U_ = 0, B_ = 0;
   uint8_t* arena_ = nullptr;
   size_t arena_bytes_ = 0, off_ = 0, soff_ = 0, stats_bytes_need_ = 0;
-  int64_t launches_ = 0, weight_bytes_ = 0, tf32_launches_ = 0;
+  int64_t launches_ = 0, weight_bytes_ = 0, tf32_launches_ = 0, lstm_tc_launches_ = 0;
+  bool lstm_smem_kernel_ = false;
 };
 
 }  // namespace jen1

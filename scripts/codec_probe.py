@@ -5,13 +5,17 @@ from jen1_b200.codec_config import CodecDesc, random_state_dict
 desc = CodecDesc()
 import os as _os
 dec = EncodecDecoder(desc, "cuda:0", _os.environ.get("CODEC_PREC", "tf32")).load_state_dict(random_state_dict(desc, 11))
+B = int(os.environ.get("CODEC_B", "1"))
 for T in [int(a) for a in sys.argv[1:]]:
-    z = torch.randn(1, 128, T, device="cuda")
+    z = torch.randn(B, 128, T, device="cuda")
     try:
         out = dec(z); torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); out = dec(z); e1.record(); torch.cuda.synchronize()
-        print("T", T, "ok %.2f ms" % e0.elapsed_time(e1), "ws %.2f GB" % (dec.workspace_bytes(1, T) / 1e9), flush=True)
+        e0.record()
+        for _ in range(3):
+            out = dec(z)
+        e1.record(); torch.cuda.synchronize()
+        print("B", B, "T", T, "ok %.2f ms" % (e0.elapsed_time(e1) / 3), "ws %.2f GB" % (dec.workspace_bytes(B, T) / 1e9), flush=True)
     except Exception as e:
         print("T", T, "FAIL", str(e)[:200], flush=True)
         break
