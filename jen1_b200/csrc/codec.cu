@@ -363,7 +363,7 @@ struct NarrowParams {
   const float* bias;
   float* out;              // raw [B][L][Cout]
   long long* stats_out;    // [B][1][2]
-  int L, Lstore, row0, Cin, Cout, k, pad_left;
+  int L, Lstore, row0, Cin, Cout, k, pad_left, slots;
   float eps;
 };
 constexpr int NR_ROWS = 256;
@@ -465,8 +465,9 @@ __global__ void __launch_bounds__(NR_ROWS) narrow_conv_kernel(const NarrowParams
       a += red[w][0];
       qq += red[w][1];
     }
-    stat_add(P.stats_out + (size_t)b * 2, a);
-    stat_add(P.stats_out + (size_t)b * 2 + 1, qq);
+    long long* so = P.stats_out + ((size_t)b * P.slots + blockIdx.x % P.slots) * 2;
+    stat_add(so, a);
+    stat_add(so + 1, qq);
   }
 }
 
@@ -721,7 +722,9 @@ CodecDecoder::Act CodecDecoder::conv(const Act& in, const Act* in2, int act, con
   o.L = in.L;
   o.Lstore = in.L;
   o.row0 = 0;
-  o.FG = W.cout >= 64 ? W.cout / 64 : 1;
+  const int fgo = W.cout >= 64 ? W.cout / 64 : 1;
+  const int slots = 32 / fgo > 1 ? 32 / fgo : 1;  // spread the statistics atomics of the long layers (<= 32 entries)
+  o.FG = fgo * slots;
   o.gamma = W.gamma;
   o.beta = W.beta;
   o.ptr = falloc((size_t)B_ * o.Lstore * o.C);
@@ -751,7 +754,8 @@ CodecDecoder::Act CodecDecoder::conv(const Act& in, const Act* in2, int act, con
   p.bias = W.bias;
   p.out = o.ptr;
   p.stats_out = o.stats;
-  p.FGo = o.FG;
+  p.FGo = fgo;
+  p.stat_slots = slots;
   if (!ck(launch_conv(p, st), "codec conv launch")) ok_ = false;
   ++launches_;
   return o;
@@ -767,7 +771,9 @@ CodecDecoder::Act CodecDecoder::convtr(const Act& in, const Act* in2, int act, c
   o.Lstore = (in.L + 1) * r;
   o.row0 = r - r / 2;
   o.L = in.L * r;
-  o.FG = cv >= 64 ? cv / 64 : 1;
+  const int fgo = cv >= 64 ? cv / 64 : 1;
+  const int slots = 32 / fgo > 1 ? 32 / fgo : 1;
+  o.FG = fgo * slots;
   o.gamma = W.gamma;
   o.beta = W.beta;
   o.ptr = falloc((size_t)B_ * o.Lstore * o.C);
@@ -795,7 +801,8 @@ CodecDecoder::Act CodecDecoder::convtr(const Act& in, const Act* in2, int act, c
   p.bias = W.bias;
   p.out = o.ptr;
   p.stats_out = o.stats;
-  p.FGo = o.FG;
+  p.FGo = fgo;
+  p.stat_slots = slots;
   if (!ck(launch_conv(p, st), "codec convtr launch")) ok_ = false;
   ++launches_;
   return o;
@@ -809,11 +816,11 @@ CodecDecoder::Act CodecDecoder::last_conv(const Act& in, const Act* in2, const C
   Act o;
   o.C = W.cout;
   o.L = o.Lstore = in.L;
-  o.FG = 1;
+  o.FG = 32;
   o.gamma = W.gamma;
   o.beta = W.beta;
   o.ptr = falloc((size_t)B_ * o.L * o.C);
-  o.stats = salloc(B_, 1);
+  o.stats = salloc(B_, o.FG);
   if (dry_) return o;
   NarrowParams P;
   memset(&P, 0, sizeof(P));
@@ -840,6 +847,7 @@ CodecDecoder::Act CodecDecoder::last_conv(const Act& in, const Act* in2, const C
   P.Cout = W.cout;
   P.k = W.k;
   P.pad_left = pad_left;
+  P.slots = o.FG;
   P.eps = d_.eps;
   dim3 grid((unsigned)((in.L + NR_ROWS - 1) / NR_ROWS), (unsigned)B_);
   narrow_conv_kernel<<<grid, NR_ROWS, smem, st>>>(P);
@@ -907,9 +915,7 @@ void CodecDecoder::walk(const float* latent, float* audio, int B, int T, cudaStr
     W.cin = H_;
     W.cout = 4 * H_;
     W.k = 1;
-    force_fp32_ = true;  // the input projection feeds T recurrent steps: keep it in fp32
     Act gx = conv(cur, nullptr, ACT_NONE, W, 0, false, false, st);
-    force_fp32_ = false;
     Act h;
     h.C = H_;
     h.L = h.Lstore = T;

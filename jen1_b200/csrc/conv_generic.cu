@@ -345,7 +345,8 @@ __global__ void __launch_bounds__(NT) conv_generic_kernel(const ConvParams p) {
           a += csum[c * 2];
           q += csum[c * 2 + 1];
         }
-        long long* so = p.stats_out + ((size_t)b * p.FGo + fg) * 2;
+        const int slots = p.stat_slots > 1 ? p.stat_slots : 1;
+        long long* so = p.stats_out + (((size_t)b * p.FGo + fg) * slots + blockIdx.x % slots) * 2;
         stat_add(so, a);
         stat_add(so + 1, q);
       }

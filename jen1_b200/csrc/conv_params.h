@@ -84,6 +84,9 @@ struct ConvParams {
   float* out_ncl;      // fp32 [B][Cout][Lout]
   long long* stats_out;  // [B][FGo][2] fixed-point accumulators (zeroed by the host before the launch chain) or nullptr
   int FGo;
+  int stat_slots;      // > 1 (generic / tf32 kernels): every fine group has this many accumulator slots, [B][FGo][slots][2],
+                       //   a CTA adds into slot (row tile % slots) -- spreads the atomics of very long layers; consumers
+                       //   that sum ALL entries of a tensor (GroupNorm(1)) simply see FGo * slots fine groups
   float* rowpart_out;  // [B][Lout][gridDim.y][2] or nullptr
 };
 

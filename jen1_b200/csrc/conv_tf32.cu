@@ -31,7 +31,10 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
 }
 }  // namespace
 
-__global__ void __launch_bounds__(NT) conv_tf32_kernel(const ConvParams p) {
+#ifndef JEN1_TF32_MINB
+#define JEN1_TF32_MINB 6
+#endif
+__global__ void __launch_bounds__(NT, JEN1_TF32_MINB) conv_tf32_kernel(const ConvParams p) {
   extern __shared__ float dsm[];  // coefA[Cin] | coefS[Cin] | coefA2[Cin]
   __shared__ __align__(16) float As[2][TM][LDK];
   __shared__ __align__(16) float Bs[2][TK][LDB];
@@ -41,7 +44,6 @@ __global__ void __launch_bounds__(NT) conv_tf32_kernel(const ConvParams p) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.z;
   const int n0 = blockIdx.x * TN;  // N tiles fastest: the CTAs that share an input tile run together (L2 reuse)
-  const int m0 = blockIdx.y * TM;
   const ConvSeg& S = p.seg[0];
   const int Ct = S.Cin;
   float* coefA = dsm;
@@ -50,25 +52,32 @@ __global__ void __launch_bounds__(NT) conv_tf32_kernel(const ConvParams p) {
   const int lstore = S.Lstore > 0 ? S.Lstore : S.L;
 
   // ------------------------------------------------------------------ prologue coefficients (GroupNorm(1) per source)
-  if (tid < 2) {
-    const ConvSrc& sr = S.s[tid];
+  if (warp < 2) {  // warp w: source w; its fine-group accumulators are summed as integers (exact), one load per lane
+    const ConvSrc& sr = S.s[warp];
     float mean = 0.f, rstd = 1.f;
     if (sr.C > 0 && sr.stats) {
-      double a = 0.0, q = 0.0;
-      for (int fg = 0; fg < sr.FG; ++fg) {
-        const long long* st = sr.stats + ((size_t)(b % sr.bmod) * sr.FG + fg) * 2;
-        a += stat_get_d(st[0]);
-        q += stat_get_d(st[1]);
+      long long a = 0, q = 0;
+      for (int fg = lane; fg < sr.FG; fg += 32) {
+        const longlong2 v = __ldcg(reinterpret_cast<const longlong2*>(sr.stats + ((size_t)(b % sr.bmod) * sr.FG + fg) * 2));
+        a += v.x;
+        q += v.y;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
       }
       const double n = (double)sr.C * (double)lstore;
-      const double m = a / n;
-      double var = q / n - m * m;
+      const double m = stat_get_d(a) / n;
+      double var = stat_get_d(q) / n - m * m;
       if (var < 0.0) var = 0.0;
       mean = (float)m;
       rstd = (float)(1.0 / sqrt(var + (double)p.eps));
     }
-    gmean[tid] = mean;
-    grstd[tid] = rstd;
+    if (lane == 0) {
+      gmean[warp] = mean;
+      grstd[warp] = rstd;
+    }
   }
   __syncthreads();
   for (int c = tid; c < Ct; c += NT) {
@@ -92,49 +101,57 @@ __global__ void __launch_bounds__(NT) conv_tf32_kernel(const ConvParams p) {
   // ------------------------------------------------------------------ main loop
   const int nk = (Ct + TK - 1) / TK;
   const int total = S.ntaps * nk;
-  const int a_c = tid & 15, a_r = tid >> 4;
-  const int b_n = tid & 63, b_k = tid >> 6;
+  // staging: one 16-byte load per thread and operand tile (A: 64 rows x 16 channels, B: 16 channels x 64 columns)
+  const int a_c4 = (tid & 3) * 4, a_r = tid >> 2;
+  const int b_n4 = (tid & 15) * 4, b_k = tid >> 4;
   const int lext = p.Lext > 0 ? p.Lext : S.L;
   const float* src0 = (const float*)S.s[0].ptr + ((size_t)(b % S.s[0].bmod) * lstore + S.row0) * Ct;
   const float* src1 = p.sum2 ? (const float*)S.s[1].ptr + ((size_t)(b % S.s[1].bmod) * lstore + S.row0) * Ct : nullptr;
+  const int m0 = blockIdx.y * TM;
+  const bool elu = p.act == ACT_ELU;
 
-  float ra[4], rb[4];
+  float4 ra, rb;
   auto fetch = [&](int it) {
     const int tap = it / nk, kc = (it - tap * nk) * TK;
     const int shift = S.shift0 + tap * S.shift_step;
     const int wt = S.wtap0 + tap * S.wtap_step;
-    const int c = kc + a_c;
-    float ca = 0.f, cs = 0.f, ca2 = 0.f;
-    if (c < Ct) {
-      ca = coefA[c];
-      cs = coefS[c];
-      ca2 = coefA2[c];
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int m = m0 + a_r + 16 * i;
-      int irow = m * S.in_stride + shift;
-      if (p.pad_mode == PAD_REFLECT) irow = irow < 0 ? -irow : (irow >= lext ? 2 * lext - 2 - irow : irow);
-      float v = 0.0f;
-      if (m < p.Lm && irow >= 0 && irow < S.L && c < Ct) {
-        v = fmaf(ca, __ldg(src0 + (size_t)irow * Ct + c), cs);
-        if (src1) v = fmaf(ca2, __ldg(src1 + (size_t)irow * Ct + c), v);
-        if (p.act == ACT_ELU) v = v > 0.0f ? v : __expf(v) - 1.0f;
+    const int c = kc + a_c4;
+    const int m = m0 + a_r;
+    int irow = m * S.in_stride + shift;
+    if (p.pad_mode == PAD_REFLECT) irow = irow < 0 ? -irow : (irow >= lext ? 2 * lext - 2 - irow : irow);
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (m < p.Lm && irow >= 0 && irow < S.L && c < Ct) {  // Ct % 4 == 0: the four channels are in or out together
+      const float4 x = __ldg(reinterpret_cast<const float4*>(src0 + (size_t)irow * Ct + c));
+      const float4 ca = *reinterpret_cast<const float4*>(coefA + c);
+      const float4 cs = *reinterpret_cast<const float4*>(coefS + c);
+      v[0] = fmaf(ca.x, x.x, cs.x);
+      v[1] = fmaf(ca.y, x.y, cs.y);
+      v[2] = fmaf(ca.z, x.z, cs.z);
+      v[3] = fmaf(ca.w, x.w, cs.w);
+      if (src1) {
+        const float4 y = __ldg(reinterpret_cast<const float4*>(src1 + (size_t)irow * Ct + c));
+        const float4 c2 = *reinterpret_cast<const float4*>(coefA2 + c);
+        v[0] = fmaf(c2.x, y.x, v[0]);
+        v[1] = fmaf(c2.y, y.y, v[1]);
+        v[2] = fmaf(c2.z, y.z, v[2]);
+        v[3] = fmaf(c2.w, y.w, v[3]);
       }
-      ra[i] = to_tf32(v);
-    }
-    const int n = n0 + b_n;
+      if (elu) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int kk = kc + b_k + 4 * i;
-      rb[i] = (kk < Ct && n < p.Cout) ? to_tf32(__ldg((const float*)S.w + ((size_t)wt * Ct + kk) * p.Cout + n)) : 0.0f;
+        for (int e = 0; e < 4; ++e) v[e] = v[e] > 0.0f ? v[e] : __expf(v[e]) - 1.0f;
+      }
+    }
+    ra = make_float4(to_tf32(v[0]), to_tf32(v[1]), to_tf32(v[2]), to_tf32(v[3]));
+    const int kk = kc + b_k, n = n0 + b_n4;
+    rb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (kk < Ct && n < p.Cout) {  // Cout % 4 == 0
+      const float4 w = __ldg(reinterpret_cast<const float4*>((const float*)S.w + ((size_t)wt * Ct + kk) * p.Cout + n));
+      rb = make_float4(to_tf32(w.x), to_tf32(w.y), to_tf32(w.z), to_tf32(w.w));
     }
   };
   auto stash = [&](int buf) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) As[buf][a_r + 16 * i][a_c] = ra[i];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) Bs[buf][b_k + 4 * i][b_n] = rb[i];
+    *reinterpret_cast<float4*>(&As[buf][a_r][a_c4]) = ra;
+    *reinterpret_cast<float4*>(&Bs[buf][b_k][b_n4]) = rb;
   };
 
   const int wm = warp & 3, wn = warp >> 2;  // warp tile: rows wm*16 .. +15, columns wn*32 .. +31
@@ -230,7 +247,8 @@ __global__ void __launch_bounds__(NT) conv_tf32_kernel(const ConvParams p) {
             a += cpart[w][c][0];
             q += cpart[w][c][1];
           }
-        long long* so = p.stats_out + ((size_t)b * p.FGo + fg) * 2;
+        const int slots = p.stat_slots > 1 ? p.stat_slots : 1;
+        long long* so = p.stats_out + (((size_t)b * p.FGo + fg) * slots + blockIdx.y % slots) * 2;
         stat_add(so, a);
         stat_add(so + 1, q);
       }
@@ -242,7 +260,7 @@ __global__ void __launch_bounds__(NT) conv_tf32_kernel(const ConvParams p) {
 bool conv_tf32_supported(const ConvParams& p) {
   return p.nseg == 1 && p.mode == PRO_AFFINE && p.nphase == 1 && p.film == nullptr && p.res == nullptr && p.out != nullptr &&
          p.rowpart_out == nullptr && p.epi_act == ACT_NONE && (p.sum2 || p.seg[0].s[1].C == 0) && p.G <= 1 &&
-         (p.act == ACT_NONE || p.act == ACT_ELU) && (p.Lm + TM - 1) / TM <= 65535;
+         (p.act == ACT_NONE || p.act == ACT_ELU) && (p.Lm + TM - 1) / TM <= 65535 && p.seg[0].Cin % 4 == 0 && p.Cout % 4 == 0;
 }
 
 cudaError_t launch_conv_tf32(const ConvParams& p, cudaStream_t stream) {
