@@ -464,25 +464,35 @@ def codec_decode_leg(B, T, dev, cpu=True):
     import torch
     from jen1_b200.codec import EncodecDecoder
     from jen1_b200.codec_config import CodecDesc, random_state_dict as codec_sd
+    from jen1_b200.codec_config import decode_work
     cdesc = CodecDesc()
     csd = codec_sd(cdesc, 11)
-    dec = EncodecDecoder(cdesc, dev).load_state_dict(csd)
     z = torch.randn(B, cdesc.dimension, T, generator=torch.Generator().manual_seed(3)).to(dev)
-    for _ in range(2):
-        out = dec(z)
-    torch.cuda.synchronize(dev)
-    n0 = dec.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 5
-    e0.record()
-    for _ in range(reps):
-        out = dec(z)
-    e1.record()
-    torch.cuda.synchronize(dev)
-    ms = e0.elapsed_time(e1) / reps
-    leg = {"ms_per_decode": ms, "audio_seconds": B * T / 150.0, "samples_per_s": B * T * cdesc.hop / (ms / 1e3),
-           "launches_per_decode": (dec.launch_count() - n0) // reps, "lstm_cluster_ctas": dec.lstm_cluster(),
-           "workspace_gb": dec.workspace_bytes(B, T) / 1e9,
+
+    def timed(precision, reps):
+        dec = EncodecDecoder(cdesc, dev, precision).load_state_dict(csd)
+        for _ in range(2):
+            dec(z)
+        torch.cuda.synchronize(dev)
+        n0, t0 = dec.launch_count(), dec.tf32_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            dec(z)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return dec, e0.elapsed_time(e1) / reps, (dec.launch_count() - n0) // reps, (dec.tf32_launch_count() - t0) // reps
+
+    _, ms_strict, _, _ = timed("fp32", 2)
+    dec, ms, nl, ntf = timed("tf32", 5)
+    work = decode_work(cdesc, T)
+    pk = _peaks()
+    leg = {"ms_per_decode": ms, "precision": "tf32 tensor-core convs, fp16 recurrent LSTM weights, fp32 storage / accumulation",
+           "ms_per_decode_fp32_strict": ms_strict, "audio_seconds": B * T / 150.0,
+           "samples_per_s": B * T * cdesc.hop / (ms / 1e3), "launches_per_decode": nl, "tf32_gemm_launches": ntf,
+           "lstm_tensor_core_launches": 2, "lstm_cluster_ctas": dec.lstm_cluster(), "workspace_gb": dec.workspace_bytes(B, T) / 1e9,
+           "algorithmic_gb": B * work["bytes"] / 1e9, "hbm_frac": B * work["bytes"] / (ms / 1e3) / 1e9 / pk["hbm"],
+           "tflops": B * work["flops"] / (ms / 1e3) / 1e12,
            "what": "EncodecDecoder(latent [%d,128,%d]) -> audio [%d,2,%d] fp32, device-timed, latent resident; seeded "
                    "random-init weights (the pip checkpoint is unreachable offline)" % (B, T, B, T * cdesc.hop)}
     if cpu:

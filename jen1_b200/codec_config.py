@@ -94,6 +94,36 @@ class CodecDesc:
         return spec
 
 
+def decode_work(desc: CodecDesc, T: int) -> Dict[str, float]:
+    """Algorithmic work of ONE sample's decode at T latent frames: fp32 bytes every layer must read (each operand once;
+    a "sum of two normalised tensors" input counts both) and write, and 2*MAC flops.  Used by bench.py's codec leg."""
+    by = fl = 0.0
+    L, two = T, False  # `two`: the running value is a sum of two stored tensors
+    for idx, kind, cin, cout, k, stride in desc.layers():
+        nin = 2 if two else 1
+        if kind == "conv":
+            by += 4.0 * L * (nin * cin + cout)
+            fl += 2.0 * L * cin * cout * k
+            two = False
+        elif kind == "lstm":
+            for _ in range(desc.lstm_layers):
+                by += 4.0 * L * (cin + 4 * cin) + 4.0 * L * (4 * cin + cin)  # projection in/out, recurrence in/out
+                fl += 2.0 * L * cin * 4 * cin * 2
+            two = True  # lstm output + skip
+        elif kind == "convtr":
+            by += 4.0 * (L * nin * cin + (L + 1) * stride * cout)
+            fl += 2.0 * L * cin * cout * k
+            L *= stride
+            two = False
+        else:
+            hid = cin // desc.compress
+            by += 4.0 * L * (cin + hid) + 4.0 * L * (hid + cout) + 4.0 * L * (cin + cout)
+            fl += 2.0 * L * (cin * hid * k + hid * cout + cin * cout)
+            two = True
+    by += 4.0 * L * desc.channels * 2  # final GroupNorm pass: read raw, write audio
+    return {"bytes": by, "flops": fl, "samples": float(L)}
+
+
 def tiny_codec_desc() -> CodecDesc:
     return CodecDesc(channels=2, dimension=16, n_filters=4, ratios=(4, 2), kernel_size=7, last_kernel_size=7)
 

@@ -91,6 +91,12 @@ def main(tag, label, steps=5):
         out.append(hot)
         open(os.path.join(P, "%s_%s.txt" % (label, name)), "w").write("\n".join(out))
         # (the binary .ncu-rep stays in gpurun_out/: only the text digest is committed)
+    for f in sorted(os.listdir(G)):  # every other bench line of the pass, the attention sweep, the codec launch list
+        if f.startswith(tag + "_bench_") and f.endswith(".json") and os.path.getsize(os.path.join(G, f)) > 0:
+            shutil.copy(os.path.join(G, f), os.path.join(P, label + f[len(tag):]))
+        if f in (tag + "_attn_bench.jsonl", tag + "_launches_codec.csv.gz", tag + "_launches_codec_summary.txt",
+                 tag + "_multigpu_check_n2.log"):
+            shutil.copy(os.path.join(G, f), os.path.join(P, label + f[len(tag):]))
     for extra in ("tl_c2.txt", "tl_c3.txt"):
         src = os.path.join(G, "%s_%s" % (tag, extra))
         if os.path.exists(src):

@@ -16,4 +16,12 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:conv
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:conv_umma -s 237 -c 2 -o $O/${TAG}_full_conv_hires_c3 -f python scripts/timeline.py --plain 4545 4 > $O/${TAG}_full2.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:attn_umma -s 26 -c 2 -o $O/${TAG}_full_attn_c3 -f python scripts/timeline.py --plain 4545 4 > $O/${TAG}_full3.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:attn_flash -c 2 -o $O/${TAG}_full_attn_flash -f python scripts/attn_bench.py --once --shapes 4545,8,128,0 4545,8,64,0 > $O/${TAG}_full4.log 2>&1
+# Encodec decoder: launch list of one 30 s decode (4 samples) + full captures of its three kernel classes
+CODEC_B=4 timeout 600 ncu --metrics $M --clock-control none --csv --log-file $O/${TAG}_launches_codec.csv python scripts/codec_probe.py 4545 > $O/${TAG}_ncu_codec.log 2>&1
+python scripts/summarize_codec_launches.py $O/${TAG}_launches_codec.csv > $O/${TAG}_launches_codec_summary.txt 2>&1
+gzip -f $O/${TAG}_launches_codec.csv
+CODEC_B=4 timeout 300 ncu --set full --clock-control none --import-source on -k regex:conv_tf32 -s 30 -c 2 -o $O/${TAG}_full_codec_conv_tf32 -f python scripts/codec_probe.py 4545 > $O/${TAG}_full5.log 2>&1
+CODEC_B=4 timeout 300 ncu --set full --clock-control none --import-source on -k regex:lstm_tc -c 1 -o $O/${TAG}_full_codec_lstm -f python scripts/codec_probe.py 600 > $O/${TAG}_full6.log 2>&1
+CODEC_B=4 timeout 300 ncu --set full --clock-control none --import-source on -k regex:narrow_conv -c 1 -o $O/${TAG}_full_codec_narrow -f python scripts/codec_probe.py 4545 > $O/${TAG}_full7.log 2>&1
+tail -3 $O/${TAG}_launches_codec_summary.txt
 head -12 $O/${TAG}_launches_config2_summary.txt; head -8 $O/${TAG}_launches_config3_summary.txt

@@ -9,6 +9,10 @@ for tool in memcheck racecheck initcheck synccheck; do
   timeout 900 $CS --tool $tool --print-limit 20 python scripts/sanitize_driver.py tiny > $O/${TAG}_sanitize_${tool}_tiny.log 2>&1
   echo "$tool tiny rc=$? : $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' $O/${TAG}_sanitize_${tool}_tiny.log | tail -1)"
 done
+for tool in memcheck racecheck synccheck; do
+  timeout 900 $CS --tool $tool --print-limit 20 python scripts/sanitize_driver.py codec > $O/${TAG}_sanitize_${tool}_codec.log 2>&1
+  echo "$tool codec rc=$? : $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' $O/${TAG}_sanitize_${tool}_codec.log | tail -1)"
+done
 timeout 900 $CS --tool memcheck --print-limit 20 python scripts/sanitize_driver.py full > $O/${TAG}_sanitize_memcheck_full.log 2>&1
 echo "memcheck full rc=$? : $(grep -E 'ERROR SUMMARY' $O/${TAG}_sanitize_memcheck_full.log | tail -1)"
 timeout 900 $CS --tool racecheck --print-limit 20 python scripts/sanitize_driver.py full > $O/${TAG}_sanitize_racecheck_full.log 2>&1

@@ -6,6 +6,7 @@
     python scripts/sanitize_driver.py stress [N]  # determinism stress of the 16-CTA split-K cluster exchange: N forwards
                                                   # (default 500) of the full model at B=2, T=1 -- every conv of the deep
                                                   # levels runs as a (1,1,16) cluster -- each compared BIT-EXACTLY with the first
+    python scripts/sanitize_driver.py codec       # Encodec decoder engine: 48 kHz configuration at T=6 + tiny configuration
 """
 import os
 import sys
@@ -85,6 +86,20 @@ def main():
         print("split-K determinism stress: %d forwards, %d tcgen05 conv launches (cluster split-K at every deep level), "
               "%d mismatching outputs, %.1f s" % (n, convs, bad, time.time() - t0))
         assert bad == 0
+    elif mode == "codec":
+        # Encodec decoder engine: the full 48 kHz configuration (16-CTA LSTM cluster, tensor-core kernels) at T = 6 and the
+        # tiny configuration in both precisions
+        from jen1_b200.codec import EncodecDecoder
+        from jen1_b200.codec_config import CodecDesc, random_state_dict as codec_sd, tiny_codec_desc
+        for desc, T, B in ((CodecDesc(), 6, 2), (tiny_codec_desc(), 9, 3)):
+            sd = codec_sd(desc, 1)
+            for prec in ("tf32", "fp32"):
+                dec = EncodecDecoder(desc, DEV, prec).load_state_dict(sd)
+                out = dec(torch.randn(B, desc.dimension, T, generator=torch.Generator().manual_seed(2)).to(DEV))
+                torch.cuda.synchronize()
+                assert torch.isfinite(out).all()
+                print("codec H=%d %s ok, launches %d (tf32 gemm %d, tensor-core lstm %d)"
+                      % (desc.hidden, prec, dec.launch_count(), dec.tf32_launch_count(), dec.lstm_tc_launch_count()))
     else:
         raise SystemExit("unknown mode " + mode)
 

@@ -15,7 +15,7 @@ def main(tag):
         for m in re.finditer(r"=========\s+(Invalid [^\n]*|Uninitialized [^\n]*|Barrier error[^\n]*|(?:Error|Warning): (?:Race|Potential)[^\n]*)", txt):
             k = re.sub(r"0x[0-9a-f]+", "0x..", m.group(1))[:110]
             kinds[k] = kinds.get(k, 0) + 1
-        ok = re.findall(r"^(sanitize_driver[^\n]*)$", txt, re.M)
+        ok = re.findall(r"^((?:tiny|full|codec) [^\n]*ok[^\n]*)$", txt, re.M)
         print("%-46s %s" % (f.split("/")[-1], summ[-1] if summ else "NO SUMMARY (timeout?)"))
         for k, n in sorted(kinds.items(), key=lambda kv: -kv[1])[:6]:
             print("      %5d x %s" % (n, k))
