@@ -156,10 +156,13 @@ __global__ void __launch_bounds__(256) lstm_cluster_kernel(const LstmParams P) {
 // the prologue, and the per-step critical path is: H/16 MMAs per warp (4 independent accumulators) -> gate math on
 // U x 8 threads -> 8-byte DSMEM broadcast of the new fp16 hidden values -> one cluster barrier.
 struct LstmTcParams {
-  const float* gx;   // [B][T][4H]
+  const float* gx;   // [B][gxT][4H]: input projections of steps gx_t0 .. gx_t0 + gxT - 1
   const float* whh;  // [4H][H] fp32 (PyTorch weight_hh layout)
   float* hout;       // [B][T][H]
-  int T, CS, U, B;
+  float* cstate;     // [B][H] cell state carried between the chunk launches of one sequence
+  int T, t0, t1;     // this launch runs steps [t0, t1); t0 > 0 resumes from hout[t0 - 1] and cstate
+  int gxT, gx_t0;
+  int CS, U, B;
 };
 
 __device__ __forceinline__ void mma_f16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -210,6 +213,13 @@ __global__ void __launch_bounds__(256, 1) lstm_tc_kernel(const LstmTcParams P) {
     }
   }
   for (int i = tid; i < (2 * CS * CHUNK + 2 * CHUNK) / 2; i += 256) reinterpret_cast<uint32_t*>(hs)[i] = 0u;
+  if (P.t0 > 0) {  // resume: h_{t0-1} of every unit (all CTAs' chunks) into buffer 0
+    __syncthreads();
+    for (int i = tid; i < Bn * H; i += 256) {
+      const int n = i / H, k = i - n * H;
+      hs[(size_t)(k / U) * CHUNK + n * LDU + k % U] = __float2half_rn(__ldcg(P.hout + ((size_t)(b0 + n) * P.T + P.t0 - 1) * H + k));
+    }
+  }
   if (tid == 0) {
     for (int i = 0; i < 2; ++i)
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&mbar[i])));
@@ -220,23 +230,26 @@ __global__ void __launch_bounds__(256, 1) lstm_tc_kernel(const LstmTcParams P) {
   // gate role: thread (n, u) finishes unit r*U + u of batch row b0 + n
   const int gn = tid / U, gu = tid - gn * U;
   const bool gate = gn < Bn;
-  const float* gxp = P.gx + ((size_t)(b0 + (gate ? gn : 0)) * P.T) * 4 * H + r * U + gu;
-  float* hop = P.hout + ((size_t)(b0 + (gate ? gn : 0)) * P.T) * H + r * U + gu;
+  const float* gxp = P.gx + ((size_t)(b0 + (gate ? gn : 0)) * P.gxT + (P.t0 - P.gx_t0)) * 4 * H + r * U + gu;
+  float* hop = P.hout + ((size_t)(b0 + (gate ? gn : 0)) * P.T + P.t0) * H + r * U + gu;
+  float* csp = P.cstate + (size_t)(b0 + (gate ? gn : 0)) * H + r * U + gu;
   float c = 0.0f, gi = 0.f, gf = 0.f, gg = 0.f, go = 0.f;
-  if (gate && P.T > 0) {
+  const int nsteps = P.t1 - P.t0;
+  if (gate && P.t0 > 0) c = __ldcg(csp);
+  if (gate && nsteps > 0) {
     gi = __ldcg(gxp);
     gf = __ldcg(gxp + H);
     gg = __ldcg(gxp + 2 * H);
     go = __ldcg(gxp + 3 * H);
   }
-  for (int t = 0; t < P.T; ++t) {
+  for (int t = 0; t < nsteps; ++t) {  // t: step inside this launch
     const int pc = t & 1, pn = pc ^ 1;
     const __half* cur = hs + (size_t)pc * CS * CHUNK;
     const uint32_t bar_n = (uint32_t)__cvta_generic_to_shared(&mbar[pn]);
     if (tid == 0)  // this step's CS incoming chunks complete the phase of the NEXT buffer's barrier
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_n), "r"(CS * CHUNK_BYTES) : "memory");
     float ni = 0.f, nf = 0.f, ng = 0.f, no = 0.f;
-    if (gate && t + 1 < P.T) {
+    if (gate && t + 1 < nsteps) {
       const float* g = gxp + (size_t)(t + 1) * 4 * H;
       ni = __ldcg(g);
       nf = __ldcg(g + H);
@@ -311,6 +324,7 @@ __global__ void __launch_bounds__(256, 1) lstm_tc_kernel(const LstmTcParams P) {
       }
     }
   }
+  if (gate) *csp = c;
   lstm_cluster_sync();  // nobody leaves while a peer may still be copying into its shared memory
 }
 
@@ -489,10 +503,13 @@ int pick_cluster(int H) {
 CodecDecoder::CodecDecoder(const Jen1CodecDesc& d, int device, int strict) : d_(d), device_(device), strict_(strict != 0) {
   const char* e = getenv("JEN1_LSTM");  // JEN1_LSTM=smem: the shared-memory-weights kernel (A/B partner of the tensor-core one)
   lstm_smem_kernel_ = e && strcmp(e, "smem") == 0;
+  lstm_no_overlap_ = e && strcmp(e, "serial") == 0;  // JEN1_LSTM=serial: tensor-core kernel, layers one after the other
 }
 
 CodecDecoder::~CodecDecoder() {
   cudaSetDevice(device_);
+  for (cudaEvent_t e : ev_) cudaEventDestroy(e);
+  if (side_) cudaStreamDestroy(side_);
   for (void* p : owned_) cudaFree(p);
   if (arena_) cudaFree(arena_);
 }
@@ -655,6 +672,12 @@ int CodecDecoder::finalize() {
     if (CS_ > 8 &&
         !ck(cudaFuncSetAttribute(lstm_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1), "lstm cluster attribute"))
       return 1;
+  }
+  if (cudaStreamCreateWithFlags(&side_, cudaStreamNonBlocking) != cudaSuccess) side_ = nullptr;
+  for (int i = 0; i <= kLstmChunks && side_; ++i) {
+    cudaEvent_t e;
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return fail("cudaEventCreate");
+    ev_.push_back(e);
   }
   host_.clear();
   finalized_ = true;
@@ -890,6 +913,131 @@ void CodecDecoder::fill_src(ConvParams& p, const Act& in, const Act* in2, int ac
   }
 }
 
+// One [t0, t1) launch of the tensor-core LSTM cluster kernel for layer `l`
+bool CodecDecoder::launch_lstm_tc(int l, const float* gx, int gxT, int gx_t0, float* hout, float* cstate, int t0, int t1, int B,
+                                  int T, cudaStream_t st) {
+  LstmTcFn tc = lstm_tc_fn(H_, U_);
+  LstmTcParams Q;
+  Q.gx = gx;
+  Q.whh = lstm_[l].whh_f32;
+  Q.hout = hout;
+  Q.cstate = cstate;
+  Q.T = T;
+  Q.t0 = t0;
+  Q.t1 = t1;
+  Q.gxT = gxT;
+  Q.gx_t0 = gx_t0;
+  Q.CS = CS_;
+  Q.U = U_;
+  Q.B = B;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(((B + 7) / 8) * CS_));
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = lstm_tc_smem(H_, U_);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)CS_;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (CS_ > 8) cudaFuncSetAttribute(tc, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  const bool good = ck(cudaLaunchKernelEx(&cfg, tc, Q), "lstm (tensor core) launch");
+  ++launches_;
+  ++lstm_tc_launches_;
+  return good;
+}
+
+// The LSTM layers over y0 (normalised by the consumer).  Returns the last layer's hidden sequence [B][T][H].
+// Two layers on the tensor-core kernel and a long sequence: the sequence is cut into chunks and layer 2 runs one chunk
+// behind layer 1 on a second stream (its input projection per chunk in between), so the two recurrences overlap.
+CodecDecoder::Act CodecDecoder::lstm_stack(const Act& y0, int B, int T, cudaStream_t st) {
+  const bool tc = !lstm_smem_kernel_ && lstm_tc_fn(H_, U_) != nullptr;
+  const int nchunk = (tc && lstm_.size() == 2 && T >= 1024 && side_ && !lstm_no_overlap_) ? kLstmChunks : 1;
+  auto proj = [&](int l, const Act& in, cudaStream_t s) {
+    ConvW W;
+    W.w = lstm_[l].wih;
+    W.bias = lstm_[l].bias;
+    W.gamma = W.beta = nullptr;
+    W.cin = H_;
+    W.cout = 4 * H_;
+    W.k = 1;
+    return conv(in, nullptr, ACT_NONE, W, 0, false, false, s);
+  };
+  auto seq = [&]() {
+    Act h;
+    h.C = H_;
+    h.L = h.Lstore = T;
+    h.ptr = falloc((size_t)B * T * H_);
+    return h;
+  };
+  if (nchunk > 1) {
+    Act gx1 = proj(0, y0, st);
+    Act h1 = seq(), h2 = seq();
+    float* c1 = falloc((size_t)B * H_);
+    float* c2 = falloc((size_t)B * H_);
+    for (int c = 0; c < nchunk; ++c) {
+      const int t0 = (int)((long long)T * c / nchunk), t1 = (int)((long long)T * (c + 1) / nchunk);
+      if (!dry_) {
+        if (!launch_lstm_tc(0, gx1.ptr, T, 0, h1.ptr, c1, t0, t1, B, T, st)) ok_ = false;
+        cudaEventRecord(ev_[c], st);
+        cudaStreamWaitEvent(side_, ev_[c], 0);
+      }
+      Act win = h1;  // rows [t0, t1) of layer 1's output
+      win.row0 = t0;
+      win.L = t1 - t0;
+      Act gx2 = proj(1, win, side_);
+      if (!dry_ && !launch_lstm_tc(1, gx2.ptr, t1 - t0, t0, h2.ptr, c2, t0, t1, B, T, side_)) ok_ = false;
+    }
+    if (!dry_) {
+      cudaEventRecord(ev_[nchunk], side_);
+      cudaStreamWaitEvent(st, ev_[nchunk], 0);
+    }
+    return h2;
+  }
+  Act cur = y0;
+  for (size_t l = 0; l < lstm_.size(); ++l) {
+    Act gx = proj((int)l, cur, st);
+    Act h = seq();
+    float* cs = falloc((size_t)B * H_);
+    if (!dry_) {
+      if (tc) {
+        if (!launch_lstm_tc((int)l, gx.ptr, T, 0, h.ptr, cs, 0, T, B, T, st)) ok_ = false;
+      } else {
+        LstmParams P;
+        P.gx = gx.ptr;
+        P.whh = lstm_[l].whh;
+        P.hout = h.ptr;
+        P.T = T;
+        P.H = H_;
+        P.CS = CS_;
+        P.U = U_;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)(B * CS_));
+        cfg.blockDim = dim3(256);
+        cfg.dynamicSmemBytes = lstm_smem();
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)CS_;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        // (function attributes are per process: another decoder instance may have set a smaller limit)
+        cudaFuncSetAttribute(lstm_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lstm_smem());
+        if (!ck(cudaLaunchKernelEx(&cfg, lstm_cluster_kernel, P), "lstm launch")) ok_ = false;
+        ++launches_;
+      }
+    }
+    cur = h;
+  }
+  return cur;
+}
+
 void CodecDecoder::walk(const float* latent, float* audio, int B, int T, cudaStream_t st) {
   B_ = B;
   // ---- latent [B][D][T] -> channels-last
@@ -904,85 +1052,9 @@ void CodecDecoder::walk(const float* latent, float* audio, int B, int T, cudaStr
   const int k0 = d_.kernel_size;
   Act y0 = conv(x, nullptr, ACT_NONE, first_, (k0 - 1) - (k0 - 1) / 2, true, true, st);
   // ---- SLSTM: value = lstm(GN(y0)) + GN(y0); the sum is taken by the next layer's prologue
-  Act cur = y0;
   Act hseq;
-  bool have_h = false;
-  for (size_t l = 0; l < lstm_.size(); ++l) {
-    ConvW W;
-    W.w = lstm_[l].wih;
-    W.bias = lstm_[l].bias;
-    W.gamma = W.beta = nullptr;
-    W.cin = H_;
-    W.cout = 4 * H_;
-    W.k = 1;
-    Act gx = conv(cur, nullptr, ACT_NONE, W, 0, false, false, st);
-    Act h;
-    h.C = H_;
-    h.L = h.Lstore = T;
-    h.ptr = falloc((size_t)B * T * H_);
-    if (!dry_) {
-      LstmTcFn tc = lstm_smem_kernel_ ? nullptr : lstm_tc_fn(H_, U_);
-      if (tc) {
-        LstmTcParams Q;
-        Q.gx = gx.ptr;
-        Q.whh = lstm_[l].whh_f32;
-        Q.hout = h.ptr;
-        Q.T = T;
-        Q.CS = CS_;
-        Q.U = U_;
-        Q.B = B;
-        cudaLaunchConfig_t cfg;
-        memset(&cfg, 0, sizeof(cfg));
-        cfg.gridDim = dim3((unsigned)(((B + 7) / 8) * CS_));
-        cfg.blockDim = dim3(256);
-        cfg.dynamicSmemBytes = lstm_tc_smem(H_, U_);
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = (unsigned)CS_;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        if (CS_ > 8) cudaFuncSetAttribute(tc, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        if (!ck(cudaLaunchKernelEx(&cfg, tc, Q), "lstm (tensor core) launch")) ok_ = false;
-        ++launches_;
-        ++lstm_tc_launches_;
-        cur = h;
-        hseq = h;
-        have_h = true;
-        continue;
-      }
-      LstmParams P;
-      P.gx = gx.ptr;
-      P.whh = lstm_[l].whh;
-      P.hout = h.ptr;
-      P.T = T;
-      P.H = H_;
-      P.CS = CS_;
-      P.U = U_;
-      cudaLaunchConfig_t cfg;
-      memset(&cfg, 0, sizeof(cfg));
-      cfg.gridDim = dim3((unsigned)(B * CS_));
-      cfg.blockDim = dim3(256);
-      cfg.dynamicSmemBytes = lstm_smem();
-      cfg.stream = st;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = (unsigned)CS_;
-      attr[0].val.clusterDim.y = 1;
-      attr[0].val.clusterDim.z = 1;
-      cfg.attrs = attr;
-      cfg.numAttrs = 1;
-      // (function attributes are per process: another decoder instance may have set a smaller limit)
-      cudaFuncSetAttribute(lstm_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lstm_smem());
-      if (!ck(cudaLaunchKernelEx(&cfg, lstm_cluster_kernel, P), "lstm launch")) ok_ = false;
-      ++launches_;
-    }
-    cur = h;
-    hseq = h;
-    have_h = true;
-  }
+  const bool have_h = !lstm_.empty();
+  if (have_h) hseq = lstm_stack(y0, B, T, st);
   // ---- upsampling stages
   Act a = y0;               // first operand of the running value
   Act a2 = hseq;            // optional second operand (value = GN(a) + value(a2))

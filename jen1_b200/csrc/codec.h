@@ -78,6 +78,10 @@ class CodecDecoder {
   Act convtr(const Act& in, const Act* in2, int act, const ConvW& W, int r, cudaStream_t st);
   Act last_conv(const Act& in, const Act* in2, const ConvW& W, int pad_left, cudaStream_t st);
   void walk(const float* latent, float* audio, int B, int T, cudaStream_t st);
+  Act lstm_stack(const Act& y0, int B, int T, cudaStream_t st);
+  bool launch_lstm_tc(int l, const float* gx, int gxT, int gx_t0, float* hout, float* cstate, int t0, int t1, int B, int T,
+                      cudaStream_t st);
+  static constexpr int kLstmChunks = 8;
 
   Jen1CodecDesc d_;
   int device_;
@@ -92,7 +96,9 @@ class CodecDecoder {
   uint8_t* arena_ = nullptr;
   size_t arena_bytes_ = 0, off_ = 0, soff_ = 0, stats_bytes_need_ = 0;
   int64_t launches_ = 0, weight_bytes_ = 0, tf32_launches_ = 0, lstm_tc_launches_ = 0;
-  bool lstm_smem_kernel_ = false;
+  bool lstm_smem_kernel_ = false, lstm_no_overlap_ = false;
+  cudaStream_t side_ = nullptr;
+  std::vector<cudaEvent_t> ev_;
 };
 
 }  // namespace jen1

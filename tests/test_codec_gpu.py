@@ -44,13 +44,15 @@ def test_decoder_matches_hf_golden(full):
         assert rel(out, c["out"]) < TOL[dec.precision], (name, rel(out, c["out"]))
 
 
-@pytest.mark.parametrize("B,T", [(1, 1), (2, 77), (3, 150), (1, 700)])
+@pytest.mark.parametrize("B,T", [(1, 1), (2, 77), (3, 150), (1, 700), (2, 1100)])  # T >= 1024: chunked, overlapped LSTM layers
 def test_decoder_matches_oracle_other_shapes(full, B, T):
     dec, sd, _ = full
     z = torch.randn(B, 128, T, generator=torch.Generator().manual_seed(100 + T))
     with torch.no_grad():
         ref = decoder_forward(dec.desc, sd, z)
+    n0 = dec.launch_count()
     out = dec(z.to(DEV)).cpu()
+    assert dec.launch_count() - n0 == (24 if T < 1024 else 24 + 7 * 3)  # 8 chunks: 7 more launches per LSTM layer + projection
     assert rel(out, ref) < TOL[dec.precision], rel(out, ref)
 
 
