@@ -587,13 +587,21 @@ bool CodecDecoder::make_conv(const std::string& prefix, const char* conv, const 
         for (int n = 0; n < cout; ++n) packed[((size_t)j * cin + c) * cout + n] = w->data[((size_t)n * cin + c) * k + j];
   }
   out->w = upload(packed);
+  {  // the same taps with Cin contiguous: [tap][columns][Cin]
+    const int taps = transposed ? 2 : k, cols = transposed ? (k / 2) * cout : cout;
+    std::vector<float> tp(packed.size());
+    for (int j = 0; j < taps; ++j)
+      for (int c = 0; c < cin; ++c)
+        for (int n = 0; n < cols; ++n) tp[((size_t)j * cols + n) * cin + c] = packed[((size_t)j * cin + c) * cols + n];
+    out->wT = upload(tp);
+  }
   out->bias = upload(bias);
   out->gamma = upload(g->data);
   out->beta = upload(be->data);
   out->cin = cin;
   out->cout = cout;
   out->k = k;
-  return out->w && out->bias && out->gamma && out->beta;
+  return out->w && out->wT && out->bias && out->gamma && out->beta;
 }
 
 int CodecDecoder::finalize() {
@@ -626,6 +634,7 @@ int CodecDecoder::finalize() {
       for (int c = 0; c < H_; ++c) wt[(size_t)c * 4 * H_ + n] = wih->data[(size_t)n * H_ + c];
     }
     L.wih = upload(wt);
+    L.wih_T = upload(wih->data);
     L.bias = upload(bsum);
     L.whh_f32 = upload(whh->data);
     const int R = 4 * U_;
@@ -758,6 +767,7 @@ CodecDecoder::Act CodecDecoder::conv(const Act& in, const Act* in2, int act, con
   fill_src(p, in, in2, act);
   ConvSeg& S = p.seg[0];
   S.w = W.w;
+  S.wT = W.wT;
   S.ntaps = W.k;
   S.in_stride = 1;
   S.shift0 = -pad_left;
@@ -806,7 +816,8 @@ CodecDecoder::Act CodecDecoder::convtr(const Act& in, const Act* in2, int act, c
   memset(&p, 0, sizeof(p));
   fill_src(p, in, in2, act);
   ConvSeg& S = p.seg[0];
-  S.w = W.w;  // packed [2][Cin][r * Cout] (make_conv, transposed)
+  S.w = W.w;
+  S.wT = W.wT;  // packed [2][Cin][r * Cout] (make_conv, transposed)
   S.ntaps = 2;
   S.in_stride = 1;
   S.shift0 = 0;
@@ -959,6 +970,7 @@ CodecDecoder::Act CodecDecoder::lstm_stack(const Act& y0, int B, int T, cudaStre
   auto proj = [&](int l, const Act& in, cudaStream_t s) {
     ConvW W;
     W.w = lstm_[l].wih;
+    W.wT = lstm_[l].wih_T;
     W.bias = lstm_[l].bias;
     W.gamma = W.beta = nullptr;
     W.cin = H_;

@@ -39,6 +39,7 @@ class CodecDecoder {
   };
   struct ConvW {  // tap-major fp32 weights [k][Cin][Cout] + bias + the GroupNorm(1, Cout) affine applied by consumers
     const float* w = nullptr;
+    const float* wT = nullptr;  // [k][Cout][Cin] copy for the TF32 kernel
     const float* bias = nullptr;
     const float* gamma = nullptr;
     const float* beta = nullptr;
@@ -46,6 +47,7 @@ class CodecDecoder {
   };
   struct LstmW {
     const float* wih = nullptr;   // [H][4H] (transposed for the k=1 tap-GEMM)
+    const float* wih_T = nullptr; // [4H][H] as loaded (TF32 kernel layout)
     const float* bias = nullptr;  // b_ih + b_hh
     const uint4* whh = nullptr;   // fp16, packed per cluster rank (codec.cu LstmParams)
     const float* whh_f32 = nullptr;  // [4H][H] as loaded (the tensor-core kernel builds its register fragments from it)

@@ -34,6 +34,7 @@ struct ConvSrc {
 struct ConvSeg {
   ConvSrc s[2];
   const void* w;  // T [n_wtaps][Cin][Cout]
+  const void* wT; // fp32 [n_wtaps][Cout][Cin]: the same weights, Cin contiguous (TF32 kernel only)
   int Cin;        // s[0].C + s[1].C
   int L;          // rows per batch in the sources
   int ntaps;

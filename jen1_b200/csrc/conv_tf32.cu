@@ -14,9 +14,7 @@
 namespace jen1 {
 
 namespace {
-constexpr int TM = 64, TN = 64, TK = 16, NT = 256;
-constexpr int LDK = TK + 4;  // A tile [m][k], row stride 20: fragment loads (20*g + t) and the staging stores are conflict-free
-constexpr int LDB = TN + 8;  // B tile [k][n], row stride 72: fragment loads (8*t + g) hit 32 distinct banks
+constexpr int TM = 64, TK = 16, NT = 256;
 
 __device__ __forceinline__ float to_tf32(float x) {
   uint32_t r;
@@ -32,18 +30,25 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
 }  // namespace
 
 #ifndef JEN1_TF32_MINB
-#define JEN1_TF32_MINB 6
+#define JEN1_TF32_MINB 4
 #endif
+// NT8: n8 MMA tiles per warp (4: 64-column CTA tile, 2: 32-column tile for the layers with <= 32 output channels).
+// The summation index of an MMA is free: k-slot 4j + t of a 16-channel step is mapped to channel 4t + j, so the four
+// operands a thread needs for both k8 halves are four CONSECUTIVE channels -- one 16-byte shared-memory load per
+// fragment row, the same 16 bytes a staging thread stores.  Tiles are [row][16 channels] (A) and [column][16 channels]
+// (B, from weights packed [tap][Cout][Cin]) with a 16-float row stride: conflict-free for 16-byte accesses.
+template <int NT8>
 __global__ void __launch_bounds__(NT, JEN1_TF32_MINB) conv_tf32_kernel(const ConvParams p) {
+  constexpr int TNW = NT8 * 16;  // CTA tile columns (2 warps across)
   extern __shared__ float dsm[];  // coefA[Cin] | coefS[Cin] | coefA2[Cin]
-  __shared__ __align__(16) float As[2][TM][LDK];
-  __shared__ __align__(16) float Bs[2][TK][LDB];
+  __shared__ __align__(16) float As[2][TM][TK];
+  __shared__ __align__(16) float Bs[2][TNW][TK];
   __shared__ float gmean[2], grstd[2];
-  __shared__ float cpart[4][TN][2];
+  __shared__ float cpart[4][TNW][2];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.z;
-  const int n0 = blockIdx.x * TN;  // N tiles fastest: the CTAs that share an input tile run together (L2 reuse)
+  const int n0 = blockIdx.x * TNW;  // N tiles fastest: the CTAs that share an input tile run together (L2 reuse)
   const ConvSeg& S = p.seg[0];
   const int Ct = S.Cin;
   float* coefA = dsm;
@@ -101,27 +106,27 @@ __global__ void __launch_bounds__(NT, JEN1_TF32_MINB) conv_tf32_kernel(const Con
   // ------------------------------------------------------------------ main loop
   const int nk = (Ct + TK - 1) / TK;
   const int total = S.ntaps * nk;
-  // staging: one 16-byte load per thread and operand tile (A: 64 rows x 16 channels, B: 16 channels x 64 columns)
+  // staging: one 16-byte load per thread and operand tile (A: 64 rows x 16 channels; B: TNW columns x 16 channels)
   const int a_c4 = (tid & 3) * 4, a_r = tid >> 2;
-  const int b_n4 = (tid & 15) * 4, b_k = tid >> 4;
   const int lext = p.Lext > 0 ? p.Lext : S.L;
-  const float* src0 = (const float*)S.s[0].ptr + ((size_t)(b % S.s[0].bmod) * lstore + S.row0) * Ct;
-  const float* src1 = p.sum2 ? (const float*)S.s[1].ptr + ((size_t)(b % S.s[1].bmod) * lstore + S.row0) * Ct : nullptr;
+  const float* src0 = (const float*)S.s[0].ptr + ((size_t)(b % S.s[0].bmod) * lstore + S.row0) * Ct + a_c4;
+  const float* src1 =
+      p.sum2 ? (const float*)S.s[1].ptr + ((size_t)(b % S.s[1].bmod) * lstore + S.row0) * Ct + a_c4 : nullptr;
   const int m0 = blockIdx.y * TM;
   const bool elu = p.act == ACT_ELU;
+  const bool row_ok = m0 + a_r < p.Lm;
+  const bool b_thread = tid < TNW * 4 && n0 + a_r < p.Cout;  // B staging: column a_r, channels a_c4 .. +3
+  const float* wsrc = (const float*)S.wT + (size_t)(n0 + a_r) * Ct + a_c4;  // + (tap * Cout) * Ct + kc
 
   float4 ra, rb;
-  auto fetch = [&](int it) {
-    const int tap = it / nk, kc = (it - tap * nk) * TK;
-    const int shift = S.shift0 + tap * S.shift_step;
-    const int wt = S.wtap0 + tap * S.wtap_step;
-    const int c = kc + a_c4;
-    const int m = m0 + a_r;
-    int irow = m * S.in_stride + shift;
+  int f_tap = 0, f_kc = 0;  // tap / first channel of the NEXT fetch (no division in the loop)
+  auto fetch = [&]() {
+    const int c = f_kc + a_c4;
+    int irow = (m0 + a_r) * S.in_stride + S.shift0 + f_tap * S.shift_step;
     if (p.pad_mode == PAD_REFLECT) irow = irow < 0 ? -irow : (irow >= lext ? 2 * lext - 2 - irow : irow);
     float v[4] = {0.f, 0.f, 0.f, 0.f};
-    if (m < p.Lm && irow >= 0 && irow < S.L && c < Ct) {  // Ct % 4 == 0: the four channels are in or out together
-      const float4 x = __ldg(reinterpret_cast<const float4*>(src0 + (size_t)irow * Ct + c));
+    if (row_ok && irow >= 0 && irow < S.L && c < Ct) {  // Ct % 4 == 0: the four channels are in or out together
+      const float4 x = __ldg(reinterpret_cast<const float4*>(src0 + (size_t)irow * Ct + f_kc));
       const float4 ca = *reinterpret_cast<const float4*>(coefA + c);
       const float4 cs = *reinterpret_cast<const float4*>(coefS + c);
       v[0] = fmaf(ca.x, x.x, cs.x);
@@ -129,7 +134,7 @@ __global__ void __launch_bounds__(NT, JEN1_TF32_MINB) conv_tf32_kernel(const Con
       v[2] = fmaf(ca.z, x.z, cs.z);
       v[3] = fmaf(ca.w, x.w, cs.w);
       if (src1) {
-        const float4 y = __ldg(reinterpret_cast<const float4*>(src1 + (size_t)irow * Ct + c));
+        const float4 y = __ldg(reinterpret_cast<const float4*>(src1 + (size_t)irow * Ct + f_kc));
         const float4 c2 = *reinterpret_cast<const float4*>(coefA2 + c);
         v[0] = fmaf(c2.x, y.x, v[0]);
         v[1] = fmaf(c2.y, y.y, v[1]);
@@ -142,45 +147,49 @@ __global__ void __launch_bounds__(NT, JEN1_TF32_MINB) conv_tf32_kernel(const Con
       }
     }
     ra = make_float4(to_tf32(v[0]), to_tf32(v[1]), to_tf32(v[2]), to_tf32(v[3]));
-    const int kk = kc + b_k, n = n0 + b_n4;
     rb = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (kk < Ct && n < p.Cout) {  // Cout % 4 == 0
-      const float4 w = __ldg(reinterpret_cast<const float4*>((const float*)S.w + ((size_t)wt * Ct + kk) * p.Cout + n));
+    if (b_thread && c < Ct) {
+      const int wt = S.wtap0 + f_tap * S.wtap_step;
+      const float4 w = __ldg(reinterpret_cast<const float4*>(wsrc + (size_t)wt * p.Cout * Ct + f_kc));
       rb = make_float4(to_tf32(w.x), to_tf32(w.y), to_tf32(w.z), to_tf32(w.w));
+    }
+    f_kc += TK;
+    if (f_kc >= Ct) {
+      f_kc = 0;
+      ++f_tap;
     }
   };
   auto stash = [&](int buf) {
     *reinterpret_cast<float4*>(&As[buf][a_r][a_c4]) = ra;
-    *reinterpret_cast<float4*>(&Bs[buf][b_k][b_n4]) = rb;
+    if (tid < TNW * 4) *reinterpret_cast<float4*>(&Bs[buf][a_r][a_c4]) = rb;
   };
 
-  const int wm = warp & 3, wn = warp >> 2;  // warp tile: rows wm*16 .. +15, columns wn*32 .. +31
+  const int wm = warp & 3, wn = warp >> 2;  // warp tile: rows wm*16 .. +15, columns wn*(8*NT8) .. 
   const int g = lane >> 2, t = lane & 3;
-  float acc[4][4];
+  float acc[NT8][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < NT8; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
 
-  fetch(0);
+  fetch();
   stash(0);
   __syncthreads();
   for (int it = 0; it < total; ++it) {
     const int buf = it & 1;
-    if (it + 1 < total) fetch(it + 1);
+    if (it + 1 < total) fetch();
+    {
+      const float4 x = *reinterpret_cast<const float4*>(&As[buf][wm * 16 + g][4 * t]);
+      const float4 y = *reinterpret_cast<const float4*>(&As[buf][wm * 16 + g + 8][4 * t]);
+      const uint32_t a0[4] = {__float_as_uint(x.x), __float_as_uint(y.x), __float_as_uint(x.y), __float_as_uint(y.y)};
+      const uint32_t a1[4] = {__float_as_uint(x.z), __float_as_uint(y.z), __float_as_uint(x.w), __float_as_uint(y.w)};
 #pragma unroll
-    for (int ks = 0; ks < TK; ks += 8) {
-      uint32_t af[4];
-      af[0] = __float_as_uint(As[buf][wm * 16 + g][ks + t]);
-      af[1] = __float_as_uint(As[buf][wm * 16 + g + 8][ks + t]);
-      af[2] = __float_as_uint(As[buf][wm * 16 + g][ks + t + 4]);
-      af[3] = __float_as_uint(As[buf][wm * 16 + g + 8][ks + t + 4]);
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        uint32_t bf[2];
-        bf[0] = __float_as_uint(Bs[buf][ks + t][wn * 32 + nt * 8 + g]);
-        bf[1] = __float_as_uint(Bs[buf][ks + t + 4][wn * 32 + nt * 8 + g]);
-        mma_tf32(acc[nt], af, bf);
+      for (int nt = 0; nt < NT8; ++nt) {
+        const float4 z = *reinterpret_cast<const float4*>(&Bs[buf][wn * (8 * NT8) + nt * 8 + g][4 * t]);
+        const uint32_t b0[2] = {__float_as_uint(z.x), __float_as_uint(z.y)};
+        const uint32_t b1[2] = {__float_as_uint(z.z), __float_as_uint(z.w)};
+        mma_tf32(acc[nt], a0, b0);
+        mma_tf32(acc[nt], a1, b1);
       }
     }
     if (it + 1 < total) stash(buf ^ 1);
@@ -188,10 +197,10 @@ __global__ void __launch_bounds__(NT, JEN1_TF32_MINB) conv_tf32_kernel(const Con
   }
 
   // ------------------------------------------------------------------ epilogue
-  // thread owns rows {wm*16 + g, +8} x columns {wn*32 + nt*8 + 2t, +1}: acc[nt][0..1] row g, acc[nt][2..3] row g + 8
-  float cS[4][2], cQ[4][2];
+  // thread owns rows {wm*16 + g, +8} x columns {wn*8*NT8 + nt*8 + 2t, +1}: acc[nt][0..1] row g, acc[nt][2..3] row g + 8
+  float cS[NT8][2], cQ[NT8][2];
 #pragma unroll
-  for (int nt = 0; nt < 4; ++nt) cS[nt][0] = cS[nt][1] = cQ[nt][0] = cQ[nt][1] = 0.f;
+  for (int nt = 0; nt < NT8; ++nt) cS[nt][0] = cS[nt][1] = cQ[nt][0] = cQ[nt][1] = 0.f;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const int m = m0 + wm * 16 + g + 8 * h;
@@ -199,18 +208,13 @@ __global__ void __launch_bounds__(NT, JEN1_TF32_MINB) conv_tf32_kernel(const Con
     const bool rv = (m < p.Lm) && (o >= 0) && (o < p.Lout);
     float* op = (float*)p.out + ((size_t)b * p.Lout + o) * p.Cout;
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-      const int n = n0 + wn * 32 + nt * 8 + 2 * t;
+    for (int nt = 0; nt < NT8; ++nt) {
+      const int n = n0 + wn * (8 * NT8) + nt * 8 + 2 * t;
       float x0 = 0.f, x1 = 0.f;
-      if (rv && n < p.Cout) x0 = acc[nt][2 * h] + (p.bias ? p.bias[n] : 0.f);
-      if (rv && n + 1 < p.Cout) x1 = acc[nt][2 * h + 1] + (p.bias ? p.bias[n + 1] : 0.f);
-      if (rv) {
-        if (n + 1 < p.Cout && (p.Cout & 1) == 0) {
-          *reinterpret_cast<float2*>(op + n) = make_float2(x0, x1);
-        } else {
-          if (n < p.Cout) op[n] = x0;
-          if (n + 1 < p.Cout) op[n + 1] = x1;
-        }
+      if (rv && n < p.Cout) {  // Cout % 4 == 0: n and n + 1 are in or out together
+        x0 = acc[nt][2 * h] + (p.bias ? p.bias[n] : 0.f);
+        x1 = acc[nt][2 * h + 1] + (p.bias ? p.bias[n + 1] : 0.f);
+        *reinterpret_cast<float2*>(op + n) = make_float2(x0, x1);
       }
       cS[nt][0] += x0;
       cS[nt][1] += x1;
@@ -221,7 +225,7 @@ __global__ void __launch_bounds__(NT, JEN1_TF32_MINB) conv_tf32_kernel(const Con
   if (p.stats_out) {
     // column sums over the warp's 16 rows (lanes with equal t), then over the 4 row-warps, then per fine group
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
+    for (int nt = 0; nt < NT8; ++nt)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         float s = cS[nt][e], q = cQ[nt][e];
@@ -231,13 +235,13 @@ __global__ void __launch_bounds__(NT, JEN1_TF32_MINB) conv_tf32_kernel(const Con
           q += __shfl_xor_sync(0xffffffffu, q, o);
         }
         if (g == 0) {
-          cpart[wm][wn * 32 + nt * 8 + 2 * t + e][0] = s;
-          cpart[wm][wn * 32 + nt * 8 + 2 * t + e][1] = q;
+          cpart[wm][wn * (8 * NT8) + nt * 8 + 2 * t + e][0] = s;
+          cpart[wm][wn * (8 * NT8) + nt * 8 + 2 * t + e][1] = q;
         }
       }
     __syncthreads();
-    const int gs = p.Cout / p.FGo;  // host guarantees gs | 64 and gs <= 64
-    const int ngl = TN / gs;
+    const int gs = min(p.Cout / p.FGo, TNW);  // channels per fine group inside this tile (host: gs | TNW or Cout < TNW)
+    const int ngl = TNW / gs;
     if (tid < ngl) {
       const int fg = n0 / gs + tid;
       if (fg < p.FGo) {
@@ -260,13 +264,19 @@ __global__ void __launch_bounds__(NT, JEN1_TF32_MINB) conv_tf32_kernel(const Con
 bool conv_tf32_supported(const ConvParams& p) {
   return p.nseg == 1 && p.mode == PRO_AFFINE && p.nphase == 1 && p.film == nullptr && p.res == nullptr && p.out != nullptr &&
          p.rowpart_out == nullptr && p.epi_act == ACT_NONE && (p.sum2 || p.seg[0].s[1].C == 0) && p.G <= 1 &&
-         (p.act == ACT_NONE || p.act == ACT_ELU) && (p.Lm + TM - 1) / TM <= 65535 && p.seg[0].Cin % 4 == 0 && p.Cout % 4 == 0;
+         (p.act == ACT_NONE || p.act == ACT_ELU) && (p.Lm + TM - 1) / TM <= 65535 && p.seg[0].Cin % 4 == 0 && p.Cout % 4 == 0 &&
+         p.seg[0].wT != nullptr && (p.stats_out == nullptr || p.Cout <= 32 || (p.Cout / p.FGo) == 64);
 }
 
 cudaError_t launch_conv_tf32(const ConvParams& p, cudaStream_t stream) {
-  dim3 grid((p.Cout + TN - 1) / TN, (p.Lm + TM - 1) / TM, p.B);
   size_t dsm = (size_t)3 * p.seg[0].Cin * sizeof(float);
-  conv_tf32_kernel<<<grid, NT, dsm, stream>>>(p);
+  if (p.Cout <= 32) {
+    dim3 grid((p.Cout + 31) / 32, (p.Lm + TM - 1) / TM, p.B);
+    conv_tf32_kernel<2><<<grid, NT, dsm, stream>>>(p);
+  } else {
+    dim3 grid((p.Cout + 63) / 64, (p.Lm + TM - 1) / TM, p.B);
+    conv_tf32_kernel<4><<<grid, NT, dsm, stream>>>(p);
+  }
   return cudaGetLastError();
 }
 
