@@ -474,23 +474,24 @@ def codec_decode_leg(B, T, dev, cpu=True):
         for _ in range(2):
             dec(z)
         torch.cuda.synchronize(dev)
-        n0, t0 = dec.launch_count(), dec.tf32_launch_count()
+        n0, t0, l0 = dec.launch_count(), dec.tf32_launch_count(), dec.lstm_tc_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(reps):
             dec(z)
         e1.record()
         torch.cuda.synchronize(dev)
-        return dec, e0.elapsed_time(e1) / reps, (dec.launch_count() - n0) // reps, (dec.tf32_launch_count() - t0) // reps
+        return (dec, e0.elapsed_time(e1) / reps, (dec.launch_count() - n0) // reps, (dec.tf32_launch_count() - t0) // reps,
+                (dec.lstm_tc_launch_count() - l0) // reps)
 
-    _, ms_strict, _, _ = timed("fp32", 2)
-    dec, ms, nl, ntf = timed("tf32", 5)
+    _, ms_strict, _, _, _ = timed("fp32", 2)
+    dec, ms, nl, ntf, nlstm = timed("tf32", 5)
     work = decode_work(cdesc, T)
     pk = _peaks()
     leg = {"ms_per_decode": ms, "precision": "tf32 tensor-core convs, fp16 recurrent LSTM weights, fp32 storage / accumulation",
            "ms_per_decode_fp32_strict": ms_strict, "audio_seconds": B * T / 150.0,
            "samples_per_s": B * T * cdesc.hop / (ms / 1e3), "launches_per_decode": nl, "tf32_gemm_launches": ntf,
-           "lstm_tensor_core_launches": 2, "lstm_cluster_ctas": dec.lstm_cluster(), "workspace_gb": dec.workspace_bytes(B, T) / 1e9,
+           "lstm_tensor_core_launches": nlstm, "lstm_cluster_ctas": dec.lstm_cluster(), "workspace_gb": dec.workspace_bytes(B, T) / 1e9,
            "algorithmic_gb": B * work["bytes"] / 1e9, "hbm_frac": B * work["bytes"] / (ms / 1e3) / 1e9 / pk["hbm"],
            "tflops": B * work["flops"] / (ms / 1e3) / 1e12,
            "what": "EncodecDecoder(latent [%d,128,%d]) -> audio [%d,2,%d] fp32, device-timed, latent resident; seeded "
