@@ -329,10 +329,6 @@ __global__ void __launch_bounds__(kAtThreads, 1) attn_umma_kernel(const __grid_c
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols)
                  : "memory");
   }
-  if (tid == 128) {  // leave no live barrier objects behind for the next CTA that gets this shared memory
-#pragma unroll
-    for (int i = 0; i < 4; ++i) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&bars[i])) : "memory");
-  }
 }
 
 }  // namespace
