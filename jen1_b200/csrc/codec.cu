@@ -740,7 +740,7 @@ int CodecDecoder::reserve(int B, int T) {
 // TF32 tensor-core tap-GEMM by default; fp32 FMA in strict mode (and for the LSTM input projection, whose result feeds
 // 4 545 recurrent steps)
 cudaError_t CodecDecoder::launch_conv(const ConvParams& p, cudaStream_t st) {
-  if (!strict_ && !force_fp32_ && conv_tf32_supported(p)) {
+  if (!strict_ && conv_tf32_supported(p)) {
     ++tf32_launches_;
     return launch_conv_tf32(p, st);
   }

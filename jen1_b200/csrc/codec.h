@@ -87,7 +87,7 @@ class CodecDecoder {
 
   Jen1CodecDesc d_;
   int device_;
-  bool finalized_ = false, dry_ = false, ok_ = true, strict_ = false, force_fp32_ = false;
+  bool finalized_ = false, dry_ = false, ok_ = true, strict_ = false;
   std::string err_;
   std::map<std::string, HostTensor> host_;
   std::vector<void*> owned_;

@@ -1,6 +1,7 @@
 """`Jen1.generate()` facade on the GPU (reference generation.py:76-132, intended semantics -- DESIGN.md section 8):
 the three tasks run through the engine, `causal` reaches the sampler for continuation, masks are resampled to the
-latent rate per sample, and a seed reproduces the output.  Latent-domain (no codec): Encodec is out of scope.
+latent rate per sample, and a seed reproduces the output.  Latent-domain unless a codec is attached (last test: the sampled
+latent goes through the Encodec-decoder engine).
 """
 import pytest
 import torch
