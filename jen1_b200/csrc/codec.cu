@@ -14,12 +14,13 @@
 //                          encodec normalises before unpad1d) and consumers read the trimmed window (ConvSeg.row0/Lstore)
 //   * SEANetResnetBlock  = three tap-GEMMs; "shortcut + block" is never materialised: the next layer's prologue adds the
 //                          two normalised tensors (ConvParams.sum2)
-//   * SLSTM              = W_ih x_t for all t as one k=1 tap-GEMM, then a persistent thread-block CLUSTER per sequence:
-//                          W_hh lives in shared memory (fp16, sliced over the cluster's CTAs), h_t is broadcast over
-//                          distributed shared memory, one cluster barrier per time step; the skip connection is folded
-//                          into the next layer's prologue (sum2 with a plain second source).
-// Convs run on the TF32 tensor-core tap-GEMM (conv_tf32.cu; mma.sync m16n8k8, fp32 accumulation) or, in strict mode and
-// for the LSTM input projection, on the fp32-FMA tap-GEMM (conv_generic.cu); the last 32 -> 2 conv has its own kernel.
+//   * SLSTM              = W_ih x_t for all t as one k=1 tap-GEMM, then a persistent thread-block CLUSTER (16 CTAs) for
+//                          up to 8 sequences: W_hh lives in registers as fp16 mma fragments, sliced over the CTAs; h_t is
+//                          broadcast with bulk copies over distributed shared memory that complete on mbarriers
+//                          (lstm_tc_kernel; lstm_cluster_kernel is the first version, kept as A/B partner and fallback);
+//                          the skip connection is folded into the next layer's prologue (sum2, plain second source).
+// Convs run on the TF32 tensor-core tap-GEMM (conv_tf32.cu; mma.sync m16n8k8, fp32 accumulation) or, in strict mode, on
+// the fp32-FMA tap-GEMM (conv_generic.cu); the last 32 -> 2 conv has its own kernel.
 #include "codec.h"
 
 #include <cuda_fp16.h>
@@ -737,8 +738,7 @@ int CodecDecoder::reserve(int B, int T) {
   return 0;
 }
 
-// TF32 tensor-core tap-GEMM by default; fp32 FMA in strict mode (and for the LSTM input projection, whose result feeds
-// 4 545 recurrent steps)
+// TF32 tensor-core tap-GEMM by default; fp32 FMA in strict mode and for shapes the TF32 kernel does not take
 cudaError_t CodecDecoder::launch_conv(const ConvParams& p, cudaStream_t st) {
   if (!strict_ && conv_tf32_supported(p)) {
     ++tf32_launches_;
