@@ -4,6 +4,7 @@ sampling loop (`GaussianDiffusion.sample` driving an arbitrary callable -- here 
 reference trajectories."""
 import os
 
+import pytest
 import torch
 
 from jen1_b200.config import UNetDesc, latent_frames, tiny_desc
@@ -151,3 +152,28 @@ def test_convert_audio_resampling_identities():
     assert mono.shape == (1, 1, L) and torch.allclose(mono[0, 0], x[0].mean(0))
     st = convert_audio(x[:, :1], 48000, 48000, 2)
     assert st.shape == (1, 2, L) and torch.equal(st[0, 0], st[0, 1])
+
+
+def test_codec_description_key_layouts_and_work_model():
+    """Encodec decoder host logic: the tensor inventory of the 48 kHz decoder, both state_dict key layouts (pip package /
+    Hugging Face port, optional `decoder.` prefix), shape checking, and the work model bench.py reports against."""
+    from jen1_b200.codec_config import CodecDesc, canonical_state_dict, decode_work, random_state_dict as codec_sd, to_hf_names
+    desc = CodecDesc()
+    assert desc.hidden == 512 and desc.hop == 320
+    kinds = [k for _, k, *_ in desc.layers()]
+    assert kinds == ["conv", "lstm"] + ["convtr", "res"] * 4 + ["conv"]
+    assert [i for i, *_ in desc.layers()] == [0, 1, 3, 4, 6, 7, 9, 10, 12, 13, 15]  # model.N indices (ELUs hold no tensors)
+    sd = codec_sd(desc, 1)
+    assert sum(v.numel() for v in sd.values()) == sum(int(torch.tensor(s).prod()) for _, s, _ in desc.tensor_spec())
+    assert sd["model.3.convtr.convtr.weight"].shape == (512, 256, 16) and sd["model.1.lstm.weight_hh_l1"].shape == (2048, 512)
+    hf = {"decoder." + k: v for k, v in to_hf_names(sd).items()}
+    assert "decoder.layers.4.block.1.conv.weight" in hf and "decoder.layers.4.shortcut.norm.bias" in hf
+    back = canonical_state_dict(desc, dict(hf, **{"encoder.layers.0.conv.weight": torch.zeros(1)}))  # extra keys ignored
+    assert set(back) == set(sd) and all(torch.equal(back[k], sd[k]) for k in sd)
+    bad = dict(sd)
+    bad["model.0.conv.conv.weight"] = torch.zeros(512, 128, 5)
+    with pytest.raises(ValueError):
+        canonical_state_dict(desc, bad)
+    w = decode_work(desc, 4545)  # SURVEY section 8(f): 181 GFLOP per 30 s sample
+    assert abs(w["flops"] / 1e9 - 181.2) < 0.5 and w["samples"] == 4545 * 320
+    assert 4.0e9 < w["bytes"] < 4.6e9
