@@ -475,20 +475,23 @@ def codec_decode_leg(B, T, dev, cpu=True):
             dec(z)
         torch.cuda.synchronize(dev)
         n0, t0, l0 = dec.launch_count(), dec.tf32_launch_count(), dec.lstm_tc_launch_count()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
+        each = []
+        for _ in range(reps):  # one event pair per decode, median: a single host / driver hiccup must not move the number
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
             dec(z)
-        e1.record()
-        torch.cuda.synchronize(dev)
-        return (dec, e0.elapsed_time(e1) / reps, (dec.launch_count() - n0) // reps, (dec.tf32_launch_count() - t0) // reps,
-                (dec.lstm_tc_launch_count() - l0) // reps)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            each.append(e0.elapsed_time(e1))
+        each.sort()
+        return (dec, each[len(each) // 2], (dec.launch_count() - n0) // reps, (dec.tf32_launch_count() - t0) // reps,
+                (dec.lstm_tc_launch_count() - l0) // reps, each)
 
-    _, ms_strict, _, _, _ = timed("fp32", 2)
-    dec, ms, nl, ntf, nlstm = timed("tf32", 5)
+    _, ms_strict, _, _, _, _ = timed("fp32", 3)
+    dec, ms, nl, ntf, nlstm, each = timed("tf32", 7)
     work = decode_work(cdesc, T)
     pk = _peaks()
-    leg = {"ms_per_decode": ms, "precision": "tf32 tensor-core convs, fp16 recurrent LSTM weights, fp32 storage / accumulation",
+    leg = {"ms_per_decode": ms, "ms_per_decode_min_max": [each[0], each[-1]], "decodes_timed": len(each), "precision": "tf32 tensor-core convs, fp16 recurrent LSTM weights, fp32 storage / accumulation",
            "ms_per_decode_fp32_strict": ms_strict, "audio_seconds": B * T / 150.0,
            "samples_per_s": B * T * cdesc.hop / (ms / 1e3), "launches_per_decode": nl, "tf32_gemm_launches": ntf,
            "lstm_tensor_core_launches": nlstm, "lstm_cluster_ctas": dec.lstm_cluster(), "workspace_gb": dec.workspace_bytes(B, T) / 1e9,

@@ -11,6 +11,14 @@ for T in [int(a) for a in sys.argv[1:]]:
     try:
         out = dec(z); torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = int(os.environ.get("CODEC_REPS", "3"))
+        each = []
+        for _ in range(reps):
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(); out = dec(z); a1.record(); torch.cuda.synchronize()
+            each.append(a0.elapsed_time(a1))
+        if reps > 3:
+            print("each:", " ".join("%.1f" % v for v in each), flush=True)
         e0.record()
         for _ in range(3):
             out = dec(z)
