@@ -4,8 +4,8 @@ TAG=${1:-kf}
 O=gpurun_out
 mkdir -p $O
 M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum
-timeout 600 python -m pytest tests/test_codec_gpu.py tests/test_generation_gpu.py -m gpu -q 2>&1 | tail -2
-for v in tree mb3; do if [ $v = tree ]; then unset JEN1_B200_LIB; else export JEN1_B200_LIB=$PWD/jen1_b200/_C/variants/$v/libjen1_b200.so; fi; echo $v; CODEC_B=4 timeout 300 python scripts/codec_probe.py 4545 2>&1 | tail -1; done
+timeout 1500 python -m pytest tests -m gpu -q --timeout 600 2>&1 | tail -2; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+CODEC_B=4 CODEC_REPS=10 timeout 300 python scripts/codec_probe.py 4545 2>&1 | tail -2
 unset JEN1_B200_LIB
 timeout 900 python bench.py --steps 100 --warmup 5 > $O/${TAG}_bench_config3.json 2> $O/${TAG}_bench_config3.err; echo "bench rc=$?"
 timeout 300 python bench.py --workload config2 --steps 100 --warmup 5 --no-gpu-eager > $O/${TAG}_bench_config2.json 2> $O/${TAG}_bench_config2.err
