@@ -118,10 +118,25 @@ __device__ __forceinline__ void bar_sync_producers() { asm volatile("bar.sync 1,
 // every outstanding global access of the thread: ~1 us in the layer chain); the data exchanged here lives in shared
 // memory only, so a CTA-scope fence (the stores are performed at this SM's shared memory, the one point every remote
 // ld.shared::cluster of them goes through) followed by the relaxed barrier is sufficient.
+// JEN1_CLUSTER_CANONICAL (A/B, profiles/r02_ab_cluster_fence.txt): 1 = the PTX-model form, barrier.cluster.arrive.release
+// + wait.acquire, for the data hand-off barrier; 2 = also for the closing barrier.  0 = CTA-scope fence + relaxed arrive.
+#ifndef JEN1_CLUSTER_CANONICAL
+#define JEN1_CLUSTER_CANONICAL 0
+#endif
 __device__ __forceinline__ void cluster_sync_all() {
+#if JEN1_CLUSTER_CANONICAL >= 1
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+#else
   asm volatile("fence.acq_rel.cta;\n\tbarrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+#endif
 }
-__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_arrive_relaxed() {
+#if JEN1_CLUSTER_CANONICAL >= 2
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+#else
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+#endif
+}
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
