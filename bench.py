@@ -515,6 +515,33 @@ def codec_decode_leg(B, T, dev, cpu=True):
     return leg
 
 
+def generate_audio_leg(desc, sd, B, T, steps, dev, dtype):
+    """The reference's public entry point end to end (generation.py:76-132): Jen1.generate(prompts, steps, seconds) ->
+    audio on the host.  Conditioner (seeded random text embeddings: T5 weights are unreachable offline), sampling loop on
+    the UNet engine, Encodec decoder engine, device -> host copy of the audio; wall clock, median of 3 calls."""
+    import torch
+    from jen1_b200.codec_config import CodecDesc, random_state_dict as codec_sd
+    from jen1_b200.generation import Jen1
+    import warnings
+    jen = Jen1(None, device=dev, desc=desc, state_dict=sd, dtype=dtype, codec_state_dict=codec_sd(CodecDesc(), 11))
+    seconds = T / 151.5  # latent_frames(seconds) == T for the benchmark shapes (10 s -> 1515, 30 s -> 4545)
+    prompts = ["prompt %d" % i for i in range(B)]
+    times = []
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for rep in range(4):
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            audio = jen.generate(prompts, seed=rep, steps=steps, batch_size=B, seconds=seconds, use_gdm=True).cpu()
+            times.append((time.perf_counter() - t0) * 1e3)
+    assert audio.shape == (B, 2, T * 320) and bool(torch.isfinite(audio).all())
+    ms = sorted(times[1:])[1]
+    return {"ms_per_call": ms, "audio_seconds": B * T / 150.0, "realtime_factor": B * T / 150.0 / (ms / 1e3), "steps": steps,
+            "what": "Jen1.generate(%d prompts, steps=%d, seconds=%.0f) -> host audio [%d, 2, %d]: conditioner, DDIM loop on the "
+                    "UNet engine, Encodec decoder engine, D2H copy; wall clock, median of 3 calls after one warm call"
+                    % (B, steps, seconds, B, T * 320)}
+
+
 def run_ours(args, wl, scaling):
     import torch
     import torch.distributed as dist
@@ -630,6 +657,8 @@ def run_ours(args, wl, scaling):
 
     if world == 1 and not args.quick:
         extra["codec_decode"] = codec_decode_leg(B, T, dev, cpu=not args.no_cpu_baseline)
+        if args.workload != "config5":
+            extra["generate_audio"] = generate_audio_leg(desc, sd, B, T, K, dev, args.dtype)
 
     if rank == 0:
         pk = _peaks()
