@@ -140,6 +140,18 @@ size_t jen1_codec_workspace_bytes(void* handle, int B, int T);
 int jen1_codec_reserve(void* handle, int B, int T);
 /* latent: DEVICE fp32 [B][dimension][T]; audio: DEVICE fp32 [B][channels][T * hop]. */
 int jen1_codec_decode(void* handle, const float* latent, float* audio, int B, int T, jen1_stream_t stream);
+/* ---- Encodec encoder + residual vector quantizer: audio -> latent, reference generation.py:145-150 (`get_emb`:
+ * audio_encoder.encode(...) segment by segment, then quantizer.decode(codes)).  Same description struct; tensors are named
+ * as in the pip package (encoder.model.N.conv.conv.weight ..., quantizer.vq.layers.i._codebook.embed).  The handle is used
+ * with jen1_codec_load_tensor / _finalize / _destroy / _last_error like a decoder handle. */
+int jen1_codec_create_encoder(const Jen1CodecDesc* desc, int device, int precision, int n_q, int codebook_size, void** out_handle);
+/* audio: DEVICE fp32 [N][channels][L] (one row per segment, already loudness-normalised by the caller);
+ * latent: DEVICE fp32 [N][dimension][T], T = ceil(L / hop) -- the encoder output before quantisation;
+ * codes: DEVICE int32 [n_q][N][T] or NULL; quantized: DEVICE fp32 [N][dimension][T] or NULL (sum of the chosen entries). */
+int jen1_codec_encode(void* handle, const float* audio, float* latent, int32_t* codes, float* quantized, int N, int L,
+                      jen1_stream_t stream);
+/* The residual vector quantizer alone (quantizer.encode + quantizer.decode) on a DEVICE latent [N][dimension][T]. */
+int jen1_codec_quantize(void* handle, const float* latent, int32_t* codes, float* quantized, int N, int T, jen1_stream_t stream);
 int64_t jen1_codec_launch_count(void* handle);
 int64_t jen1_codec_tf32_launch_count(void* handle); /* how many of them were the TF32 tensor-core tap-GEMM */
 int64_t jen1_codec_lstm_tc_launch_count(void* handle); /* ... and the tensor-core LSTM cluster kernel */

@@ -61,6 +61,9 @@ SIGNATURES = {
     "jen1_engine_fused_transformer_launch_count": (C.c_int64, [C.c_void_p]),
     "jen1_engine_debug_tensor": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
     "jen1_codec_create": (C.c_int, [C.POINTER(Jen1CodecDesc), C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "jen1_codec_create_encoder": (C.c_int, [C.POINTER(Jen1CodecDesc), C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "jen1_codec_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "jen1_codec_quantize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "jen1_codec_destroy": (None, [C.c_void_p]),
     "jen1_codec_last_error": (C.c_char_p, [C.c_void_p]),
     "jen1_codec_load_tensor": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int]),

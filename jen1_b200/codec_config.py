@@ -94,6 +94,92 @@ class CodecDesc:
         return spec
 
 
+def encoder_layers(desc: CodecDesc) -> List[tuple]:
+    """SEANetEncoder (encodec/modules/seanet.py), the decoder's mirror: [(index, kind, cin, cout, k, stride)] in `model.N`
+    order: conv k7 channels -> n_filters; per ratio r (reversed decoder ratios, channels C -> 2C): ResnetBlock(C), ELU,
+    SConv1d(C -> 2C, k = 2r, stride r); SLSTM; ELU; SConv1d(16*n_filters -> dimension, k7)."""
+    out = [(0, "conv", desc.channels, desc.n_filters, desc.kernel_size, 1)]
+    idx, c = 0, desc.n_filters
+    for r in reversed(desc.ratios):
+        out.append((idx + 1, "res", c, c, desc.residual_kernel_size, 1))
+        out.append((idx + 3, "down", c, 2 * c, 2 * r, r))
+        idx += 3
+        c *= 2
+    out.append((idx + 1, "lstm", c, c, 0, 0))
+    out.append((idx + 3, "conv", c, desc.dimension, desc.last_kernel_size, 1))
+    return out
+
+
+def encoder_tensor_spec(desc: CodecDesc, n_q: int = 16, codebook_size: int = 1024) -> List[tuple]:
+    """[(name, shape, kind)]: the encoder's tensors (`encoder.model.N...`, pip naming) and the residual vector quantizer's
+    codebooks (`quantizer.vq.layers.i._codebook.embed`)."""
+    spec = []
+
+    def conv(prefix, cin, cout, k):
+        spec.append((prefix + ".conv.conv.weight", (cout, cin, k), "w:%d" % (cin * k)))
+        spec.append((prefix + ".conv.conv.bias", (cout,), "w:%d" % (cin * k)))
+        spec.append((prefix + ".conv.norm.weight", (cout,), "norm_w"))
+        spec.append((prefix + ".conv.norm.bias", (cout,), "norm_b"))
+
+    for idx, kind, cin, cout, k, stride in encoder_layers(desc):
+        p = "encoder.model.%d" % idx
+        if kind in ("conv", "down"):
+            conv(p, cin, cout, k)
+        elif kind == "lstm":
+            for layer in range(desc.lstm_layers):
+                spec.append(("%s.lstm.weight_ih_l%d" % (p, layer), (4 * cout, cin), "w:%d" % cout))
+                spec.append(("%s.lstm.weight_hh_l%d" % (p, layer), (4 * cout, cout), "w:%d" % cout))
+                spec.append(("%s.lstm.bias_ih_l%d" % (p, layer), (4 * cout,), "w:%d" % cout))
+                spec.append(("%s.lstm.bias_hh_l%d" % (p, layer), (4 * cout,), "w:%d" % cout))
+        else:
+            hid = cin // desc.compress
+            conv(p + ".block.1", cin, hid, k)
+            conv(p + ".block.3", hid, cout, 1)
+            conv(p + ".shortcut", cin, cout, 1)
+    for i in range(n_q):
+        spec.append(("quantizer.vq.layers.%d._codebook.embed" % i, (codebook_size, desc.dimension), "codebook"))
+    return spec
+
+
+def random_encoder_state_dict(desc: CodecDesc, seed: int = 0, n_q: int = 16, codebook_size: int = 1024) -> Dict[str, torch.Tensor]:
+    g = torch.Generator(device="cpu")
+    g.manual_seed(int(seed))
+    sd = {}
+    for name, shape, kind in encoder_tensor_spec(desc, n_q, codebook_size):
+        if kind.startswith("w:"):
+            bound = 1.0 / math.sqrt(int(kind[2:]))
+            t = (torch.rand(shape, generator=g, dtype=torch.float32) * 2.0 - 1.0) * bound
+        elif kind == "norm_w":
+            t = 1.0 + 0.1 * torch.randn(shape, generator=g, dtype=torch.float32)
+        elif kind == "norm_b":
+            t = 0.1 * torch.randn(shape, generator=g, dtype=torch.float32)
+        else:  # codebooks: stage i has residual-sized entries
+            i = int(name.split(".")[3])
+            t = torch.randn(shape, generator=g, dtype=torch.float32) * (0.7 ** i)
+        sd[name] = t
+    return sd
+
+
+def canonical_encoder_state_dict(desc: CodecDesc, sd: Dict[str, torch.Tensor], n_q: int = 16, codebook_size: int = 1024):
+    """pip layout (`encoder.model.N.conv.conv.weight`, `quantizer.vq.layers.i._codebook.embed`) or the Hugging Face
+    port's (`encoder.layers.N.conv.weight`, `quantizer.layers.i.codebook.embed`) -> canonical (pip) names."""
+    out = {}
+    for name, shape, _ in encoder_tensor_spec(desc, n_q, codebook_size):
+        hf = name.replace("encoder.model.", "encoder.layers.", 1)
+        hf = hf.replace(".conv.conv.", ".conv.").replace(".conv.norm.", ".norm.")
+        hf = hf.replace("quantizer.vq.layers.", "quantizer.layers.").replace("._codebook.embed", ".codebook.embed")
+        for c in (name, hf):
+            if c in sd:
+                t = sd[c].detach().to(torch.float32).cpu().contiguous()
+                if tuple(t.shape) != tuple(shape):
+                    raise ValueError("tensor %s has shape %s, expected %s" % (c, tuple(t.shape), tuple(shape)))
+                out[name] = t
+                break
+        else:
+            raise KeyError("encoder state_dict is missing %s (also tried %s)" % (name, hf))
+    return out
+
+
 def decode_work(desc: CodecDesc, T: int) -> Dict[str, float]:
     """Algorithmic work of ONE sample's decode at T latent frames: fp32 bytes every layer must read (each operand once;
     a "sum of two normalised tensors" input counts both) and write, and 2*MAC flops.  Used by bench.py's codec leg."""

@@ -163,6 +163,37 @@ int jen1_codec_create(const Jen1CodecDesc* desc, int device, int precision, void
   *out_handle = k;
   return 0;
 }
+int jen1_codec_create_encoder(const Jen1CodecDesc* desc, int device, int precision, int n_q, int codebook_size, void** out_handle) {
+  if (!desc || !out_handle) return 1;
+  *out_handle = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    snprintf(g_create_error, sizeof g_create_error, "no CUDA device %d (the codec engine has no CPU fallback)", device);
+    return 2;
+  }
+  if (precision != JEN1_CODEC_FP32 && precision != JEN1_CODEC_TF32) return 3;
+  CodecDecoder* k = new (std::nothrow) CodecDecoder(*desc, device, precision == JEN1_CODEC_FP32, true, n_q, codebook_size);
+  if (!k) return 4;
+  *out_handle = k;
+  return 0;
+}
+int jen1_codec_encode(void* h, const float* audio, float* latent, int32_t* codes, float* quantized, int N, int L,
+                      jen1_stream_t stream) {
+  if (!h) return 1;
+  try {
+    return K(h)->encode(audio, latent, codes, quantized, N, L, reinterpret_cast<cudaStream_t>(stream));
+  } catch (...) {
+    return 99;
+  }
+}
+int jen1_codec_quantize(void* h, const float* latent, int32_t* codes, float* quantized, int N, int T, jen1_stream_t stream) {
+  if (!h) return 1;
+  try {
+    return K(h)->quantize(latent, codes, quantized, N, T, reinterpret_cast<cudaStream_t>(stream));
+  } catch (...) {
+    return 99;
+  }
+}
 void jen1_codec_destroy(void* h) { delete K(h); }
 const char* jen1_codec_last_error(void* h) { return h ? K(h)->last_error() : g_create_error; }
 int jen1_codec_load_tensor(void* h, const char* name, const float* host_data, const int64_t* shape, int ndim) {

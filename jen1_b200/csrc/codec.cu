@@ -342,6 +342,104 @@ size_t lstm_tc_smem(int H, int U) {
   return (size_t)(2 * CS * CHUNK + 2 * CHUNK) * 2 + (size_t)8 * (4 * U + 4) * 4 + 16 + 16;
 }
 
+// ------------------------------------------------------------------------------------------------ residual VQ
+// ResidualVectorQuantizer.encode + decode (encodec/quantization/core_vq.py; reference generation.py:146-149): per stage the
+// nearest codebook entry of the residual (euclidean: argmax of 2 r.e - |e|^2, lowest index on ties), residual -= entry,
+// quantized += entry.  fp32 throughout (an argmax does not forgive rounded operands).  One CTA = 32 frames of one row:
+// residual and running sum live in shared memory [dim][frame]; the codebook streams through in 64-entry chunks; thread
+// (frame, group of 8 entries) keeps 8 dot products.
+struct RvqParams {
+  const float* emb;        // [N][D][T]
+  const float* codebooks;  // [nq][K][D]
+  const float* enorm;      // [nq][K]
+  float* quant;            // [N][D][T] or nullptr
+  int32_t* codes;          // [nq][N][T] or nullptr
+  int N, T, D, K, nq;
+};
+constexpr int RQ_F = 32, RQ_C = 64;
+
+__global__ void __launch_bounds__(256) rvq_kernel(const RvqParams P) {
+  extern __shared__ float rsm[];
+  const int D = P.D, lde = D + 1;
+  float* R = rsm;                    // [D][32] residual
+  float* Q = R + D * RQ_F;           // [D][32] quantized
+  float* E = Q + D * RQ_F;           // [64][D + 1] codebook chunk
+  float* bs = E + RQ_C * lde;        // [8][32] best score per entry group
+  int* bi = reinterpret_cast<int*>(bs + 8 * RQ_F);  // [8][32] its index
+  int* pick = bi + 8 * RQ_F;         // [32]
+  const int tid = threadIdx.x, f = tid & 31, cg = tid >> 5;
+  const int n = blockIdx.y, t0 = blockIdx.x * RQ_F;
+  for (int i = tid; i < D * RQ_F; i += 256) {
+    const int d = i >> 5, ff = i & 31;
+    R[i] = (t0 + ff < P.T) ? P.emb[((size_t)n * D + d) * P.T + t0 + ff] : 0.f;
+    Q[i] = 0.f;
+  }
+  __syncthreads();
+  for (int q = 0; q < P.nq; ++q) {
+    const float* cb = P.codebooks + (size_t)q * P.K * D;
+    float best = -3.4e38f;
+    int besti = 0;
+    for (int c0 = 0; c0 < P.K; c0 += RQ_C) {
+      for (int i = tid; i < RQ_C * D; i += 256) {
+        const int c = i / D, d = i - c * D;
+        E[c * lde + d] = __ldg(cb + (size_t)(c0 + c) * D + d);
+      }
+      __syncthreads();
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      const float* e0 = E + (cg * 8) * lde;
+      for (int d = 0; d < D; ++d) {
+        const float r = R[d * RQ_F + f];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(r, e0[j * lde + d], acc[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int idx = c0 + cg * 8 + j;
+        const float sc = 2.0f * acc[j] - __ldg(P.enorm + (size_t)q * P.K + idx);
+        if (sc > best) {  // ascending index inside a thread: strict > keeps the first maximum
+          best = sc;
+          besti = idx;
+        }
+      }
+      __syncthreads();
+    }
+    bs[cg * RQ_F + f] = best;
+    bi[cg * RQ_F + f] = besti;
+    __syncthreads();
+    if (tid < RQ_F) {
+      float b = bs[tid];
+      int ix = bi[tid];
+      for (int g = 1; g < 8; ++g) {
+        const float s2 = bs[g * RQ_F + tid];
+        const int i2 = bi[g * RQ_F + tid];
+        if (s2 > b || (s2 == b && i2 < ix)) {
+          b = s2;
+          ix = i2;
+        }
+      }
+      pick[tid] = ix;
+      if (P.codes && t0 + tid < P.T) P.codes[((size_t)q * P.N + n) * P.T + t0 + tid] = ix;
+    }
+    __syncthreads();
+    {
+      const float* e = cb + (size_t)pick[f] * D;
+      for (int d = cg; d < D; d += 8) {
+        const float v = __ldg(e + d);
+        R[d * RQ_F + f] -= v;
+        Q[d * RQ_F + f] += v;
+      }
+    }
+    __syncthreads();
+  }
+  if (P.quant)
+    for (int i = tid; i < D * RQ_F; i += 256) {
+      const int d = i >> 5, ff = i & 31;
+      if (t0 + ff < P.T) P.quant[((size_t)n * D + d) * P.T + t0 + ff] = Q[i];
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ final GroupNorm
 // audio[b][c][l] = gamma[c] * (raw[b][l][c] - mean_b) * rstd_b + beta[c]   (GroupNorm(1, C) of the last conv, NCL fp32 out)
 __global__ void final_norm_kernel(const float* __restrict__ raw, const long long* __restrict__ stats, int FG,
@@ -501,7 +599,8 @@ int pick_cluster(int H) {
 }  // namespace
 
 // ================================================================================================== CodecDecoder
-CodecDecoder::CodecDecoder(const Jen1CodecDesc& d, int device, int strict) : d_(d), device_(device), strict_(strict != 0) {
+CodecDecoder::CodecDecoder(const Jen1CodecDesc& d, int device, int strict, bool encoder, int n_q, int codebook_size)
+    : d_(d), device_(device), encoder_(encoder), n_q_(n_q), K_(codebook_size), strict_(strict != 0) {
   const char* e = getenv("JEN1_LSTM");  // JEN1_LSTM=smem: the shared-memory-weights kernel (A/B partner of the tensor-core one)
   lstm_smem_kernel_ = e && strcmp(e, "smem") == 0;
   lstm_no_overlap_ = e && strcmp(e, "serial") == 0;  // JEN1_LSTM=serial: tensor-core kernel, layers one after the other
@@ -607,6 +706,9 @@ bool CodecDecoder::make_conv(const std::string& prefix, const char* conv, const 
 
 int CodecDecoder::finalize() {
   if (finalized_) return 0;
+  if (encoder_) {  // SEANetEncoder: model.0 conv, then (resblock, ELU, down conv) per ratio, LSTM, ELU, conv
+    lstm_prefix_ = "encoder.model." + std::to_string(3 * d_.n_ratios + 1) + ".lstm.";
+  }
   if (cudaSetDevice(device_) != cudaSuccess) return fail("no CUDA device " + std::to_string(device_) + " (this library has no CPU path)");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || device_ >= ndev) return fail("no CUDA device (this library has no CPU path)");
@@ -615,13 +717,37 @@ int CodecDecoder::finalize() {
   hop_ = 1;
   for (int i = 0; i < d_.n_ratios; ++i) hop_ *= d_.ratios[i];
   if (H_ % 16) return fail("hidden size must be a multiple of 16");
+  if (encoder_) return finalize_encoder();
   if (!make_conv("model.0", ".conv.conv", ".conv.norm", d_.dimension, H_, d_.kernel_size, false, &first_)) return 1;
+  if (load_lstm()) return 1;
+  // ---- upsampling stages
+  int idx = 2, c = H_;
+  for (int i = 0; i < d_.n_ratios; ++i) {
+    const int r = d_.ratios[i];
+    Stage S;
+    S.ratio = r;
+    const std::string pt = "model." + std::to_string(idx + 1), pr = "model." + std::to_string(idx + 2);
+    const int hid = (c / 2) / d_.compress;
+    if (!make_conv(pt, ".convtr.convtr", ".convtr.norm", c, c / 2, 2 * r, true, &S.up)) return 1;
+    if (!make_conv(pr + ".block.1", ".conv.conv", ".conv.norm", c / 2, hid, d_.residual_kernel_size, false, &S.res1)) return 1;
+    if (!make_conv(pr + ".block.3", ".conv.conv", ".conv.norm", hid, c / 2, 1, false, &S.res2)) return 1;
+    if (!make_conv(pr + ".shortcut", ".conv.conv", ".conv.norm", c / 2, c / 2, 1, false, &S.shortcut)) return 1;
+    stages_.push_back(S);
+    idx += 3;
+    c /= 2;
+  }
+  if (!make_conv("model." + std::to_string(idx + 1), ".conv.conv", ".conv.norm", c, d_.channels, d_.last_kernel_size, false, &last_))
+    return 1;
+  return finish_finalize();
+}
+
+int CodecDecoder::load_lstm() {
   // ---- LSTM
   CS_ = pick_cluster(H_);
   if (d_.lstm_layers > 0 && CS_ == 0) return fail("LSTM hidden size does not fit the cluster kernel");
   U_ = CS_ ? H_ / CS_ : 0;
   for (int l = 0; l < d_.lstm_layers; ++l) {
-    const std::string p = "model.1.lstm.";
+    const std::string p = lstm_prefix_;
     const std::string s = "_l" + std::to_string(l);
     const HostTensor* wih = get(p + "weight_ih" + s, {4 * H_, H_});
     const HostTensor* whh = get(p + "weight_hh" + s, {4 * H_, H_});
@@ -657,24 +783,10 @@ int CodecDecoder::finalize() {
     if (!L.wih || !L.bias) return 1;
     lstm_.push_back(L);
   }
-  // ---- upsampling stages
-  int idx = 2, c = H_;
-  for (int i = 0; i < d_.n_ratios; ++i) {
-    const int r = d_.ratios[i];
-    Stage S;
-    S.ratio = r;
-    const std::string pt = "model." + std::to_string(idx + 1), pr = "model." + std::to_string(idx + 2);
-    const int hid = (c / 2) / d_.compress;
-    if (!make_conv(pt, ".convtr.convtr", ".convtr.norm", c, c / 2, 2 * r, true, &S.up)) return 1;
-    if (!make_conv(pr + ".block.1", ".conv.conv", ".conv.norm", c / 2, hid, d_.residual_kernel_size, false, &S.res1)) return 1;
-    if (!make_conv(pr + ".block.3", ".conv.conv", ".conv.norm", hid, c / 2, 1, false, &S.res2)) return 1;
-    if (!make_conv(pr + ".shortcut", ".conv.conv", ".conv.norm", c / 2, c / 2, 1, false, &S.shortcut)) return 1;
-    stages_.push_back(S);
-    idx += 3;
-    c /= 2;
-  }
-  if (!make_conv("model." + std::to_string(idx + 1), ".conv.conv", ".conv.norm", c, d_.channels, d_.last_kernel_size, false, &last_))
-    return 1;
+  return 0;
+}
+
+int CodecDecoder::finish_finalize() {
   if (CS_ > 0) {
     const size_t smem = lstm_smem();
     if (!ck(cudaFuncSetAttribute(lstm_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "lstm smem attribute"))
@@ -692,6 +804,65 @@ int CodecDecoder::finalize() {
   host_.clear();
   finalized_ = true;
   return 0;
+}
+
+// SEANetEncoder + residual vector quantizer.  The audio input is padded from `channels` to 4 channels (zero weights) so
+// that the first conv takes the tensor-core path too.
+int CodecDecoder::finalize_encoder() {
+  if (n_q_ < 1 || n_q_ > 32 || K_ < 64 || K_ % 64) return fail("bad quantizer description");
+  cin0_ = (d_.channels + 3) / 4 * 4;
+  {  // first conv with zero-padded input channels
+    const std::string pfx = "encoder.model.0";
+    const HostTensor* w = get(pfx + ".conv.conv.weight", {d_.n_filters, d_.channels, d_.kernel_size});
+    if (!w) return 1;
+    HostTensor padded;
+    padded.shape = {d_.n_filters, cin0_, d_.kernel_size};
+    padded.data.assign((size_t)d_.n_filters * cin0_ * d_.kernel_size, 0.f);
+    for (int n = 0; n < d_.n_filters; ++n)
+      for (int c = 0; c < d_.channels; ++c)
+        for (int j = 0; j < d_.kernel_size; ++j)
+          padded.data[((size_t)n * cin0_ + c) * d_.kernel_size + j] = w->data[((size_t)n * d_.channels + c) * d_.kernel_size + j];
+    host_[pfx + ".conv.conv.weight"] = padded;
+    if (!make_conv(pfx, ".conv.conv", ".conv.norm", cin0_, d_.n_filters, d_.kernel_size, false, &first_)) return 1;
+  }
+  int idx = 0, c = d_.n_filters;
+  for (int i = d_.n_ratios - 1; i >= 0; --i) {  // reversed decoder ratios
+    const int r = d_.ratios[i];
+    Stage S;
+    S.ratio = r;
+    const std::string pr = "encoder.model." + std::to_string(idx + 1), pd = "encoder.model." + std::to_string(idx + 3);
+    const int hid = c / d_.compress;
+    if (!make_conv(pr + ".block.1", ".conv.conv", ".conv.norm", c, hid, d_.residual_kernel_size, false, &S.res1)) return 1;
+    if (!make_conv(pr + ".block.3", ".conv.conv", ".conv.norm", hid, c, 1, false, &S.res2)) return 1;
+    if (!make_conv(pr + ".shortcut", ".conv.conv", ".conv.norm", c, c, 1, false, &S.shortcut)) return 1;
+    if (!make_conv(pd, ".conv.conv", ".conv.norm", c, 2 * c, 2 * r, false, &S.up)) return 1;
+    stages_.push_back(S);
+    idx += 3;
+    c *= 2;
+  }
+  if (c != H_) return fail("encoder channel bookkeeping");
+  if (load_lstm()) return 1;
+  if (!make_conv("encoder.model." + std::to_string(idx + 3), ".conv.conv", ".conv.norm", H_, d_.dimension, d_.last_kernel_size, false,
+                 &last_))
+    return 1;
+  std::vector<float> cb((size_t)n_q_ * K_ * d_.dimension), en((size_t)n_q_ * K_);
+  for (int q = 0; q < n_q_; ++q) {
+    const HostTensor* e = get("quantizer.vq.layers." + std::to_string(q) + "._codebook.embed", {K_, d_.dimension});
+    if (!e) return 1;
+    for (int j = 0; j < K_; ++j) {
+      double n2 = 0.0;
+      for (int dd = 0; dd < d_.dimension; ++dd) {
+        const float v = e->data[(size_t)j * d_.dimension + dd];
+        cb[((size_t)q * K_ + j) * d_.dimension + dd] = v;
+        n2 += (double)v * v;
+      }
+      en[(size_t)q * K_ + j] = (float)n2;
+    }
+  }
+  codebooks_ = upload(cb);
+  enorm_ = upload(en);
+  if (!codebooks_ || !enorm_) return 1;
+  return finish_finalize();
 }
 
 size_t CodecDecoder::lstm_smem() const {
@@ -748,11 +919,13 @@ cudaError_t CodecDecoder::launch_conv(const ConvParams& p, cudaStream_t st) {
 }
 
 CodecDecoder::Act CodecDecoder::conv(const Act& in, const Act* in2, int act, const ConvW& W, int pad_left, bool reflect,
-                                     bool want_stats, cudaStream_t st) {
+                                     bool want_stats, cudaStream_t st, int stride) {
+  // stride > 1 (encoder down convs): ceil(L / stride) frames; the padding on the right grows by what completes the last
+  // frame (encodec get_extra_padding_for_conv1d) -- with reflect index mapping that needs no special case
   Act o;
   o.C = W.cout;
-  o.L = in.L;
-  o.Lstore = in.L;
+  o.L = (in.L + stride - 1) / stride;
+  o.Lstore = o.L;
   o.row0 = 0;
   const int fgo = W.cout >= 64 ? W.cout / 64 : 1;
   const int slots = 32 / fgo > 1 ? 32 / fgo : 1;  // spread the statistics atomics of the long layers (<= 32 entries)
@@ -769,17 +942,18 @@ CodecDecoder::Act CodecDecoder::conv(const Act& in, const Act* in2, int act, con
   S.w = W.w;
   S.wT = W.wT;
   S.ntaps = W.k;
-  S.in_stride = 1;
+  S.in_stride = stride;
   S.shift0 = -pad_left;
   S.shift_step = 1;
   S.wtap0 = 0;
   S.wtap_phase = 0;
   S.wtap_step = 1;
   p.pad_mode = reflect ? PAD_REFLECT : PAD_ZERO;
-  const int max_pad = pad_left > (W.k - 1 - pad_left) ? pad_left : (W.k - 1 - pad_left);
+  const int pad_right = (o.L - 1) * stride + W.k - pad_left - in.L;  // includes the extra padding of strided convs
+  const int max_pad = pad_left > pad_right ? pad_left : pad_right;
   p.Lext = (reflect && in.L <= max_pad) ? max_pad + 1 : 0;  // encodec pad1d: zero-extend a too-short signal first
   p.B = B_;
-  p.Lm = in.L;
+  p.Lm = o.L;
   p.nphase = 1;
   p.out_stride = 1;
   p.Lout = o.Lstore;
@@ -1091,7 +1265,100 @@ void CodecDecoder::walk(const float* latent, float* audio, int B, int T, cudaStr
   }
 }
 
+// ---- encoder walk: audio [N][channels][L] -> raw last conv (+ statistics) -> normalised latent (NCL) -> residual VQ
+void CodecDecoder::walk_encoder(const float* audio, float* latent, int32_t* codes, float* quantized, int N, int L, cudaStream_t st) {
+  B_ = N;
+  Act x;
+  x.C = cin0_;
+  x.L = x.Lstore = L;
+  x.ptr = falloc((size_t)N * L * x.C);
+  if (!dry_) {
+    if (!ck(launch_pack_ncl<float>(audio, x.ptr, nullptr, N, d_.channels, cin0_, L, st), "codec pack")) ok_ = false;
+    ++launches_;
+  }
+  const int k0 = d_.kernel_size;
+  Act v = conv(x, nullptr, ACT_NONE, first_, (k0 - 1) - (k0 - 1) / 2, true, true, st);
+  for (const Stage& S : stages_) {
+    const int kr = S.res1.k, r = S.ratio;
+    Act r1 = conv(v, nullptr, ACT_ELU, S.res1, (kr - 1) - (kr - 1) / 2, true, true, st);
+    Act r2 = conv(r1, nullptr, ACT_ELU, S.res2, 0, true, true, st);
+    Act sc = conv(v, nullptr, ACT_NONE, S.shortcut, 0, true, true, st);
+    // ELU(shortcut + block) -> strided conv k = 2r: padding total r, right r/2 (+ extra), left r - r/2
+    v = conv(sc, &r2, ACT_ELU, S.up, r - r / 2, true, true, st, r);
+  }
+  Act a = v, a2;
+  bool two = false;
+  if (!lstm_.empty()) {
+    a2 = lstm_stack(v, N, v.L, st);
+    two = true;
+  }
+  const int kl = d_.last_kernel_size;
+  Act fin = conv(a, two ? &a2 : nullptr, ACT_ELU, last_, (kl - 1) - (kl - 1) / 2, true, true, st);
+  if (!dry_) {
+    dim3 grid((unsigned)std::min<long long>(((long long)fin.L + 255) / 256, 4096), (unsigned)N);
+    final_norm_kernel<<<grid, 256, 0, st>>>(fin.ptr, fin.stats, fin.FG, fin.gamma, fin.beta, d_.eps, fin.C, fin.L, latent);
+    if (!ck(cudaGetLastError(), "final norm launch")) ok_ = false;
+    ++launches_;
+    if ((codes || quantized) && quantize(latent, codes, quantized, N, fin.L, st)) ok_ = false;
+  }
+}
+
+int CodecDecoder::quantize(const float* latent, int32_t* codes, float* quantized, int N, int T, cudaStream_t st) {
+  if (!finalized_ || !encoder_) return fail("quantize needs a finalized encoder engine");
+  if (!latent || N < 1 || T < 1) return fail("quantize: bad arguments");
+  cudaSetDevice(device_);
+  RvqParams P;
+  P.emb = latent;
+  P.codebooks = codebooks_;
+  P.enorm = enorm_;
+  P.quant = quantized;
+  P.codes = codes;
+  P.N = N;
+  P.T = T;
+  P.D = d_.dimension;
+  P.K = K_;
+  P.nq = n_q_;
+  const size_t smem = ((size_t)2 * P.D * RQ_F + (size_t)RQ_C * (P.D + 1) + 8 * RQ_F) * sizeof(float) + (8 * RQ_F + RQ_F) * sizeof(int);
+  cudaFuncSetAttribute(rvq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  dim3 g2((unsigned)((T + RQ_F - 1) / RQ_F), (unsigned)N);
+  rvq_kernel<<<g2, 256, smem, st>>>(P);
+  ++launches_;
+  return ck(cudaGetLastError(), "rvq launch") ? 0 : 1;
+}
+
+size_t CodecDecoder::encode_workspace_bytes(int N, int L) {
+  dry_ = true;
+  off_ = 0;
+  soff_ = 0;
+  walk_encoder(nullptr, nullptr, nullptr, nullptr, N, L, nullptr);
+  dry_ = false;
+  stats_bytes_need_ = soff_;
+  return off_ + soff_ + 4096;
+}
+
+int CodecDecoder::encode(const float* audio, float* latent, int32_t* codes, float* quantized, int N, int L, cudaStream_t st) {
+  if (!finalized_ || !encoder_) return fail("encode needs a finalized encoder engine");
+  if (!audio || !latent || N < 1 || L < 1) return fail("encode: bad arguments");
+  cudaSetDevice(device_);
+  const size_t need = encode_workspace_bytes(N, L);
+  if (need > arena_bytes_) {
+    if (arena_) cudaFree(arena_);
+    arena_ = nullptr;
+    arena_bytes_ = 0;
+    if (!ck(cudaMalloc((void**)&arena_, need), "cudaMalloc(codec workspace)")) return 1;
+    arena_bytes_ = need;
+  }
+  ok_ = true;
+  off_ = 0;
+  const size_t act_bytes = arena_bytes_ - stats_bytes_need_ - 2048;
+  soff_ = act_bytes & ~(size_t)255;
+  if (!ck(cudaMemsetAsync(arena_ + soff_, 0, stats_bytes_need_, st), "codec statistics memset")) return 1;
+  walk_encoder(audio, latent, codes, quantized, N, L, st);
+  return ok_ ? 0 : 1;
+}
+
 int CodecDecoder::decode(const float* latent, float* audio, int B, int T, cudaStream_t st) {
+  if (encoder_) return fail("decode called on an encoder engine");
   if (!finalized_) return fail("decode before finalize");
   if (!latent || !audio || B < 1 || T < 1) return fail("decode: bad arguments");
   cudaSetDevice(device_);

@@ -15,7 +15,8 @@ namespace jen1 {
 
 class CodecDecoder {
  public:
-  CodecDecoder(const Jen1CodecDesc& d, int device, int strict);
+  // encoder = false: SEANetDecoder (latent -> audio); true: SEANetEncoder + residual vector quantizer (audio -> latent)
+  CodecDecoder(const Jen1CodecDesc& d, int device, int strict, bool encoder = false, int n_q = 0, int codebook_size = 0);
   ~CodecDecoder();
 
   int load_tensor(const char* name, const float* data, const int64_t* shape, int ndim);
@@ -23,6 +24,12 @@ class CodecDecoder {
   size_t workspace_bytes(int B, int T);
   int reserve(int B, int T);
   int decode(const float* latent, float* audio, int B, int T, cudaStream_t st);
+  // audio [N][channels][L] -> latent [N][dimension][T] (continuous), codes [n_q][N][T] (or null), quantized [N][dimension][T]
+  // (or null); T = ceil(L / hop)
+  int encode(const float* audio, float* latent, int32_t* codes, float* quantized, int N, int L, cudaStream_t st);
+  size_t encode_workspace_bytes(int N, int L);
+  int quantize(const float* latent, int32_t* codes, float* quantized, int N, int T, cudaStream_t st);
+  bool is_encoder() const { return encoder_; }
 
   const char* last_error() const { return err_.c_str(); }
   int64_t launch_count() const { return launches_; }
@@ -54,7 +61,7 @@ class CodecDecoder {
   };
   struct Stage {
     int ratio = 1;
-    ConvW up, res1, res2, shortcut;
+    ConvW up, res1, res2, shortcut;  // encoder: `up` is the strided down conv that follows the resblock
   };
   // an activation: raw values + (optionally) the statistics / affine of the GroupNorm its consumers must apply
   struct Act {
@@ -76,7 +83,12 @@ class CodecDecoder {
   long long* salloc(int B, int FG);
   void fill_src(ConvParams& p, const Act& in, const Act* in2, int act);
   cudaError_t launch_conv(const ConvParams& p, cudaStream_t st);
-  Act conv(const Act& in, const Act* in2, int act, const ConvW& W, int pad_left, bool reflect, bool want_stats, cudaStream_t st);
+  Act conv(const Act& in, const Act* in2, int act, const ConvW& W, int pad_left, bool reflect, bool want_stats, cudaStream_t st,
+           int stride = 1);
+  void walk_encoder(const float* audio, float* latent, int32_t* codes, float* quantized, int N, int L, cudaStream_t st);
+  int finalize_encoder();
+  int load_lstm();
+  int finish_finalize();
   Act convtr(const Act& in, const Act* in2, int act, const ConvW& W, int r, cudaStream_t st);
   Act last_conv(const Act& in, const Act* in2, const ConvW& W, int pad_left, cudaStream_t st);
   void walk(const float* latent, float* audio, int B, int T, cudaStream_t st);
@@ -87,8 +99,13 @@ class CodecDecoder {
 
   Jen1CodecDesc d_;
   int device_;
+  bool encoder_ = false;
+  int n_q_ = 0, K_ = 0, cin0_ = 0;      // quantizer stages, codebook size, padded channel count of the audio input
+  const float* codebooks_ = nullptr;   // [n_q][K][dimension]
+  const float* enorm_ = nullptr;       // [n_q][K] squared norms
   bool finalized_ = false, dry_ = false, ok_ = true, strict_ = false;
   std::string err_;
+  std::string lstm_prefix_ = "model.1.lstm.";
   std::map<std::string, HostTensor> host_;
   std::vector<void*> owned_;
   ConvW first_, last_;

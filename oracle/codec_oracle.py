@@ -104,3 +104,63 @@ def decoder_forward(desc, sd, z, taps=None):
         if taps is not None:
             taps[p] = x
     return x
+
+
+# ------------------------------------------------------------------------------------------------ encoder + RVQ
+def sconv1d_strided(sd, p, x, stride, eps):
+    """SConv1d with stride (encodec/modules/conv.py): reflect pad left = total - total//2, right = total//2 + the extra
+    padding that makes the last frame complete (get_extra_padding_for_conv1d); conv; GroupNorm(1)."""
+    import math
+    w = sd[p + ".conv.conv.weight"]
+    k = w.shape[-1]
+    total = k - stride
+    length = x.shape[-1]
+    n_frames = math.ceil((length - k + total) / stride + 1) - 1
+    extra = n_frames * stride + k - total - length
+    right = total // 2
+    left = total - right
+    y = F.conv1d(_pad_reflect(x, left, right + extra), w, sd[p + ".conv.conv.bias"], stride=stride)
+    return _gn1(y, sd[p + ".conv.norm.weight"], sd[p + ".conv.norm.bias"], eps)
+
+
+def encoder_forward(desc, sd, audio, taps=None):
+    """audio [N, channels, L] -> latent [N, dimension, ceil(L / hop)] (SEANetEncoder; tensors named encoder.model.N...)."""
+    from jen1_b200.codec_config import encoder_layers
+    eps = desc.eps
+    x = audio
+    for idx, kind, cin, cout, k, stride in encoder_layers(desc):
+        p = "encoder.model.%d" % idx
+        if kind == "conv":
+            x = sconv1d(sd, p, F.elu(x) if idx > 0 else x, eps)
+        elif kind == "res":
+            x = resblock(sd, p, x, eps)
+        elif kind == "down":
+            x = sconv1d_strided(sd, p, F.elu(x), stride, eps)
+        else:
+            x = slstm(sd, p, x, desc.lstm_layers)
+        if taps is not None:
+            taps[p] = x
+    return x
+
+
+def rvq_encode(sd, emb, n_q):
+    """ResidualVectorQuantizer.encode (encodec/quantization/core_vq.py): per stage the nearest codebook entry of the
+    residual (euclidean; first index on ties), residual -= entry.  emb [N, D, T] -> codes [n_q, N, T]."""
+    residual = emb.permute(0, 2, 1)
+    codes = []
+    for i in range(n_q):
+        e = sd["quantizer.vq.layers.%d._codebook.embed" % i]
+        flat = residual.reshape(-1, e.shape[1])
+        dist = -(flat.pow(2).sum(1, keepdim=True) - 2 * flat @ e.t() + e.pow(2).sum(1)[None])
+        ind = dist.max(dim=-1).indices.view(residual.shape[:-1])
+        residual = residual - F.embedding(ind, e)
+        codes.append(ind)
+    return torch.stack(codes)
+
+
+def rvq_decode(sd, codes):
+    """ResidualVectorQuantizer.decode: sum of the selected entries -> [N, D, T] (what reference generation.py:149 returns)."""
+    out = 0.0
+    for i, ind in enumerate(codes):
+        out = out + F.embedding(ind, sd["quantizer.vq.layers.%d._codebook.embed" % i])
+    return out.permute(0, 2, 1)

@@ -139,10 +139,53 @@ def make_codec_golden():
     print("  %-28s %8.1f KB" % ("codec_decoder.pt", os.path.getsize(os.path.join(GOLD, "codec_decoder.pt")) / 1024))
 
 
+def make_codec_encoder_golden():
+    """Encodec-48k ENCODER + residual vector quantizer: Hugging Face port (EncodecEncoder, EncodecResidualVectorQuantizer),
+    seeded weights / codebooks regenerated from the seed by jen1_b200.codec_config.random_encoder_state_dict."""
+    from transformers import EncodecConfig
+    from transformers.models.encodec.modeling_encodec import EncodecEncoder, EncodecResidualVectorQuantizer
+    from jen1_b200.codec_config import CodecDesc, random_encoder_state_dict
+    desc = CodecDesc()
+    cfg = EncodecConfig(sampling_rate=48000, audio_channels=desc.channels, normalize=True, chunk_length_s=1.0, overlap=0.01,
+                        hidden_size=desc.dimension, num_filters=desc.n_filters, num_residual_layers=1,
+                        upsampling_ratios=list(desc.ratios), norm_type="time_group_norm", kernel_size=desc.kernel_size,
+                        last_kernel_size=desc.last_kernel_size, residual_kernel_size=desc.residual_kernel_size,
+                        dilation_growth_rate=2, use_causal_conv=False, pad_mode="reflect", compress=desc.compress,
+                        num_lstm_layers=desc.lstm_layers, trim_right_ratio=1.0, use_conv_shortcut=True,
+                        target_bandwidths=[3.0, 6.0, 12.0, 24.0], codebook_size=1024)
+    enc = EncodecEncoder(cfg).eval()
+    rvq = EncodecResidualVectorQuantizer(cfg).eval()
+    assert rvq.num_quantizers == 16
+    sd = random_encoder_state_dict(desc, 21)
+    hf = {}
+    for k, v in sd.items():
+        if k.startswith("encoder."):
+            n = k[len("encoder."):].replace("model.", "layers.", 1).replace(".conv.conv.", ".conv.").replace(".conv.norm.", ".norm.")
+            hf[n] = v
+    enc.load_state_dict(hf, strict=True)
+    for i in range(16):
+        rvq.layers[i].codebook.embed.copy_(sd["quantizer.vq.layers.%d._codebook.embed" % i])
+    cases = {}
+    for name, N, L, seed in (("n2_l6400", 2, 6400, 5), ("n1_l5000", 1, 5000, 6), ("n3_l963", 3, 963, 7)):
+        g = torch.Generator().manual_seed(seed)
+        a = torch.randn(N, desc.channels, L, generator=g) * 0.5
+        with torch.no_grad():
+            emb = enc(a)
+            codes = rvq.encode(emb)          # [n_q, N, T]
+            q = rvq.decode(codes)            # [N, D, T]
+        cases[name] = dict(audio=a, emb=emb.clone(), codes=codes.clone().to(torch.int32), quantized=q.clone())
+        print("  encoder %-9s emb %s codes %s |emb| max %.3f" % (name, tuple(emb.shape), tuple(codes.shape), emb.abs().max().item()))
+    torch.save(dict(weight_seed=21, cases=cases), os.path.join(GOLD, "codec_encoder.pt"))
+    print("  %-28s %8.1f KB" % ("codec_encoder.pt", os.path.getsize(os.path.join(GOLD, "codec_encoder.pt")) / 1024))
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     if len(sys.argv) > 1 and sys.argv[1] == "codec":
         make_codec_golden()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "codec_encoder":
+        make_codec_encoder_golden()
         return
     ref_import.install_shims()
     if len(sys.argv) > 1 and sys.argv[1] == "c2":
