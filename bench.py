@@ -515,6 +515,39 @@ def codec_decode_leg(B, T, dev, cpu=True):
     return leg
 
 
+def codec_encode_leg(B, T, dev):
+    """The encode side of the codec (reference generation.py:145-150, used by the inpaint / continuation tasks): B clips of
+    T/150 s -> quantised latents through EncodecCodec.encode_latent (segmentation + normalisation on the host side in torch,
+    encoder + residual vector quantizer on the engine)."""
+    import torch
+    from jen1_b200.codec import EncodecCodec
+    from jen1_b200.codec_config import CodecDesc, random_encoder_state_dict, random_state_dict as codec_sd
+    cdesc = CodecDesc()
+    sd = dict(codec_sd(cdesc, 11))
+    sd.update(random_encoder_state_dict(cdesc, 21))
+    codec = EncodecCodec(sd, cdesc, dev)
+    seconds = T / 151.5
+    L = int(round(seconds * 48000))
+    audio = (torch.randn(B, 2, L, generator=torch.Generator().manual_seed(5)) * 0.3).to(dev)
+    for _ in range(2):
+        lat = codec.encode_latent(audio)
+    torch.cuda.synchronize(dev)
+    each = []
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        lat = codec.encode_latent(audio)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        each.append(e0.elapsed_time(e1))
+    each.sort()
+    assert tuple(lat.shape) == (B, 128, T) and bool(torch.isfinite(lat).all())
+    return {"ms_per_encode": each[len(each) // 2], "ms_per_encode_min_max": [each[0], each[-1]], "audio_seconds": B * seconds,
+            "segments": B * len(range(0, L, codec.stride)),
+            "what": "EncodecCodec.encode_latent(audio [%d,2,%d]) -> quantised latent [%d,128,%d]: 1 s segments (1 %% overlap, "
+                    "loudness-normalised) batched through the encoder engine, 16-stage residual VQ; device-timed" % (B, L, B, T)}
+
+
 def generate_audio_leg(desc, sd, B, T, steps, dev, dtype):
     """The reference's public entry point end to end (generation.py:76-132): Jen1.generate(prompts, steps, seconds) ->
     audio on the host.  Conditioner (seeded random text embeddings: T5 weights are unreachable offline), sampling loop on
@@ -657,6 +690,7 @@ def run_ours(args, wl, scaling):
 
     if world == 1 and not args.quick:
         extra["codec_decode"] = codec_decode_leg(B, T, dev, cpu=not args.no_cpu_baseline)
+        extra["codec_encode"] = codec_encode_leg(B, T, dev)
         if args.workload != "config5":
             extra["generate_audio"] = generate_audio_leg(desc, sd, B, T, K, dev, args.dtype)
 

@@ -17,6 +17,7 @@
  *   GaussianDiffusion.ddim_sample loop body                           | jen1_sample_begin / jen1_sample_step
  *                                       jen1/diffusion/gdm/gdm.py:202-222 |
  *   self.audio_encoder.decoder(sample_embs)        generation.py:130  | jen1_codec_create / _load_tensor / _decode
+ *   get_emb: audio_encoder.encode + quantizer.decode  generation.py:145-150 | jen1_codec_create_encoder / _encode
  *
  * Conventions: every function returns 0 on success or a non-zero code; the message is available from
  * jen1_last_error(handle).  Nothing throws or aborts across the ABI.  A handle is bound to one CUDA device and

@@ -100,6 +100,13 @@ def main():
                 assert torch.isfinite(out).all()
                 print("codec H=%d %s ok, launches %d (tf32 gemm %d, tensor-core lstm %d)"
                       % (desc.hidden, prec, dec.launch_count(), dec.tf32_launch_count(), dec.lstm_tc_launch_count()))
+        from jen1_b200.codec import EncodecEncoder
+        from jen1_b200.codec_config import random_encoder_state_dict
+        enc = EncodecEncoder(CodecDesc(), DEV, "tf32").load_state_dict(random_encoder_state_dict(CodecDesc(), 2))
+        lat, codes, qz = enc.encode(torch.randn(2, 2, 2000, generator=torch.Generator().manual_seed(3)).to(DEV))
+        torch.cuda.synchronize()
+        assert torch.isfinite(lat).all() and torch.isfinite(qz).all() and int(codes.max()) < 1024
+        print("codec encoder + RVQ ok, launches %d" % enc.launch_count())
     else:
         raise SystemExit("unknown mode " + mode)
 
