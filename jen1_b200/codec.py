@@ -187,10 +187,11 @@ class EncodecEncoder:
 
 
 class EncodecCodec:
-    """The `codec` object `jen1_b200.generation.Jen1` expects, with the decode side on the B200 engine:
-    `decode_latent(latent) -> [B, channels, samples]` (reference generation.py:130).  The encoder side
-    (`encode_latent`, reference generation.py:145-150: Encodec encoder + RVQ encode/decode) is not built -- prompts that
-    need it pass `init_latent=` instead."""
+    """The `codec` object `jen1_b200.generation.Jen1` expects, both sides on the B200 engine:
+    `decode_latent(latent) -> [B, channels, samples]` (reference generation.py:130) and `encode_latent(audio) ->
+    [B, dimension, T]` (reference generation.py:145-150: EncodecModel.encode segment by segment, then quantizer.decode).
+    The encode side needs the full Encodec state_dict (`encoder.*`, `quantizer.*`); with a decoder-only state_dict prompts
+    that need audio input pass `init_latent=` instead."""
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], desc: Optional[CodecDesc] = None, device="cuda:0",
                  precision: str = "tf32", sample_rate: int = 48000, segment_s: float = 1.0, overlap: float = 0.01,

@@ -1,4 +1,6 @@
-// Encodec (SEANet) decoder: latent [B][128][T] -> audio [B][2][T*hop]  (SURVEY.md section 8 row f1).
+// Encodec (SEANet) codec engine: decoder, latent [B][128][T] -> audio [B][2][T*hop], and
+// encoder + residual vector quantizer, audio segments [N][2][L] -> latent [N][128][ceil(L/hop)] -> codes / quantised latent
+// (reference generation.py:145-150).  The encoder is the mirror walk over the same helpers (walk_encoder).
 //
 // Reference: generation.py:130 `self.audio_encoder.decoder(sample_embs)` with the 48 kHz model of pip encodec==0.1.1
 // (generation.py:34; the package is not vendored -- the algorithm restated here is encodec/modules/seanet.py

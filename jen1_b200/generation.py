@@ -13,8 +13,9 @@ each deviation is listed in DESIGN.md:
   * per-sample masks / latents keep their batch dimension (generation.py:173-180 drops it);
   * Encodec (pip `encodec`, not installed, weights unreachable) is an injectable `codec` object with
     `encode_latent(audio)->[B,128,T]`, `decode_latent(latent)->[B,2,samples]`; `codec_state_dict=` (the Encodec model's
-    or its decoder's state_dict) builds the B200 decoder engine (jen1_b200/codec.py) for the decode side; without either
-    the facade works in the latent domain (`init_latent=` in, latents out).
+    state_dict, or only its decoder's) builds the B200 codec engines (jen1_b200/codec.py: decoder, and encoder + residual
+    vector quantizer when the encoder's tensors are present); without either the facade works in the latent domain
+    (`init_latent=` in, latents out).
 """
 from __future__ import annotations
 
