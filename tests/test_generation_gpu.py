@@ -90,3 +90,28 @@ def test_generate_decodes_through_the_codec_engine():
     lat = jen.generate(["a", "b"], seed=3, steps=10, batch_size=B, seconds=secs, use_gdm=True, return_latents=True)
     assert audio.shape == (B, 2, T * cdesc.hop) and torch.isfinite(audio).all()
     assert torch.equal(audio, codec.decode_latent(lat))
+
+
+def test_continuation_from_audio_goes_through_the_encoder_engine():
+    """generate(task='music_cont', init_audio=...) with a full Encodec state_dict: prompt audio -> Encodec encoder + residual
+    vector quantizer engine (reference generation.py:95,145-150) -> causal sampling -> decoder engine -> audio."""
+    from jen1_b200.codec_config import CodecDesc, random_encoder_state_dict, random_state_dict as codec_sd
+    from jen1_b200.config import UNetDesc
+    from jen1_b200.generation import Jen1
+    desc = UNetDesc(in_channels=128, channels=32, multipliers=(1, 1, 2, 2, 4), factors=(1, 4, 2, 2), num_blocks=(1, 2, 2, 1),
+                    attentions=(0, 0, 1, 1), out_channels=128, context_channels=(129,), context_embedding_features=64,
+                    context_embedding_max_length=12, attention_heads=4)
+    cdesc = CodecDesc()
+    csd = dict(codec_sd(cdesc, 11))
+    csd.update(random_encoder_state_dict(cdesc, 21))
+    jen = Jen1(None, device=DEV, desc=desc, state_dict=random_state_dict(desc, 3), dtype="fp32", codec_state_dict=csd)
+    assert jen.codec.encoder is not None
+    prompt_audio = torch.randn(2, 48000, generator=torch.Generator().manual_seed(1)) * 0.2  # 1 s of stereo
+    n0 = jen.codec.encoder.launch_count()
+    audio = jen.generate("x", seed=5, steps=5, batch_size=1, seconds=2, use_gdm=True, task="music_cont",
+                         init_audio=prompt_audio, init_audio_sr=48000)
+    assert jen.codec.encoder.launch_count() > n0
+    T = latent_frames(2)
+    assert audio.shape == (1, 2, T * 320) and torch.isfinite(audio).all()
+    lat = jen.codec.encode_latent(prompt_audio.unsqueeze(0))
+    assert lat.shape == (1, 128, latent_frames(1))  # 150 frames + 2 of the 1 % overlap segment (reference segment loop)
