@@ -164,6 +164,18 @@ class EncodecEncoder:
     def launch_count(self) -> int:
         return int(self._lib.jen1_codec_launch_count(self._h))
 
+    def quantize(self, latent: torch.Tensor):
+        """Residual vector quantizer alone: latent [N, dimension, T] -> (codes [n_q, N, T] int32, quantized [N, dimension, T])."""
+        z = latent.detach().to(self.device, torch.float32).contiguous()
+        N, _, T = z.shape
+        codes = torch.empty(self.n_q, N, T, device=self.device, dtype=torch.int32)
+        qz = torch.empty_like(z)
+        with torch.cuda.device(self.device):
+            st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+            self._check(self._lib.jen1_codec_quantize(self._h, C.c_void_p(z.data_ptr()), C.c_void_p(codes.data_ptr()),
+                                                      C.c_void_p(qz.data_ptr()), int(N), int(T), st), "jen1_codec_quantize")
+        return codes, qz
+
     def encode(self, audio: torch.Tensor, quantize: bool = True):
         """audio [N, channels, L] -> (latent [N, dimension, T], codes [n_q, N, T] int32, quantized [N, dimension, T]);
         `quantize=False` skips the vector quantizer and returns (latent, None, None)."""
@@ -235,7 +247,8 @@ class EncodecCodec:
             i = j
         for i, j in groups:
             batch = torch.cat(full[i:j], dim=0)  # [(j - i) * B, C, Lseg], segment-major
-            _, _, qz = self.encoder.encode(batch)
-            qz = qz.view(j - i, B, qz.shape[1], qz.shape[2])
-            outs.extend(qz[s] for s in range(j - i))
-        return torch.cat(outs, dim=2)
+            lat, _, _ = self.encoder.encode(batch, quantize=False)
+            lat = lat.view(j - i, B, lat.shape[1], lat.shape[2])
+            outs.extend(lat[s] for s in range(j - i))
+        # the quantizer works frame by frame: one pass over the concatenated latents of all segments
+        return self.encoder.quantize(torch.cat(outs, dim=2))[1]

@@ -347,9 +347,8 @@ size_t lstm_tc_smem(int H, int U) {
 // ------------------------------------------------------------------------------------------------ residual VQ
 // ResidualVectorQuantizer.encode + decode (encodec/quantization/core_vq.py; reference generation.py:146-149): per stage the
 // nearest codebook entry of the residual (euclidean: argmax of 2 r.e - |e|^2, lowest index on ties), residual -= entry,
-// quantized += entry.  fp32 throughout (an argmax does not forgive rounded operands).  One CTA = 32 frames of one row:
-// residual and running sum live in shared memory [dim][frame]; the codebook streams through in 64-entry chunks; thread
-// (frame, group of 8 entries) keeps 8 dot products.
+// quantized += entry.  fp32 throughout (an argmax does not forgive rounded operands).  One CTA = 64 frames of one row:
+// residual and running sum live in shared memory [dim][frame]; the codebook streams through in 64-entry chunks.
 struct RvqParams {
   const float* emb;        // [N][D][T]
   const float* codebooks;  // [nq][K][D]
@@ -358,62 +357,78 @@ struct RvqParams {
   int32_t* codes;          // [nq][N][T] or nullptr
   int N, T, D, K, nq;
 };
-constexpr int RQ_F = 32, RQ_C = 64;
+constexpr int RQ_F = 64, RQ_C = 64;  // frames per CTA, codebook entries per chunk
 
+// 256 threads = 16 frame groups (4 frames) x 16 entry groups (4 entries): a 4 x 4 register tile per thread, one 16-byte
+// load of residuals + 4 scalar loads of entries per 16 FMAs.
 __global__ void __launch_bounds__(256) rvq_kernel(const RvqParams P) {
-  extern __shared__ float rsm[];
-  const int D = P.D, lde = D + 1;
-  float* R = rsm;                    // [D][32] residual
-  float* Q = R + D * RQ_F;           // [D][32] quantized
-  float* E = Q + D * RQ_F;           // [64][D + 1] codebook chunk
-  float* bs = E + RQ_C * lde;        // [8][32] best score per entry group
-  int* bi = reinterpret_cast<int*>(bs + 8 * RQ_F);  // [8][32] its index
-  int* pick = bi + 8 * RQ_F;         // [32]
-  const int tid = threadIdx.x, f = tid & 31, cg = tid >> 5;
+  extern __shared__ __align__(16) float rsm[];
+  const int D = P.D;
+  constexpr int lde = RQ_C + 1;
+  float* R = rsm;                    // [D][64] residual
+  float* Q = R + D * RQ_F;           // [D][64] quantized
+  float* E = Q + D * RQ_F;           // [D][65] codebook chunk, transposed
+  float* bs = E + D * lde;           // [16][64] best score per entry group
+  int* bi = reinterpret_cast<int*>(bs + 16 * RQ_F);  // [16][64] its index
+  int* pick = bi + 16 * RQ_F;        // [64]
+  const int tid = threadIdx.x, tf = tid & 15, tc = tid >> 4;
   const int n = blockIdx.y, t0 = blockIdx.x * RQ_F;
   for (int i = tid; i < D * RQ_F; i += 256) {
-    const int d = i >> 5, ff = i & 31;
+    const int d = i >> 6, ff = i & 63;
     R[i] = (t0 + ff < P.T) ? P.emb[((size_t)n * D + d) * P.T + t0 + ff] : 0.f;
     Q[i] = 0.f;
   }
   __syncthreads();
   for (int q = 0; q < P.nq; ++q) {
     const float* cb = P.codebooks + (size_t)q * P.K * D;
-    float best = -3.4e38f;
-    int besti = 0;
+    float best[4] = {-3.4e38f, -3.4e38f, -3.4e38f, -3.4e38f};
+    int besti[4] = {0, 0, 0, 0};
     for (int c0 = 0; c0 < P.K; c0 += RQ_C) {
-      for (int i = tid; i < RQ_C * D; i += 256) {
+      for (int i = tid; i < RQ_C * D; i += 256) {  // coalesced along the entry's dimensions, stored transposed
         const int c = i / D, d = i - c * D;
-        E[c * lde + d] = __ldg(cb + (size_t)(c0 + c) * D + d);
+        E[d * lde + c] = __ldg(cb + (size_t)(c0 + c) * D + d);
       }
       __syncthreads();
-      float acc[8];
+      float acc[4][4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-      const float* e0 = E + (cg * 8) * lde;
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[a][j] = 0.f;
+#pragma unroll 4
       for (int d = 0; d < D; ++d) {
-        const float r = R[d * RQ_F + f];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = fmaf(r, e0[j * lde + d], acc[j]);
+        const float4 r = *reinterpret_cast<const float4*>(R + d * RQ_F + 4 * tf);
+        const float* e = E + d * lde + 4 * tc;
+        const float e0 = e[0], e1 = e[1], e2 = e[2], e3 = e[3];
+        acc[0][0] = fmaf(r.x, e0, acc[0][0]); acc[0][1] = fmaf(r.x, e1, acc[0][1]); acc[0][2] = fmaf(r.x, e2, acc[0][2]); acc[0][3] = fmaf(r.x, e3, acc[0][3]);
+        acc[1][0] = fmaf(r.y, e0, acc[1][0]); acc[1][1] = fmaf(r.y, e1, acc[1][1]); acc[1][2] = fmaf(r.y, e2, acc[1][2]); acc[1][3] = fmaf(r.y, e3, acc[1][3]);
+        acc[2][0] = fmaf(r.z, e0, acc[2][0]); acc[2][1] = fmaf(r.z, e1, acc[2][1]); acc[2][2] = fmaf(r.z, e2, acc[2][2]); acc[2][3] = fmaf(r.z, e3, acc[2][3]);
+        acc[3][0] = fmaf(r.w, e0, acc[3][0]); acc[3][1] = fmaf(r.w, e1, acc[3][1]); acc[3][2] = fmaf(r.w, e2, acc[3][2]); acc[3][3] = fmaf(r.w, e3, acc[3][3]);
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int idx = c0 + cg * 8 + j;
-        const float sc = 2.0f * acc[j] - __ldg(P.enorm + (size_t)q * P.K + idx);
-        if (sc > best) {  // ascending index inside a thread: strict > keeps the first maximum
-          best = sc;
-          besti = idx;
+      for (int j = 0; j < 4; ++j) {
+        const int idx = c0 + 4 * tc + j;
+        const float en = __ldg(P.enorm + (size_t)q * P.K + idx);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          const float sc = 2.0f * acc[a][j] - en;
+          if (sc > best[a]) {  // ascending index inside a thread: strict > keeps the first maximum
+            best[a] = sc;
+            besti[a] = idx;
+          }
         }
       }
       __syncthreads();
     }
-    bs[cg * RQ_F + f] = best;
-    bi[cg * RQ_F + f] = besti;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      bs[tc * RQ_F + 4 * tf + a] = best[a];
+      bi[tc * RQ_F + 4 * tf + a] = besti[a];
+    }
     __syncthreads();
     if (tid < RQ_F) {
       float b = bs[tid];
       int ix = bi[tid];
-      for (int g = 1; g < 8; ++g) {
+      for (int g = 1; g < 16; ++g) {
         const float s2 = bs[g * RQ_F + tid];
         const int i2 = bi[g * RQ_F + tid];
         if (s2 > b || (s2 == b && i2 < ix)) {
@@ -426,8 +441,9 @@ __global__ void __launch_bounds__(256) rvq_kernel(const RvqParams P) {
     }
     __syncthreads();
     {
+      const int f = tid & 63;
       const float* e = cb + (size_t)pick[f] * D;
-      for (int d = cg; d < D; d += 8) {
+      for (int d = tid >> 6; d < D; d += 4) {
         const float v = __ldg(e + d);
         R[d * RQ_F + f] -= v;
         Q[d * RQ_F + f] += v;
@@ -437,7 +453,7 @@ __global__ void __launch_bounds__(256) rvq_kernel(const RvqParams P) {
   }
   if (P.quant)
     for (int i = tid; i < D * RQ_F; i += 256) {
-      const int d = i >> 5, ff = i & 31;
+      const int d = i >> 6, ff = i & 63;
       if (t0 + ff < P.T) P.quant[((size_t)n * D + d) * P.T + t0 + ff] = Q[i];
     }
 }
@@ -1320,7 +1336,7 @@ int CodecDecoder::quantize(const float* latent, int32_t* codes, float* quantized
   P.D = d_.dimension;
   P.K = K_;
   P.nq = n_q_;
-  const size_t smem = ((size_t)2 * P.D * RQ_F + (size_t)RQ_C * (P.D + 1) + 8 * RQ_F) * sizeof(float) + (8 * RQ_F + RQ_F) * sizeof(int);
+  const size_t smem = ((size_t)2 * P.D * RQ_F + (size_t)P.D * (RQ_C + 1) + 16 * RQ_F) * sizeof(float) + (16 * RQ_F + RQ_F) * sizeof(int);
   cudaFuncSetAttribute(rvq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 g2((unsigned)((T + RQ_F - 1) / RQ_F), (unsigned)N);
   rvq_kernel<<<g2, 256, smem, st>>>(P);

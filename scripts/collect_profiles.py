@@ -95,7 +95,7 @@ def main(tag, label, steps=5):
         if f.startswith(tag + "_bench_") and f.endswith(".json") and os.path.getsize(os.path.join(G, f)) > 0:
             shutil.copy(os.path.join(G, f), os.path.join(P, label + f[len(tag):]))
         if f in (tag + "_attn_bench.jsonl", tag + "_launches_codec.csv.gz", tag + "_launches_codec_summary.txt",
-                 tag + "_multigpu_check_n2.log"):
+                 tag + "_launches_codec_encode.csv.gz", tag + "_launches_codec_encode_summary.txt", tag + "_multigpu_check_n2.log"):
             shutil.copy(os.path.join(G, f), os.path.join(P, label + f[len(tag):]))
     for extra in ("tl_c2.txt", "tl_c3.txt"):
         src = os.path.join(G, "%s_%s" % (tag, extra))
