@@ -3,17 +3,21 @@
 // keys in one TMEM accumulator, <= 256 keys, the model's own shapes).  One CTA = (batch row, head, 128-query tile); the
 // keys stream through in tiles of 128:
 //
-//   loaders (warps 5-7)   K_j, V_j tiles -> 2-stage shared-memory ring with cp.async (K-major 128-byte-swizzled rows; V is
-//                         consumed as an MN-major operand straight from its [key][channel] layout)
+//   loaders (warps 5-7)   K_j, V_j tiles -> shared-memory rings (TMA: one thread per ring, or cp.async; K-major 128-byte-
+//                         swizzled rows; V is consumed as an MN-major operand straight from its [key][channel] layout).
+//                         The K and the V ring have their OWN full / empty barriers: a K stage is free as soon as S_j has
+//                         been computed, a whole tile period before the V stage (free after P_j V_j), so the load of
+//                         K_{j+NS} is never on the critical path of S_{j+NS} even with a two-stage ring (d = 128)
 //   MMA issuer (warp 4)   S_j = Q K_j^T  -> TMEM buffer j & 1 (2 x 128 columns);  O_j = P_j V_j -> TMEM buffer 2 + (j & 1).
 //                         S_{j+1} is issued BEFORE P_j V_j, so the tensor core computes the next logits while the softmax
 //                         warps are busy with the current ones
 //   softmax (warps 0-3)   thread == query row (TMEM lane): running max m and sum l in base 2 (online softmax), P_j = 2^(s-m)
-//                         rounded to bf16 into a swizzled A tile; the partial product O_j comes back from TMEM and is folded
+//                         rounded to bf16 into a swizzled A tile (double-buffered: writing P_j does not wait for
+//                         P_{j-1} V_{j-1}); the partial product O_j comes back from TMEM and is folded
 //                         into register accumulators  o = o * 2^(m_old - m_new) + O_j  -- no read-modify-write of TMEM and no
 //                         separate correction pass
 //
-// Five mbarrier pipelines connect them (kv_full/kv_empty, s_full/s_empty, p_full, o_full/o_empty).  Causal tiles that lie
+// Six mbarrier pipelines connect them (k_full/k_empty, v_full/v_empty, s_full/s_empty, p_full, o_full/o_empty).  Causal tiles that lie
 // completely above the diagonal are skipped.  Keys beyond the key count are zero-filled and excluded from the softmax.
 #include <cuda.h>
 #include <float.h>
@@ -60,6 +64,9 @@ __device__ __forceinline__ void tma_load_tile(void* dst, const CUtensorMap* tm, 
       : "memory");
 }
 // suspending wait (hardware time-limited sleep) for the warps whose waits are long: keeps them off the issue slots
+#ifndef JEN1_FA_POLL
+#define JEN1_FA_POLL 0  // A/B: 1 = the MMA issuer polls (test_wait) instead of the suspending try_wait
+#endif
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
   const uint32_t a = smem_u32(bar);
   uint32_t done;
@@ -75,6 +82,13 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) 
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mma_wait(uint64_t* bar, uint32_t parity) {
+#if JEN1_FA_POLL
+  mbar_wait(bar, parity);
+#else
+  mbar_wait_sleep(bar, parity);
+#endif
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -133,6 +147,28 @@ __device__ __forceinline__ float ex2_fast(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// packed fp32 pairs (sm_100: FFMA2 / FADD2 / FMUL2 -- one issue slot for two lanes of arithmetic)
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
 __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
@@ -164,32 +200,37 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_flash_kernel(const __grid_
   uint8_t* Qs = smem;
   uint8_t* Ks = Qs + tile_bytes;                      // [NS stages]
   uint8_t* Vs = Ks + NS * tile_bytes;                 // [NS stages]
-  uint8_t* Ps = Vs + NS * tile_bytes;                 // [2 key blocks][128 queries][128 B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(Ps + 2 * 128 * 128);
+  uint8_t* Ps = Vs + NS * tile_bytes;                 // [2 buffers][2 key blocks][128 queries][128 B]
+  constexpr uint32_t kPBytes = 2 * 128 * 128;         // one P buffer
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Ps + 2 * kPBytes);
   uint64_t* q_full = bars;           // 1: producers of Q (all threads)
-  uint64_t* kv_full = bars + 1;      // [4] loaders -> MMA
-  uint64_t* kv_empty = bars + 5;     // [4] MMA (commit) -> loaders
-  uint64_t* s_full = bars + 9;       // [2] MMA (commit) -> softmax
-  uint64_t* s_empty = bars + 11;     // [2] softmax -> MMA
-  uint64_t* p_full = bars + 13;      // softmax -> MMA
-  uint64_t* o_full = bars + 14;      // [2] MMA (commit) -> softmax
-  uint64_t* o_empty = bars + 16;     // [2] softmax -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
-  float* xbuf = reinterpret_cast<float*>(bars + 20);  // [2 parities][2 halves][128 rows]: row-max / row-sum exchange
+  uint64_t* k_full = bars + 1;       // [4] loaders -> MMA
+  uint64_t* k_empty = bars + 5;      // [4] MMA (commit after S_j) -> loaders
+  uint64_t* v_full = bars + 9;       // [4] loaders -> MMA
+  uint64_t* v_empty = bars + 13;     // [4] MMA (commit after P_j V_j) -> loaders
+  uint64_t* s_full = bars + 17;      // [2] MMA (commit) -> softmax
+  uint64_t* s_empty = bars + 19;     // [2] softmax -> MMA
+  uint64_t* p_full = bars + 21;      // [2] softmax -> MMA
+  uint64_t* o_full = bars + 23;      // [2] MMA (commit) -> softmax
+  uint64_t* o_empty = bars + 25;     // [2] softmax -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 27);
+  float* xbuf = reinterpret_cast<float*>(bars + 28);  // [2 parities][2 halves][128 rows]: row-max / row-sum exchange
 
   if (tid == 128) {
     mbar_init(q_full, use_tma ? 1 : kFaThreads);
     for (int s = 0; s < 4; ++s) {
-      mbar_init(&kv_full[s], use_tma ? 1 : kFaLoaders);
-      mbar_init(&kv_empty[s], 1);
+      mbar_init(&k_full[s], use_tma ? 1 : kFaLoaders);
+      mbar_init(&v_full[s], use_tma ? 1 : kFaLoaders);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&s_full[s], 1);
       mbar_init(&s_empty[s], 256);
+      mbar_init(&p_full[s], 256);
       mbar_init(&o_full[s], 1);
       mbar_init(&o_empty[s], 256);
     }
-    mbar_init(p_full, 256);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 4) {
@@ -245,16 +286,22 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_flash_kernel(const __grid_
 
   if (warp >= 5 && warp < 8) {
     // ======================================================================== K / V loaders
-    if (use_tma) {  // one thread: 2 * DB bulk tensor copies per key tile, completion counted in bytes on kv_full
+    if (use_tma) {  // one thread per ring (warp 5: K, warp 6: V): DB bulk tensor copies per key tile, completion counted in bytes
       if (tid == 160) {
         for (int j = 0; j < nt; ++j) {
           const int s = j % NS;
-          if (j >= NS) mbar_wait_sleep(&kv_empty[s], (uint32_t)((j / NS - 1) & 1));
-          mbar_expect_tx(&kv_full[s], 2 * tile_bytes);
-          for (int db = 0; db < DB; ++db) {
-            tma_load_tile(Ks + (size_t)s * tile_bytes + (size_t)db * 128 * 128, &tmap, p.k_off + h * d + db * 64, j * kBN, r, &kv_full[s]);
-            tma_load_tile(Vs + (size_t)s * tile_bytes + (size_t)db * 128 * 128, &tmap, p.v_off + h * d + db * 64, j * kBN, r, &kv_full[s]);
-          }
+          if (j >= NS) mbar_wait_sleep(&k_empty[s], (uint32_t)((j / NS - 1) & 1));
+          mbar_expect_tx(&k_full[s], tile_bytes);
+          for (int db = 0; db < DB; ++db)
+            tma_load_tile(Ks + (size_t)s * tile_bytes + (size_t)db * 128 * 128, &tmap, p.k_off + h * d + db * 64, j * kBN, r, &k_full[s]);
+        }
+      } else if (tid == 192) {
+        for (int j = 0; j < nt; ++j) {
+          const int s = j % NS;
+          if (j >= NS) mbar_wait_sleep(&v_empty[s], (uint32_t)((j / NS - 1) & 1));
+          mbar_expect_tx(&v_full[s], tile_bytes);
+          for (int db = 0; db < DB; ++db)
+            tma_load_tile(Vs + (size_t)s * tile_bytes + (size_t)db * 128 * 128, &tmap, p.v_off + h * d + db * 64, j * kBN, r, &v_full[s]);
         }
       }
       __syncwarp();
@@ -263,7 +310,10 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_flash_kernel(const __grid_
     const bf16* kbase = (const bf16*)p.kv + (size_t)r * N * p.kv_ld + h * d;  // self-attention layout: key rows r * N + j
     for (int j = 0; j < nt; ++j) {
       const int s = j % NS;
-      if (j >= NS) mbar_wait_sleep(&kv_empty[s], (uint32_t)((j / NS - 1) & 1));
+      if (j >= NS) {  // (the V stage is released last)
+        mbar_wait_sleep(&k_empty[s], (uint32_t)((j / NS - 1) & 1));
+        mbar_wait_sleep(&v_empty[s], (uint32_t)((j / NS - 1) & 1));
+      }
       uint8_t* kt = Ks + (size_t)s * tile_bytes;
       uint8_t* vt = Vs + (size_t)s * tile_bytes;
       const int j0 = j * kBN;
@@ -288,7 +338,8 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_flash_kernel(const __grid_
       }
       asm volatile("cp.async.commit_group;\n\tcp.async.wait_all;" ::: "memory");
       fence_async_smem();
-      mbar_arrive(&kv_full[s]);
+      mbar_arrive(&k_full[s]);
+      mbar_arrive(&v_full[s]);
     }
     }
   } else if (warp == 4) {
@@ -299,7 +350,7 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_flash_kernel(const __grid_
       const uint32_t q_addr = smem_u32(Qs), p_addr = smem_u32(Ps);
       auto issue_s = [&](int j) {
         const int s = j & 1, ks = j % NS;
-        mbar_wait_sleep(&kv_full[ks], (uint32_t)((j / NS) & 1));
+        mma_wait(&k_full[ks], (uint32_t)((j / NS) & 1));
         if (j >= 2) mbar_wait(&s_empty[s], (uint32_t)(((j >> 1) - 1) & 1));  // softmax has read S_{j-2}
         tc_fence_after();
         const uint32_t k_addr = smem_u32(Ks + (size_t)ks * tile_bytes);
@@ -314,23 +365,25 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_flash_kernel(const __grid_
           }
         }
         umma_commit(&s_full[s]);
+        umma_commit(&k_empty[ks]);  // K_j is free once S_j is complete
       };
       auto issue_o = [&](int j) {
         const int s = j & 1;
-        mbar_wait_sleep(p_full, (uint32_t)(j & 1));                            // P_j written
+        const int ks = j % NS;
+        mma_wait(&v_full[ks], (uint32_t)((j / NS) & 1));
+        mma_wait(&p_full[s], (uint32_t)((j >> 1) & 1));                 // P_j written
         if (j >= 2) mbar_wait(&o_empty[s], (uint32_t)(((j >> 1) - 1) & 1));    // softmax has read O_{j-2}
         tc_fence_after();
-        const int ks = j % NS;
         const uint32_t v_addr = smem_u32(Vs + (size_t)ks * tile_bytes);
         uint32_t acc = 0;
         for (int k16 = 0; k16 < kBN / 16; ++k16) {
-          const uint64_t ad = make_desc_sw128(p_addr + (uint32_t)(k16 >> 2) * 128u * 128u + (uint32_t)(k16 & 3) * 32u, 16u, 1024u);
+          const uint64_t ad = make_desc_sw128(p_addr + (uint32_t)s * kPBytes + (uint32_t)(k16 >> 2) * 128u * 128u + (uint32_t)(k16 & 3) * 32u, 16u, 1024u);
           const uint64_t bd = make_desc_sw128(v_addr + (uint32_t)k16 * 2048u, 128u * 128u, 1024u);
           umma_bf16(tmem_base + (uint32_t)(256 + s * 128), ad, bd, idesc_o, acc);
           acc = 1;
         }
         umma_commit(&o_full[s]);
-        umma_commit(&kv_empty[ks]);  // K_j and V_j are free once S_j and O_j are complete
+        umma_commit(&v_empty[ks]);  // V_j is free once O_j is complete
       };
       mbar_wait(q_full, 0);
       tc_fence_after();
@@ -347,20 +400,26 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_flash_kernel(const __grid_
     // [0, d/2), half 1 (warps 8-11) the other halves.  The row maximum is exchanged through shared memory (one named
     // barrier per tile); the running sum is kept per half and combined at the end.  Each thread: 64 logits in
     // registers (ONE TMEM load per tile), 64 exponentials, one 64-key block of the P row, d/2 accumulators.
+    // The warps are bound by their own instruction latency (two softmax warps per scheduler), so the tile body is written
+    // for few instructions and short dependency chains: packed fp32 pairs (FFMA2 / FADD2 / FMUL2) for the scaling, the row
+    // sum and the accumulator fold, four independent max chains, eight independent sum chains, and the key masking of
+    // edge tiles (last tile, causal diagonal) in a code path of its own.
     const int half = warp >> 3;                       // 0 / 1
     const int rowi = (warp & 3) * 32 + lane;          // query row of this thread == TMEM lane
     const int i = i0 + rowi;
     const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     const float sc = p.scale * 1.4426950408889634f;   // base-2 softmax
+    const uint64_t sc2 = pk2(sc, sc);
     const int jmax = p.causal ? i + (M - N) : M - 1;  // last key this query may see
     constexpr int DH = DMAX / 2;
     const int dc = d >= 64 ? d / 2 : (half == 0 ? d : 0);  // output channels folded by this thread: [half * dc, +dc)
     float m = -FLT_MAX, l = 0.f;
-    float o[DH];
+    uint64_t o2[DH / 2];  // accumulators as packed pairs (channel 2e, 2e + 1)
 #pragma unroll
-    for (int e = 0; e < DH; ++e) o[e] = 0.f;
-    uint8_t* prow = Ps + (size_t)half * 128 * 128 + (size_t)rowi * 128;
+    for (int e = 0; e < DH / 2; ++e) o2[e] = 0ull;
+    uint8_t* prow0 = Ps + (size_t)half * 128 * 128 + (size_t)rowi * 128;
     for (int j = 0; j < nt; ++j) {
+      uint8_t* prow = prow0 + (size_t)(j & 1) * kPBytes;  // P_{j-2} V_{j-2} has completed: its fold (tile j - 1) waited for it
       const int s = j & 1, j0 = j * kBN + half * 64;
       mbar_wait(&s_full[s], (uint32_t)((j >> 1) & 1));
       tc_fence_after();
@@ -370,11 +429,21 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_flash_kernel(const __grid_
       mbar_arrive(&s_empty[s]);  // the logits are in registers: the TMEM buffer may be overwritten
       const int kmaxv = min(jmax, M - 1) - j0;  // last valid key of this thread's 64 (may be < 0)
       const bool edge = kmaxv < 63;
-      float mx = -FLT_MAX;
+      float mx;
       if (!edge) {
+        float m4[4] = {v[0], v[1], v[2], v[3]};
 #pragma unroll
-        for (int q = 0; q < 64; ++q) mx = fmaxf(mx, v[q]);
+        for (int q = 4; q < 64; q += 8) {  // four independent chains of 3-input maxima
+          m4[0] = fmaxf(m4[0], fmaxf(v[q], v[q + 1]));
+          m4[1] = fmaxf(m4[1], fmaxf(v[q + 2], v[q + 3]));
+          m4[2] = fmaxf(m4[2], fmaxf(v[q + 4], v[q + 5]));
+          m4[3] = fmaxf(m4[3], fmaxf(v[q + 6], v[q + 7]));
+        }
+        m4[0] = fmaxf(m4[0], fmaxf(v[60], v[61]));
+        m4[1] = fmaxf(m4[1], fmaxf(v[62], v[63]));
+        mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
       } else {
+        mx = -FLT_MAX;
 #pragma unroll
         for (int q = 0; q < 64; ++q)
           if (q <= kmaxv) mx = fmaxf(mx, v[q]);
@@ -386,43 +455,77 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_flash_kernel(const __grid_
       mx = fmaxf(fmaxf(mx, xb[(half ^ 1) * 128 + rowi]), m);
       const float alpha = ex2_fast(m - mx);
       m = mx;
-      float sum = 0.f;
-      if (j > 0) mbar_wait(&o_full[(j - 1) & 1], (uint32_t)(((j - 1) >> 1) & 1));  // P V_{j-1} done: the P tile is free
+      const uint64_t nm2 = pk2(-mx, -mx);
+      uint64_t sum2[4] = {0ull, 0ull, 0ull, 0ull};
+      if (!edge) {
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {  // 8 keys = one 16-byte chunk of the P row
-        float e[8];
+        for (int c = 0; c < 8; ++c) {  // 8 keys = one 16-byte chunk of the P row
+          uint32_t pw[4];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          float pj = ex2_fast(fmaf(v[c * 8 + q], sc, -mx));
-          if (edge && c * 8 + q > kmaxv) pj = 0.0f;
-          sum += pj;  // (the bf16 rounding of P happens in pack2; the row sum keeps the unrounded terms)
-          e[q] = pj;
+          for (int q = 0; q < 4; ++q) {
+            float e0, e1;
+            upk2(ffma2(pk2(v[c * 8 + 2 * q], v[c * 8 + 2 * q + 1]), sc2, nm2), e0, e1);
+            e0 = ex2_fast(e0);
+            e1 = ex2_fast(e1);
+            sum2[q] = fadd2(sum2[q], pk2(e0, e1));  // (the bf16 rounding of P happens in pack2; the row sum keeps the unrounded terms)
+            pw[q] = pack2(e0, e1);
+          }
+          *reinterpret_cast<uint4*>(prow + ((c ^ (rowi & 7)) * 16)) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
         }
-        *reinterpret_cast<uint4*>(prow + ((c ^ (rowi & 7)) * 16)) = make_uint4(pack2(e[0], e[1]), pack2(e[2], e[3]), pack2(e[4], e[5]), pack2(e[6], e[7]));
+      } else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint32_t pw[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int k0 = c * 8 + 2 * q;
+            float e0 = ex2_fast(fmaf(v[k0], sc, -mx)), e1 = ex2_fast(fmaf(v[k0 + 1], sc, -mx));
+            if (k0 > kmaxv) e0 = 0.0f;
+            if (k0 + 1 > kmaxv) e1 = 0.0f;
+            sum2[q] = fadd2(sum2[q], pk2(e0, e1));
+            pw[q] = pack2(e0, e1);
+          }
+          *reinterpret_cast<uint4*>(prow + ((c ^ (rowi & 7)) * 16)) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+        }
       }
       fence_async_smem();
-      mbar_arrive(p_full);
+      mbar_arrive(&p_full[j & 1]);
+      float sum;
+      {
+        float a0, a1;
+        upk2(fadd2(fadd2(sum2[0], sum2[1]), fadd2(sum2[2], sum2[3])), a0, a1);
+        sum = a0 + a1;
+      }
       // fold the PREVIOUS tile's partial product into the accumulators (its MMA ran while this tile's logits were being
-      // exponentiated): o_{j-1} = o_{j-2} * alpha_{j-1} + O_{j-1}, then expressed at this tile's maximum (* alpha_j)
+      // exponentiated): o_{j-1} = o_{j-2} * alpha_{j-1} + O_{j-1}, then expressed at this tile's maximum (* alpha_j).
+      // Once the running maximum of a whole warp has settled alpha is exactly 1 and the multiplication is skipped.
       if (j > 0) {
         const int so = (j - 1) & 1;
+        mbar_wait(&o_full[so], (uint32_t)(((j - 1) >> 1) & 1));  // P_{j-1} V_{j-1} done
         tc_fence_after();
         const uint32_t to = trow + (uint32_t)(256 + so * 128 + half * dc);
+        const bool rescale = !__all_sync(0xffffffffu, alpha == 1.0f);
+        const uint64_t al2 = pk2(alpha, alpha);
         if (dc == 64) {
           if constexpr (DH >= 64) {
             float w[64];
             tmem_ld64(to, w);
+            if (rescale) {
 #pragma unroll
-            for (int q = 0; q < 64; ++q) o[q] = (o[q] + w[q]) * alpha;
+              for (int q = 0; q < 32; ++q) o2[q] = fmul2(fadd2(o2[q], pk2(w[2 * q], w[2 * q + 1])), al2);
+            } else {
+#pragma unroll
+              for (int q = 0; q < 32; ++q) o2[q] = fadd2(o2[q], pk2(w[2 * q], w[2 * q + 1]));
+            }
           }
         } else {
 #pragma unroll
           for (int c0 = 0; c0 < DH; c0 += 16) {
-            if (c0 < dc) {  // dc is a multiple of 16 here except d = 16 split... (d >= 64: dc = 32; d < 64: dc = d or 0)
+            if (c0 < dc) {  // dc is a multiple of 16 (d >= 64: dc = 32; d < 64: dc = d or 0)
               float w[16];
               tmem_ld16(to + (uint32_t)c0, w);
 #pragma unroll
-              for (int q = 0; q < 16; ++q) o[c0 + q] = (o[c0 + q] + w[q]) * alpha;
+              for (int q = 0; q < 8; ++q) o2[c0 / 2 + q] = fmul2(fadd2(o2[c0 / 2 + q], pk2(w[2 * q], w[2 * q + 1])), al2);
             }
           }
         }
@@ -437,6 +540,7 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_flash_kernel(const __grid_
       xb[half * 128 + rowi] = l;
       asm volatile("bar.sync 2, 256;" ::: "memory");
       const float inv = 1.0f / (xb[rowi] + xb[128 + rowi]);
+      const uint64_t inv2 = pk2(inv, inv);
       mbar_wait(&o_full[so], (uint32_t)(((nt - 1) >> 1) & 1));
       tc_fence_after();
       const uint32_t to = trow + (uint32_t)(256 + so * 128 + half * dc);
@@ -447,12 +551,15 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_flash_kernel(const __grid_
           float w[16];
           tmem_ld16(to + (uint32_t)c0, w);
           if (i < N) {
-            *reinterpret_cast<uint4*>(orow + c0) =
-                make_uint4(pack2((o[c0] + w[0]) * inv, (o[c0 + 1] + w[1]) * inv), pack2((o[c0 + 2] + w[2]) * inv, (o[c0 + 3] + w[3]) * inv),
-                           pack2((o[c0 + 4] + w[4]) * inv, (o[c0 + 5] + w[5]) * inv), pack2((o[c0 + 6] + w[6]) * inv, (o[c0 + 7] + w[7]) * inv));
-            *reinterpret_cast<uint4*>(orow + c0 + 8) =
-                make_uint4(pack2((o[c0 + 8] + w[8]) * inv, (o[c0 + 9] + w[9]) * inv), pack2((o[c0 + 10] + w[10]) * inv, (o[c0 + 11] + w[11]) * inv),
-                           pack2((o[c0 + 12] + w[12]) * inv, (o[c0 + 13] + w[13]) * inv), pack2((o[c0 + 14] + w[14]) * inv, (o[c0 + 15] + w[15]) * inv));
+            uint32_t ow[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              float a0, a1;
+              upk2(fmul2(fadd2(o2[c0 / 2 + q], pk2(w[2 * q], w[2 * q + 1])), inv2), a0, a1);
+              ow[q] = pack2(a0, a1);
+            }
+            *reinterpret_cast<uint4*>(orow + c0) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            *reinterpret_cast<uint4*>(orow + c0 + 8) = make_uint4(ow[4], ow[5], ow[6], ow[7]);
           }
         }
       }
@@ -480,7 +587,9 @@ bool attn_flash_supported(const AttnParams& p) {
 
 static size_t attn_flash_smem(int d) {
   const int DB = (d + 63) / 64, NS = d <= 64 ? 4 : 2;
-  return (size_t)(1 + 2 * NS) * DB * 128 * 128 + 2 * 128 * 128 + 160 + 2 * 2 * 128 * 4 + 1024;
+  // Q + K / V rings + two P buffers + 28 barriers (+ TMEM slot) + the row max / sum exchange; the dynamic shared-memory
+  // window is 1024-byte aligned (no manual round-up in the kernel, hence no slack here: d = 128 uses 226.2 of 227 KB)
+  return (size_t)(1 + 2 * NS) * DB * 128 * 128 + 2 * (2 * 128 * 128) + 28 * 8 + 2 * 2 * 128 * 4;
 }
 
 cudaError_t attn_flash_init() {
