@@ -30,9 +30,10 @@ namespace jen1 {
 
 namespace {
 
-constexpr int kFaThreads = 384;  // warps 0-3 softmax A, 4 MMA issuer, 5-7 loaders, 8-11 softmax B
+constexpr int kFaThreads = 384;  // warps 0-3 softmax of query tile 0, 4 MMA issuer, 5-7 loaders, 8-11 softmax of query tile 1
 constexpr int kFaLoaders = 96;   // warps 5-7
 constexpr int kBN = 128;         // keys per tile
+constexpr int kBM = 256;         // queries per CTA: two tiles of 128, one per softmax warpgroup
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -184,37 +185,50 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 }
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
-// DMAX: head-dim capacity of the register accumulators (64 or 128)
-template <int DMAX>
+// tcgen05.st: 16 consecutive columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15};\n\t"
+      "tcgen05.wait::st.sync.aligned;" ::"r"(__float_as_uint(v[0])),
+      "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])),
+      "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])),
+      "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])),
+      "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])), "r"(taddr)
+      : "memory");
+}
+
+// The running maximum a row scales with may lag the true maximum by up to 2^kTau (P <= 2^kTau, exact in bf16's exponent
+// range): the accumulator in TMEM is only rescaled when a row's maximum grows by more than that, which after the first
+// few key tiles practically never happens.
+constexpr float kTau = 8.0f;
+
 __global__ void __launch_bounds__(kFaThreads, 1) attn_flash_kernel(const __grid_constant__ AttnParams p,
                                                                    const __grid_constant__ CUtensorMap tmap, const int use_tma) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int i0 = blockIdx.x * 128, h = blockIdx.y, r = blockIdx.z;
+  const int i0 = blockIdx.x * kBM, h = blockIdx.y, r = blockIdx.z;
   const int d = p.d, M = p.M, N = p.N;
   const int DB = (d + 63) >> 6;                       // 64-channel blocks of the head dim
   const int sh = d == 16 ? 1 : (d == 32 ? 2 : (d == 64 ? 3 : 4));
   const int cpr = 1 << sh;                            // 16-byte chunks per head row
-  const uint32_t tile_bytes = (uint32_t)DB * 128u * 128u;  // one Q / K / V tile
-  const int NS = d <= 64 ? 4 : 2;                     // K / V ring depth (what fits next to Q and P)
-  uint8_t* Qs = smem;
-  uint8_t* Ks = Qs + tile_bytes;                      // [NS stages]
-  uint8_t* Vs = Ks + NS * tile_bytes;                 // [NS stages]
-  uint8_t* Ps = Vs + NS * tile_bytes;                 // [2 buffers][2 key blocks][128 queries][128 B]
-  constexpr uint32_t kPBytes = 2 * 128 * 128;         // one P buffer
+  const uint32_t tile_bytes = (uint32_t)DB * 128u * 128u;  // one Q / K / V tile of 128 rows
+  const int NSK = d <= 64 ? 4 : 2, NSV = d <= 64 ? 2 : 1;  // K / V ring depths (what fits next to two Q and two P tiles)
+  uint8_t* Qs = smem;                                 // [2 query tiles]
+  uint8_t* Ks = Qs + 2 * tile_bytes;                  // [NSK stages]
+  uint8_t* Vs = Ks + NSK * tile_bytes;                // [NSV stages]
+  uint8_t* Ps = Vs + NSV * tile_bytes;                // [2 query tiles][2 key blocks][128 queries][128 B]
+  constexpr uint32_t kPBytes = 2 * 128 * 128;         // one P tile
   uint64_t* bars = reinterpret_cast<uint64_t*>(Ps + 2 * kPBytes);
-  uint64_t* q_full = bars;           // 1: producers of Q (all threads)
+  uint64_t* q_full = bars;           // 1: producers of Q
   uint64_t* k_full = bars + 1;       // [4] loaders -> MMA
-  uint64_t* k_empty = bars + 5;      // [4] MMA (commit after S_j) -> loaders
+  uint64_t* k_empty = bars + 5;      // [4] MMA (commit after the S_j of both query tiles) -> loaders
   uint64_t* v_full = bars + 9;       // [4] loaders -> MMA
-  uint64_t* v_empty = bars + 13;     // [4] MMA (commit after P_j V_j) -> loaders
-  uint64_t* s_full = bars + 17;      // [2] MMA (commit) -> softmax
-  uint64_t* s_empty = bars + 19;     // [2] softmax -> MMA
+  uint64_t* v_empty = bars + 13;     // [4] MMA (commit after the P_j V_j of both query tiles) -> loaders
+  uint64_t* s_full = bars + 17;      // [2 query tiles] MMA (commit) -> softmax
+  uint64_t* s_empty = bars + 19;     // [2] softmax (logits are in registers) -> MMA
   uint64_t* p_full = bars + 21;      // [2] softmax -> MMA
   uint64_t* o_full = bars + 23;      // [2] MMA (commit) -> softmax
-  uint64_t* o_empty = bars + 25;     // [2] softmax -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 27);
-  float* xbuf = reinterpret_cast<float*>(bars + 28);  // [2 parities][2 halves][128 rows]: row-max / row-sum exchange
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
 
   if (tid == 128) {
     mbar_init(q_full, use_tma ? 1 : kFaThreads);
@@ -226,10 +240,9 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_flash_kernel(const __grid_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&s_full[s], 1);
-      mbar_init(&s_empty[s], 256);
-      mbar_init(&p_full[s], 256);
+      mbar_init(&s_empty[s], 128);
+      mbar_init(&p_full[s], 128);
       mbar_init(&o_full[s], 1);
-      mbar_init(&o_empty[s], 256);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -245,38 +258,47 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_flash_kernel(const __grid_
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
 
-  // key tiles this query tile needs (causal: tiles completely above the diagonal are skipped)
-  int nt = (M + kBN - 1) / kBN;
-  if (p.causal) {
-    const int last_key = min(M - 1, i0 + 127 + (M - N));
-    nt = min(nt, last_key / kBN + 1);
+  // key tiles each query tile needs (causal: tiles completely above its diagonal are skipped; a query tile that starts
+  // beyond N has none)
+  const int nt_all = (M + kBN - 1) / kBN;
+  int ntg[2];
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    int n = (i0 + g * 128 < N) ? nt_all : 0;
+    if (n > 0 && p.causal) {
+      const int last_key = min(M - 1, i0 + g * 128 + 127 + (M - N));
+      n = min(n, last_key / kBN + 1);
+    }
+    ntg[g] = n;
   }
+  const int nt = max(ntg[0], ntg[1]);
 
-  // ---- Q tile (once): TMA (head dims that are multiples of 64) or all threads with cp.async; chunks beyond the head
-  //      dim inside the last 64-channel block read as zero
+  // ---- Q tiles (once): TMA (head dims that are multiples of 64; rows beyond N arrive as zeros) or all threads with
+  //      cp.async; chunks beyond the head dim inside the last 64-channel block read as zero
   if (use_tma) {
     if (tid == 160) {
-      mbar_expect_tx(q_full, tile_bytes);
-      for (int db = 0; db < DB; ++db) tma_load_tile(Qs + (size_t)db * 128 * 128, &tmap, p.q_off + h * d + db * 64, i0, r, q_full);
+      mbar_expect_tx(q_full, 2 * tile_bytes);
+      for (int g = 0; g < 2; ++g)
+        for (int db = 0; db < DB; ++db)
+          tma_load_tile(Qs + (size_t)g * tile_bytes + (size_t)db * 128 * 128, &tmap, p.q_off + h * d + db * 64, i0 + g * 128, r, q_full);
     }
   } else {
-    const int nqr = min(128, N - i0);
     const bf16* qsrc = (const bf16*)p.q + ((size_t)r * N + i0) * p.q_ld + p.q_off + h * d;
-    for (int i = tid; i < (nqr << sh); i += kFaThreads) {
-      const int rw = i >> sh, part = i & (cpr - 1);
-      cp_async16(Qs + ((uint32_t)(part >> 3) * 128u + (uint32_t)rw) * 128u + (uint32_t)(((part & 7) ^ (rw & 7)) * 16),
-                 qsrc + (size_t)rw * p.q_ld + part * 8);
-    }
-    for (int i = (nqr << sh) + tid; i < (128 << sh); i += kFaThreads) {  // query rows beyond N: zeros (never stored)
-      const int rw = i >> sh, part = i & (cpr - 1);
-      *reinterpret_cast<uint4*>(Qs + ((uint32_t)(part >> 3) * 128u + (uint32_t)rw) * 128u + (uint32_t)(((part & 7) ^ (rw & 7)) * 16)) =
-          make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < (256 << sh); i += kFaThreads) {
+      const int rw = i >> sh, part = i & (cpr - 1);  // rw: row of the 256-query block
+      uint8_t* dst = Qs + (size_t)(rw >> 7) * tile_bytes + ((uint32_t)(part >> 3) * 128u + (uint32_t)(rw & 127)) * 128u +
+                     (uint32_t)(((part & 7) ^ (rw & 7)) * 16);
+      if (i0 + rw < N)
+        cp_async16(dst, qsrc + (size_t)rw * p.q_ld + part * 8);
+      else
+        *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);  // query rows beyond N: zeros (never stored)
     }
     if (cpr < 8) {
       const int zc = 8 - cpr;
-      for (int it = tid; it < 128 * zc; it += kFaThreads) {
+      for (int it = tid; it < 256 * zc; it += kFaThreads) {
         const int rw = it / zc, ch = cpr + (it - rw * zc);
-        *reinterpret_cast<uint4*>(Qs + (uint32_t)rw * 128u + (uint32_t)((ch ^ (rw & 7)) * 16)) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(Qs + (size_t)(rw >> 7) * tile_bytes + (uint32_t)(rw & 127) * 128u + (uint32_t)((ch ^ (rw & 7)) * 16)) =
+            make_uint4(0u, 0u, 0u, 0u);
       }
     }
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_all;" ::: "memory");
@@ -289,16 +311,16 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_flash_kernel(const __grid_
     if (use_tma) {  // one thread per ring (warp 5: K, warp 6: V): DB bulk tensor copies per key tile, completion counted in bytes
       if (tid == 160) {
         for (int j = 0; j < nt; ++j) {
-          const int s = j % NS;
-          if (j >= NS) mbar_wait_sleep(&k_empty[s], (uint32_t)((j / NS - 1) & 1));
+          const int s = j % NSK;
+          if (j >= NSK) mbar_wait_sleep(&k_empty[s], (uint32_t)((j / NSK - 1) & 1));
           mbar_expect_tx(&k_full[s], tile_bytes);
           for (int db = 0; db < DB; ++db)
             tma_load_tile(Ks + (size_t)s * tile_bytes + (size_t)db * 128 * 128, &tmap, p.k_off + h * d + db * 64, j * kBN, r, &k_full[s]);
         }
       } else if (tid == 192) {
         for (int j = 0; j < nt; ++j) {
-          const int s = j % NS;
-          if (j >= NS) mbar_wait_sleep(&v_empty[s], (uint32_t)((j / NS - 1) & 1));
+          const int s = j % NSV;
+          if (j >= NSV) mbar_wait_sleep(&v_empty[s], (uint32_t)((j / NSV - 1) & 1));
           mbar_expect_tx(&v_full[s], tile_bytes);
           for (int db = 0; db < DB; ++db)
             tma_load_tile(Vs + (size_t)s * tile_bytes + (size_t)db * 128 * 128, &tmap, p.v_off + h * d + db * 64, j * kBN, r, &v_full[s]);
@@ -306,41 +328,37 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_flash_kernel(const __grid_
       }
       __syncwarp();
     } else {
-    const int lt = tid - 160;
-    const bf16* kbase = (const bf16*)p.kv + (size_t)r * N * p.kv_ld + h * d;  // self-attention layout: key rows r * N + j
-    for (int j = 0; j < nt; ++j) {
-      const int s = j % NS;
-      if (j >= NS) {  // (the V stage is released last)
-        mbar_wait_sleep(&k_empty[s], (uint32_t)((j / NS - 1) & 1));
-        mbar_wait_sleep(&v_empty[s], (uint32_t)((j / NS - 1) & 1));
-      }
-      uint8_t* kt = Ks + (size_t)s * tile_bytes;
-      uint8_t* vt = Vs + (size_t)s * tile_bytes;
-      const int j0 = j * kBN;
-      for (int i = lt; i < (kBN << (sh + 1)); i += kFaLoaders) {
-        const int v = i >= (kBN << sh) ? 1 : 0;
-        const int q = i - (v ? (kBN << sh) : 0);
-        const int rw = q >> sh, part = q & (cpr - 1);
-        uint8_t* dst = (v ? vt : kt) + ((uint32_t)(part >> 3) * 128u + (uint32_t)rw) * 128u + (uint32_t)(((part & 7) ^ (rw & 7)) * 16);
-        if (j0 + rw < M)
-          cp_async16(dst, kbase + (size_t)(j0 + rw) * p.kv_ld + (v ? p.v_off : p.k_off) + part * 8);
-        else
-          *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
-      }
-      if (cpr < 8 && j < NS) {  // zero chunks beyond the head dim: once per stage (never overwritten afterwards)
-        const int zc = 8 - cpr;
-        for (int it = lt; it < 2 * kBN * zc; it += kFaLoaders) {
-          const int v = it >= kBN * zc ? 1 : 0;
-          const int q = it - (v ? kBN * zc : 0);
-          const int rw = q / zc, ch = cpr + (q - rw * zc);
-          *reinterpret_cast<uint4*>((v ? vt : kt) + (uint32_t)rw * 128u + (uint32_t)((ch ^ (rw & 7)) * 16)) = make_uint4(0u, 0u, 0u, 0u);
+      const int lt = tid - 160;
+      const bf16* kbase = (const bf16*)p.kv + (size_t)r * N * p.kv_ld + h * d;  // self-attention layout: key rows r * N + j
+      // one tile of K (v = 0) or V (v = 1) rows [j0, j0 + 128) -> `dst` (first == true: also zero the chunks beyond the head dim)
+      auto load_tile = [&](uint8_t* dst, int j0, int v, bool first) {
+        for (int q = lt; q < (kBN << sh); q += kFaLoaders) {
+          const int rw = q >> sh, part = q & (cpr - 1);
+          uint8_t* a = dst + ((uint32_t)(part >> 3) * 128u + (uint32_t)rw) * 128u + (uint32_t)(((part & 7) ^ (rw & 7)) * 16);
+          if (j0 + rw < M)
+            cp_async16(a, kbase + (size_t)(j0 + rw) * p.kv_ld + (v ? p.v_off : p.k_off) + part * 8);
+          else
+            *reinterpret_cast<uint4*>(a) = make_uint4(0u, 0u, 0u, 0u);
         }
+        if (cpr < 8 && first) {  // once per stage (never overwritten afterwards)
+          const int zc = 8 - cpr;
+          for (int q = lt; q < kBN * zc; q += kFaLoaders) {
+            const int rw = q / zc, ch = cpr + (q - rw * zc);
+            *reinterpret_cast<uint4*>(dst + (uint32_t)rw * 128u + (uint32_t)((ch ^ (rw & 7)) * 16)) = make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
+        asm volatile("cp.async.commit_group;\n\tcp.async.wait_all;" ::: "memory");
+        fence_async_smem();
+      };
+      for (int j = 0; j < nt; ++j) {
+        const int ks = j % NSK, vs = j % NSV;
+        if (j >= NSK) mbar_wait_sleep(&k_empty[ks], (uint32_t)((j / NSK - 1) & 1));
+        load_tile(Ks + (size_t)ks * tile_bytes, j * kBN, 0, j < NSK);
+        mbar_arrive(&k_full[ks]);
+        if (j >= NSV) mbar_wait_sleep(&v_empty[vs], (uint32_t)((j / NSV - 1) & 1));
+        load_tile(Vs + (size_t)vs * tile_bytes, j * kBN, 1, j < NSV);
+        mbar_arrive(&v_full[vs]);
       }
-      asm volatile("cp.async.commit_group;\n\tcp.async.wait_all;" ::: "memory");
-      fence_async_smem();
-      mbar_arrive(&k_full[s]);
-      mbar_arrive(&v_full[s]);
-    }
     }
   } else if (warp == 4) {
     // ======================================================================== MMA issuer
@@ -348,118 +366,133 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_flash_kernel(const __grid_
       const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBN >> 3) << 17) | ((128u >> 4) << 24);
       const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(d >> 3) << 17) | ((128u >> 4) << 24);
       const uint32_t q_addr = smem_u32(Qs), p_addr = smem_u32(Ps);
-      auto issue_s = [&](int j) {
-        const int s = j & 1, ks = j % NS;
-        mma_wait(&k_full[ks], (uint32_t)((j / NS) & 1));
-        if (j >= 2) mbar_wait(&s_empty[s], (uint32_t)(((j >> 1) - 1) & 1));  // softmax has read S_{j-2}
+      // S^g_j = Q^g K_j^T -> TMEM columns [g * 128, +128)
+      auto issue_s = [&](int g, int j) {
+        if (j > 0) mbar_wait(&s_empty[g], (uint32_t)((j - 1) & 1));  // the softmax warps hold S^g_{j-1} in registers
         tc_fence_after();
-        const uint32_t k_addr = smem_u32(Ks + (size_t)ks * tile_bytes);
+        const uint32_t k_addr = smem_u32(Ks + (size_t)(j % NSK) * tile_bytes);
         uint32_t acc = 0;
         for (int db = 0; db < DB; ++db) {
           const int kmax = min(4, (d - db * 64) / 16);
           for (int kk = 0; kk < kmax; ++kk) {
-            const uint64_t ad = make_desc_sw128(q_addr + (uint32_t)db * 128u * 128u + (uint32_t)kk * 32u, 16u, 1024u);
+            const uint64_t ad = make_desc_sw128(q_addr + (uint32_t)g * tile_bytes + (uint32_t)db * 128u * 128u + (uint32_t)kk * 32u, 16u, 1024u);
             const uint64_t bd = make_desc_sw128(k_addr + (uint32_t)db * 128u * 128u + (uint32_t)kk * 32u, 16u, 1024u);
-            umma_bf16(tmem_base + (uint32_t)(s * 128), ad, bd, idesc_s, acc);
+            umma_bf16(tmem_base + (uint32_t)(g * 128), ad, bd, idesc_s, acc);
             acc = 1;
           }
         }
-        umma_commit(&s_full[s]);
-        umma_commit(&k_empty[ks]);  // K_j is free once S_j is complete
+        umma_commit(&s_full[g]);
       };
-      auto issue_o = [&](int j) {
-        const int s = j & 1;
-        const int ks = j % NS;
-        mma_wait(&v_full[ks], (uint32_t)((j / NS) & 1));
-        mma_wait(&p_full[s], (uint32_t)((j >> 1) & 1));                 // P_j written
-        if (j >= 2) mbar_wait(&o_empty[s], (uint32_t)(((j >> 1) - 1) & 1));    // softmax has read O_{j-2}
+      // O^g += P^g_j V_j -> TMEM columns [256 + g * 128, +d): accumulates over ALL key tiles
+      auto issue_o = [&](int g, int j) {
+        mma_wait(&p_full[g], (uint32_t)(j & 1));  // P^g_j written (and O^g rescaled if the row maxima moved)
         tc_fence_after();
-        const uint32_t v_addr = smem_u32(Vs + (size_t)ks * tile_bytes);
-        uint32_t acc = 0;
+        const uint32_t v_addr = smem_u32(Vs + (size_t)(j % NSV) * tile_bytes);
         for (int k16 = 0; k16 < kBN / 16; ++k16) {
-          const uint64_t ad = make_desc_sw128(p_addr + (uint32_t)s * kPBytes + (uint32_t)(k16 >> 2) * 128u * 128u + (uint32_t)(k16 & 3) * 32u, 16u, 1024u);
+          const uint64_t ad = make_desc_sw128(p_addr + (uint32_t)g * kPBytes + (uint32_t)(k16 >> 2) * 128u * 128u + (uint32_t)(k16 & 3) * 32u, 16u, 1024u);
           const uint64_t bd = make_desc_sw128(v_addr + (uint32_t)k16 * 2048u, 128u * 128u, 1024u);
-          umma_bf16(tmem_base + (uint32_t)(256 + s * 128), ad, bd, idesc_o, acc);
-          acc = 1;
+          umma_bf16(tmem_base + (uint32_t)(256 + g * 128), ad, bd, idesc_o, (j > 0 || k16 > 0) ? 1u : 0u);
         }
-        umma_commit(&o_full[s]);
-        umma_commit(&v_empty[ks]);  // V_j is free once O_j is complete
+        umma_commit(&o_full[g]);
       };
       mbar_wait(q_full, 0);
-      tc_fence_after();
+      mma_wait(&k_full[0], 0);
+      if (ntg[0] > 0) issue_s(0, 0);
+      if (ntg[1] > 0) issue_s(1, 0);
+      umma_commit(&k_empty[0]);
       for (int j = 0; j < nt; ++j) {
-        issue_s(j);
-        if (j > 0) issue_o(j - 1);
+        if (j + 1 < nt) {  // the next logits of both query tiles are computed while the softmax warps work on tile j
+          const int ks = (j + 1) % NSK;
+          mma_wait(&k_full[ks], (uint32_t)(((j + 1) / NSK) & 1));
+          if (j + 1 < ntg[0]) issue_s(0, j + 1);
+          if (j + 1 < ntg[1]) issue_s(1, j + 1);
+          umma_commit(&k_empty[ks]);  // K_{j+1} is free once both S_{j+1} are complete
+        }
+        const int vs = j % NSV;
+        mma_wait(&v_full[vs], (uint32_t)((j / NSV) & 1));
+        if (j < ntg[0]) issue_o(0, j);
+        if (j < ntg[1]) issue_o(1, j);
+        umma_commit(&v_empty[vs]);  // V_j is free once both P_j V_j are complete
       }
-      issue_o(nt - 1);
     }
     __syncwarp();
   } else {
-    // ======================================================================== online softmax + accumulation
-    // Two warpgroups share every row: `half` 0 (warps 0-3) owns key columns [0, 64) of each tile and output channels
-    // [0, d/2), half 1 (warps 8-11) the other halves.  The row maximum is exchanged through shared memory (one named
-    // barrier per tile); the running sum is kept per half and combined at the end.  Each thread: 64 logits in
-    // registers (ONE TMEM load per tile), 64 exponentials, one 64-key block of the P row, d/2 accumulators.
-    // The warps are bound by their own instruction latency (two softmax warps per scheduler), so the tile body is written
-    // for few instructions and short dependency chains: packed fp32 pairs (FFMA2 / FADD2 / FMUL2) for the scaling, the row
-    // sum and the accumulator fold, four independent max chains, eight independent sum chains, and the key masking of
-    // edge tiles (last tile, causal diagonal) in a code path of its own.
-    const int half = warp >> 3;                       // 0 / 1
-    const int rowi = (warp & 3) * 32 + lane;          // query row of this thread == TMEM lane
-    const int i = i0 + rowi;
+    // ======================================================================== online softmax
+    // Warpgroup g (warps 0-3: g = 0, warps 8-11: g = 1) owns query tile g; thread == query row == TMEM lane, with the
+    // row's 128 logits of a key tile in registers.  No exchange between threads: the row maximum, the row sum and the
+    // scaling are private, and the two warpgroups drift apart by about one MMA so that the warps sharing a scheduler
+    // are in different phases (one in the MUFU-bound exponentials while the other loads / reduces).  The output
+    // accumulator stays in TMEM across all key tiles (tcgen05.mma accumulate) and is rescaled in place only when a row
+    // maximum moves by more than 2^kTau.  The tile body is written for few instructions and short dependency chains:
+    // packed fp32 pairs (FFMA2 / FADD2), four independent max chains, eight independent sum chains, and the key
+    // masking of edge tiles (last tile, causal diagonal) in a code path of its own.
+    const int g = warp >> 3;
+    const int ntm = ntg[g];
+    const int rowi = (warp & 3) * 32 + lane;          // query row of this thread inside its tile == TMEM lane
+    const int i = i0 + g * 128 + rowi;
     const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t ts = trow + (uint32_t)(g * 128), to = trow + (uint32_t)(256 + g * 128);
     const float sc = p.scale * 1.4426950408889634f;   // base-2 softmax
     const uint64_t sc2 = pk2(sc, sc);
     const int jmax = p.causal ? i + (M - N) : M - 1;  // last key this query may see
-    constexpr int DH = DMAX / 2;
-    const int dc = d >= 64 ? d / 2 : (half == 0 ? d : 0);  // output channels folded by this thread: [half * dc, +dc)
     float m = -FLT_MAX, l = 0.f;
-    uint64_t o2[DH / 2];  // accumulators as packed pairs (channel 2e, 2e + 1)
-#pragma unroll
-    for (int e = 0; e < DH / 2; ++e) o2[e] = 0ull;
-    uint8_t* prow0 = Ps + (size_t)half * 128 * 128 + (size_t)rowi * 128;
-    for (int j = 0; j < nt; ++j) {
-      uint8_t* prow = prow0 + (size_t)(j & 1) * kPBytes;  // P_{j-2} V_{j-2} has completed: its fold (tile j - 1) waited for it
-      const int s = j & 1, j0 = j * kBN + half * 64;
-      mbar_wait(&s_full[s], (uint32_t)((j >> 1) & 1));
+    uint8_t* prow = Ps + (size_t)g * kPBytes + (size_t)rowi * 128;
+    for (int j = 0; j < ntm; ++j) {
+      mbar_wait(&s_full[g], (uint32_t)(j & 1));
       tc_fence_after();
-      float v[64];
-      tmem_ld64(trow + (uint32_t)(s * 128 + half * 64), v);
+      float v[128];
+      tmem_ld64(ts, *reinterpret_cast<float(*)[64]>(&v[0]));
+      tmem_ld64(ts + 64u, *reinterpret_cast<float(*)[64]>(&v[64]));
       tc_fence_before();
-      mbar_arrive(&s_empty[s]);  // the logits are in registers: the TMEM buffer may be overwritten
-      const int kmaxv = min(jmax, M - 1) - j0;  // last valid key of this thread's 64 (may be < 0)
-      const bool edge = kmaxv < 63;
+      mbar_arrive(&s_empty[g]);  // the logits are in registers: S^g may be overwritten
+      const int kmaxv = min(jmax, M - 1) - j * kBN;  // last valid key of this row in the tile (may be < 0)
+      const bool edge = kmaxv < 127;
       float mx;
       if (!edge) {
         float m4[4] = {v[0], v[1], v[2], v[3]};
 #pragma unroll
-        for (int q = 4; q < 64; q += 8) {  // four independent chains of 3-input maxima
+        for (int q = 4; q < 124; q += 8) {  // four independent chains of 3-input maxima
           m4[0] = fmaxf(m4[0], fmaxf(v[q], v[q + 1]));
           m4[1] = fmaxf(m4[1], fmaxf(v[q + 2], v[q + 3]));
           m4[2] = fmaxf(m4[2], fmaxf(v[q + 4], v[q + 5]));
           m4[3] = fmaxf(m4[3], fmaxf(v[q + 6], v[q + 7]));
         }
-        m4[0] = fmaxf(m4[0], fmaxf(v[60], v[61]));
-        m4[1] = fmaxf(m4[1], fmaxf(v[62], v[63]));
+        m4[0] = fmaxf(m4[0], fmaxf(v[124], v[125]));
+        m4[1] = fmaxf(m4[1], fmaxf(v[126], v[127]));
         mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
       } else {
         mx = -FLT_MAX;
 #pragma unroll
-        for (int q = 0; q < 64; ++q)
+        for (int q = 0; q < 128; ++q)
           if (q <= kmaxv) mx = fmaxf(mx, v[q]);
       }
       mx = (mx == -FLT_MAX) ? mx : mx * sc;  // sc > 0: max commutes with the scaling
-      float* xb = xbuf + (size_t)(j & 1) * 256;
-      xb[half * 128 + rowi] = mx;
-      asm volatile("bar.sync 2, 256;" ::: "memory");
-      mx = fmaxf(fmaxf(mx, xb[(half ^ 1) * 128 + rowi]), m);
-      const float alpha = ex2_fast(m - mx);
-      m = mx;
-      const uint64_t nm2 = pk2(-mx, -mx);
+      if (j > 0) {  // P^g_{j-1} V_{j-1} has completed: the P tile is free and O^g is stable
+        mbar_wait(&o_full[g], (uint32_t)((j - 1) & 1));
+        tc_fence_after();
+      }
+      const bool grow = mx > m + kTau || m == -FLT_MAX;
+      if (__any_sync(0xffffffffu, grow)) {  // rare after the first tiles: move this warp's rows to their new maxima
+        const float m_new = grow ? fmaxf(mx, m) : m;
+        const float alpha = ex2_fast(m - m_new);  // 1 for the rows that stay; 0 for a row without any key so far
+        if (j > 0) {
+#pragma unroll 1
+          for (int c0 = 0; c0 < d; c0 += 16) {
+            float w[16];
+            tmem_ld16(to + (uint32_t)c0, w);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) w[q] *= alpha;
+            tmem_st16(to + (uint32_t)c0, w);
+          }
+        }
+        l *= alpha;
+        m = m_new;
+      }
+      const uint64_t nm2 = pk2(-m, -m);
       uint64_t sum2[4] = {0ull, 0ull, 0ull, 0ull};
       if (!edge) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {  // 8 keys = one 16-byte chunk of the P row
+        for (int c = 0; c < 16; ++c) {  // 8 keys = one 16-byte chunk of the P row; chunks 0-7 key block 0, 8-15 key block 1
           uint32_t pw[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -470,97 +503,45 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_flash_kernel(const __grid_
             sum2[q] = fadd2(sum2[q], pk2(e0, e1));  // (the bf16 rounding of P happens in pack2; the row sum keeps the unrounded terms)
             pw[q] = pack2(e0, e1);
           }
-          *reinterpret_cast<uint4*>(prow + ((c ^ (rowi & 7)) * 16)) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+          *reinterpret_cast<uint4*>(prow + (size_t)(c >> 3) * 128 * 128 + (((c & 7) ^ (rowi & 7)) * 16)) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
         }
       } else {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
+        for (int c = 0; c < 16; ++c) {
           uint32_t pw[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int k0 = c * 8 + 2 * q;
-            float e0 = ex2_fast(fmaf(v[k0], sc, -mx)), e1 = ex2_fast(fmaf(v[k0 + 1], sc, -mx));
+            float e0 = ex2_fast(fmaf(v[k0], sc, -m)), e1 = ex2_fast(fmaf(v[k0 + 1], sc, -m));
             if (k0 > kmaxv) e0 = 0.0f;
             if (k0 + 1 > kmaxv) e1 = 0.0f;
             sum2[q] = fadd2(sum2[q], pk2(e0, e1));
             pw[q] = pack2(e0, e1);
           }
-          *reinterpret_cast<uint4*>(prow + ((c ^ (rowi & 7)) * 16)) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+          *reinterpret_cast<uint4*>(prow + (size_t)(c >> 3) * 128 * 128 + (((c & 7) ^ (rowi & 7)) * 16)) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
         }
       }
       fence_async_smem();
-      mbar_arrive(&p_full[j & 1]);
-      float sum;
-      {
-        float a0, a1;
-        upk2(fadd2(fadd2(sum2[0], sum2[1]), fadd2(sum2[2], sum2[3])), a0, a1);
-        sum = a0 + a1;
-      }
-      // fold the PREVIOUS tile's partial product into the accumulators (its MMA ran while this tile's logits were being
-      // exponentiated): o_{j-1} = o_{j-2} * alpha_{j-1} + O_{j-1}, then expressed at this tile's maximum (* alpha_j).
-      // Once the running maximum of a whole warp has settled alpha is exactly 1 and the multiplication is skipped.
-      if (j > 0) {
-        const int so = (j - 1) & 1;
-        mbar_wait(&o_full[so], (uint32_t)(((j - 1) >> 1) & 1));  // P_{j-1} V_{j-1} done
-        tc_fence_after();
-        const uint32_t to = trow + (uint32_t)(256 + so * 128 + half * dc);
-        const bool rescale = !__all_sync(0xffffffffu, alpha == 1.0f);
-        const uint64_t al2 = pk2(alpha, alpha);
-        if (dc == 64) {
-          if constexpr (DH >= 64) {
-            float w[64];
-            tmem_ld64(to, w);
-            if (rescale) {
-#pragma unroll
-              for (int q = 0; q < 32; ++q) o2[q] = fmul2(fadd2(o2[q], pk2(w[2 * q], w[2 * q + 1])), al2);
-            } else {
-#pragma unroll
-              for (int q = 0; q < 32; ++q) o2[q] = fadd2(o2[q], pk2(w[2 * q], w[2 * q + 1]));
-            }
-          }
-        } else {
-#pragma unroll
-          for (int c0 = 0; c0 < DH; c0 += 16) {
-            if (c0 < dc) {  // dc is a multiple of 16 (d >= 64: dc = 32; d < 64: dc = d or 0)
-              float w[16];
-              tmem_ld16(to + (uint32_t)c0, w);
-#pragma unroll
-              for (int q = 0; q < 8; ++q) o2[c0 / 2 + q] = fmul2(fadd2(o2[c0 / 2 + q], pk2(w[2 * q], w[2 * q + 1])), al2);
-            }
-          }
-        }
-        tc_fence_before();
-        mbar_arrive(&o_empty[so]);
-      }
-      l = l * alpha + sum;
+      tc_fence_before();
+      mbar_arrive(&p_full[g]);
+      float a0, a1;
+      upk2(fadd2(fadd2(sum2[0], sum2[1]), fadd2(sum2[2], sum2[3])), a0, a1);
+      l += a0 + a1;
     }
-    {  // last tile's partial product; the two halves of the row sum are combined through shared memory
-      const int so = (nt - 1) & 1;
-      float* xb = xbuf + (size_t)(nt & 1) * 256;
-      xb[half * 128 + rowi] = l;
-      asm volatile("bar.sync 2, 256;" ::: "memory");
-      const float inv = 1.0f / (xb[rowi] + xb[128 + rowi]);
-      const uint64_t inv2 = pk2(inv, inv);
-      mbar_wait(&o_full[so], (uint32_t)(((nt - 1) >> 1) & 1));
+    if (ntm > 0) {  // normalise and store this thread's row
+      mbar_wait(&o_full[g], (uint32_t)((ntm - 1) & 1));
       tc_fence_after();
-      const uint32_t to = trow + (uint32_t)(256 + so * 128 + half * dc);
-      bf16* orow = (bf16*)p.out + ((size_t)r * N + (i < N ? i : 0)) * p.C + h * d + half * dc;
-#pragma unroll
-      for (int c0 = 0; c0 < DH; c0 += 16) {
-        if (c0 < dc) {
-          float w[16];
-          tmem_ld16(to + (uint32_t)c0, w);
-          if (i < N) {
-            uint32_t ow[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              float a0, a1;
-              upk2(fmul2(fadd2(o2[c0 / 2 + q], pk2(w[2 * q], w[2 * q + 1])), inv2), a0, a1);
-              ow[q] = pack2(a0, a1);
-            }
-            *reinterpret_cast<uint4*>(orow + c0) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-            *reinterpret_cast<uint4*>(orow + c0 + 8) = make_uint4(ow[4], ow[5], ow[6], ow[7]);
-          }
+      const float inv = 1.0f / l;
+      bf16* orow = (bf16*)p.out + ((size_t)r * N + (i < N ? i : 0)) * p.C + h * d;
+#pragma unroll 1
+      for (int c0 = 0; c0 < d; c0 += 16) {
+        float w[16];
+        tmem_ld16(to + (uint32_t)c0, w);
+        if (i < N) {
+          *reinterpret_cast<uint4*>(orow + c0) =
+              make_uint4(pack2(w[0] * inv, w[1] * inv), pack2(w[2] * inv, w[3] * inv), pack2(w[4] * inv, w[5] * inv), pack2(w[6] * inv, w[7] * inv));
+          *reinterpret_cast<uint4*>(orow + c0 + 8) =
+              make_uint4(pack2(w[8] * inv, w[9] * inv), pack2(w[10] * inv, w[11] * inv), pack2(w[12] * inv, w[13] * inv), pack2(w[14] * inv, w[15] * inv));
         }
       }
     }
@@ -586,16 +567,14 @@ bool attn_flash_supported(const AttnParams& p) {
 }
 
 static size_t attn_flash_smem(int d) {
-  const int DB = (d + 63) / 64, NS = d <= 64 ? 4 : 2;
-  // Q + K / V rings + two P buffers + 28 barriers (+ TMEM slot) + the row max / sum exchange; the dynamic shared-memory
-  // window is 1024-byte aligned (no manual round-up in the kernel, hence no slack here: d = 128 uses 226.2 of 227 KB)
-  return (size_t)(1 + 2 * NS) * DB * 128 * 128 + 2 * (2 * 128 * 128) + 28 * 8 + 2 * 2 * 128 * 4;
+  // two Q tiles + K / V rings + two P tiles + 25 barriers + the TMEM slot; the dynamic shared-memory window is 1024-byte
+  // aligned (no manual round-up in the kernel, hence no slack here: d = 128 uses 224.2 of 227 KB)
+  const int DB = (d + 63) / 64, NSK = d <= 64 ? 4 : 2, NSV = d <= 64 ? 2 : 1;
+  return (size_t)(2 + NSK + NSV) * DB * 128 * 128 + 2 * (2 * 128 * 128) + 26 * 8;
 }
 
 cudaError_t attn_flash_init() {
-  cudaError_t e = cudaFuncSetAttribute(attn_flash_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_flash_smem(64));
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(attn_flash_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_flash_smem(128));
+  return cudaFuncSetAttribute(attn_flash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_flash_smem(128));
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -633,17 +612,16 @@ cudaError_t launch_attention_flash(const AttnParams& p, bool pdl, cudaStream_t s
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((p.N + 127) / 128, p.H, p.B2);
+  cfg.gridDim = dim3((p.N + kBM - 1) / kBM, p.H, p.B2);
   cfg.blockDim = dim3(kFaThreads);
-  cfg.dynamicSmemBytes = attn_flash_smem(p.d <= 64 ? 64 : 128);
+  cfg.dynamicSmemBytes = attn_flash_smem(p.d);
   cfg.stream = stream;
   cudaLaunchAttribute attrs[1];
   attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attrs[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attrs;
   cfg.numAttrs = pdl ? 1 : 0;
-  if (p.d <= 64) return cudaLaunchKernelEx(&cfg, attn_flash_kernel<64>, p, tm, use_tma);
-  return cudaLaunchKernelEx(&cfg, attn_flash_kernel<128>, p, tm, use_tma);
+  return cudaLaunchKernelEx(&cfg, attn_flash_kernel, p, tm, use_tma);
 }
 
 }  // namespace jen1
