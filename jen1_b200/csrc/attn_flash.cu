@@ -21,6 +21,7 @@
 // completely above the diagonal are skipped.  Keys beyond the key count are zero-filled and excluded from the softmax.
 #include <cuda.h>
 #include <float.h>
+#include <stdio.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -84,9 +85,24 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+#ifndef JEN1_FA_HINT
+#define JEN1_FA_HINT 0  // A/B: > 0 = suspend-time hint (ns) of the MMA issuer's try_wait
+#endif
 __device__ __forceinline__ void mma_wait(uint64_t* bar, uint32_t parity) {
 #if JEN1_FA_POLL
   mbar_wait(bar, parity);
+#elif JEN1_FA_HINT > 0
+  const uint32_t a = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(a), "r"(parity), "r"((uint32_t)JEN1_FA_HINT)
+        : "memory");
+  } while (!done);
 #else
   mbar_wait_sleep(bar, parity);
 #endif
@@ -103,6 +119,16 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// one lane of a converged warp (elect.sync): the issue pattern the compiler recognises as uniform
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -202,17 +228,36 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) 
 // few key tiles practically never happens.
 constexpr float kTau = 8.0f;
 
+// JEN1_FA_TRACE=1 (debug build, scripts/build_variant.py): CTA (0,0,0) records clock64 at the pipeline hand-offs of its
+// first 36 key tiles and prints them at the end (MMA issuer: P^0_j seen / P^0_j V_j issued; thread 0: S seen, P written,
+// P_{j-1} V_{j-1} seen)
+#ifndef JEN1_FA_TRACE
+#define JEN1_FA_TRACE 0
+#endif
+#if JEN1_FA_TRACE
+#define FA_TR(arr, j) do { if (trace_on && (j) < 36) arr[j] = clock64(); } while (0)
+#else
+#define FA_TR(arr, j) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(kFaThreads, 1) attn_flash_kernel(const __grid_constant__ AttnParams p,
                                                                    const __grid_constant__ CUtensorMap tmap, const int use_tma) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int i0 = blockIdx.x * kBM, h = blockIdx.y, r = blockIdx.z;
+  // causal: the query blocks with the most key tiles are scheduled first (longest job first)
+  const int i0 = (p.causal ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x) * kBM, h = blockIdx.y, r = blockIdx.z;
   const int d = p.d, M = p.M, N = p.N;
   const int DB = (d + 63) >> 6;                       // 64-channel blocks of the head dim
   const int sh = d == 16 ? 1 : (d == 32 ? 2 : (d == 64 ? 3 : 4));
   const int cpr = 1 << sh;                            // 16-byte chunks per head row
   const uint32_t tile_bytes = (uint32_t)DB * 128u * 128u;  // one Q / K / V tile of 128 rows
-  const int NSK = d <= 64 ? 4 : 2, NSV = d <= 64 ? 2 : 1;  // K / V ring depths (what fits next to two Q and two P tiles)
+  // K / V ring depths (what fits next to two Q and two P tiles).  S_{j+1} is issued a whole tile period ahead of its use,
+  // so K_{j+1} (loaded once S_j has completed) has that period to arrive even with ONE stage; V_j is needed at the END of
+  // tile j, one stage would put its load (started after P_{j-1} V_{j-1}) on the critical path: d = 128 gives V the two stages
+#ifndef JEN1_FA_NSK128
+#define JEN1_FA_NSK128 1
+#endif
+  const int NSK = d <= 64 ? 4 : JEN1_FA_NSK128, NSV = d <= 64 ? 2 : 3 - JEN1_FA_NSK128;
   uint8_t* Qs = smem;                                 // [2 query tiles]
   uint8_t* Ks = Qs + 2 * tile_bytes;                  // [NSK stages]
   uint8_t* Vs = Ks + NSK * tile_bytes;                // [NSV stages]
@@ -255,6 +300,11 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_flash_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+#if JEN1_FA_TRACE
+  const bool trace_on = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  long long tr0[36], tr1[36], tr2[36], tr3[36];
+  const long long tr_base = clock64();
+#endif
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
 
@@ -362,60 +412,77 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_flash_kernel(const __grid_
     }
   } else if (warp == 4) {
     // ======================================================================== MMA issuer
-    if (lane == 0) {
+    // The whole warp runs the (warp-uniform) control flow and one elected lane issues: with the issue code under a
+    // divergent `lane == 0` branch the compiler wraps every tcgen05 instruction in an elect / branch loop and rebuilds
+    // the descriptors per instruction (~85 clocks per MMA measured -- slower than the tensor pipe executes them).
+    // Descriptors are built once; a K step only adds a constant to the 14-bit start-address field.
+    {
       const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBN >> 3) << 17) | ((128u >> 4) << 24);
       const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(d >> 3) << 17) | ((128u >> 4) << 24);
-      const uint32_t q_addr = smem_u32(Qs), p_addr = smem_u32(Ps);
+      const uint64_t qd = make_desc_sw128(smem_u32(Qs), 16u, 1024u), kd = make_desc_sw128(smem_u32(Ks), 16u, 1024u);
+      const uint64_t pd = make_desc_sw128(smem_u32(Ps), 16u, 1024u), vd = make_desc_sw128(smem_u32(Vs), 128u * 128u, 1024u);
+      const uint32_t tile16 = tile_bytes >> 4;  // descriptor address units (16 bytes)
+      const int nk = d >> 4;                    // K steps of S = Q K^T
       // S^g_j = Q^g K_j^T -> TMEM columns [g * 128, +128)
       auto issue_s = [&](int g, int j) {
         if (j > 0) mbar_wait(&s_empty[g], (uint32_t)((j - 1) & 1));  // the softmax warps hold S^g_{j-1} in registers
         tc_fence_after();
-        const uint32_t k_addr = smem_u32(Ks + (size_t)(j % NSK) * tile_bytes);
-        uint32_t acc = 0;
-        for (int db = 0; db < DB; ++db) {
-          const int kmax = min(4, (d - db * 64) / 16);
-          for (int kk = 0; kk < kmax; ++kk) {
-            const uint64_t ad = make_desc_sw128(q_addr + (uint32_t)g * tile_bytes + (uint32_t)db * 128u * 128u + (uint32_t)kk * 32u, 16u, 1024u);
-            const uint64_t bd = make_desc_sw128(k_addr + (uint32_t)db * 128u * 128u + (uint32_t)kk * 32u, 16u, 1024u);
-            umma_bf16(tmem_base + (uint32_t)(g * 128), ad, bd, idesc_s, acc);
-            acc = 1;
+        const uint64_t ad = qd + (uint64_t)((uint32_t)g * tile16), bd = kd + (uint64_t)((uint32_t)(j % NSK) * tile16);
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {  // 64-channel block kk >> 2 (16 KB apart), 32 bytes per K step inside the swizzle atom
+            const uint64_t off = (uint64_t)((kk >> 2) * 1024 + (kk & 3) * 2);
+            if (kk < nk) umma_bf16(tmem_base + (uint32_t)(g * 128), ad + off, bd + off, idesc_s, kk > 0 ? 1u : 0u);
           }
+          umma_commit(&s_full[g]);
         }
-        umma_commit(&s_full[g]);
+        __syncwarp();
       };
       // O^g += P^g_j V_j -> TMEM columns [256 + g * 128, +d): accumulates over ALL key tiles
       auto issue_o = [&](int g, int j) {
         mma_wait(&p_full[g], (uint32_t)(j & 1));  // P^g_j written (and O^g rescaled if the row maxima moved)
+        if (g == 0) FA_TR(tr0, j); else FA_TR(tr2, j);
         tc_fence_after();
-        const uint32_t v_addr = smem_u32(Vs + (size_t)(j % NSV) * tile_bytes);
-        for (int k16 = 0; k16 < kBN / 16; ++k16) {
-          const uint64_t ad = make_desc_sw128(p_addr + (uint32_t)g * kPBytes + (uint32_t)(k16 >> 2) * 128u * 128u + (uint32_t)(k16 & 3) * 32u, 16u, 1024u);
-          const uint64_t bd = make_desc_sw128(v_addr + (uint32_t)k16 * 2048u, 128u * 128u, 1024u);
-          umma_bf16(tmem_base + (uint32_t)(256 + g * 128), ad, bd, idesc_o, (j > 0 || k16 > 0) ? 1u : 0u);
+        const uint64_t ad = pd + (uint64_t)((uint32_t)g * (kPBytes >> 4)), bd = vd + (uint64_t)((uint32_t)(j % NSV) * tile16);
+        if (elect_one()) {
+#pragma unroll
+          for (int k16 = 0; k16 < kBN / 16; ++k16)
+            umma_bf16(tmem_base + (uint32_t)(256 + g * 128), ad + (uint64_t)((k16 >> 2) * 1024 + (k16 & 3) * 2), bd + (uint64_t)(k16 * 128),
+                      idesc_o, (j > 0 || k16 > 0) ? 1u : 0u);
+          umma_commit(&o_full[g]);
         }
-        umma_commit(&o_full[g]);
+        __syncwarp();
+        if (g == 0) FA_TR(tr1, j); else FA_TR(tr3, j);
+      };
+      auto commit = [&](uint64_t* bar) {
+        if (elect_one()) umma_commit(bar);
+        __syncwarp();
       };
       mbar_wait(q_full, 0);
       mma_wait(&k_full[0], 0);
       if (ntg[0] > 0) issue_s(0, 0);
       if (ntg[1] > 0) issue_s(1, 0);
-      umma_commit(&k_empty[0]);
+      commit(&k_empty[0]);
       for (int j = 0; j < nt; ++j) {
         if (j + 1 < nt) {  // the next logits of both query tiles are computed while the softmax warps work on tile j
           const int ks = (j + 1) % NSK;
           mma_wait(&k_full[ks], (uint32_t)(((j + 1) / NSK) & 1));
           if (j + 1 < ntg[0]) issue_s(0, j + 1);
           if (j + 1 < ntg[1]) issue_s(1, j + 1);
-          umma_commit(&k_empty[ks]);  // K_{j+1} is free once both S_{j+1} are complete
+          commit(&k_empty[ks]);  // K_{j+1} is free once both S_{j+1} are complete
         }
         const int vs = j % NSV;
         mma_wait(&v_full[vs], (uint32_t)((j / NSV) & 1));
         if (j < ntg[0]) issue_o(0, j);
         if (j < ntg[1]) issue_o(1, j);
-        umma_commit(&v_empty[vs]);  // V_j is free once both P_j V_j are complete
+        commit(&v_empty[vs]);  // V_j is free once both P_j V_j are complete
       }
+#if JEN1_FA_TRACE
+      if (trace_on && lane == 0)
+        for (int j = 0; j < min(nt, 36); ++j)
+          printf("[fa-mma] j %2d  P0 seen %7lld  PV0 issued %7lld  P1 seen %7lld  PV1 issued %7lld\n", j, tr0[j] - tr_base, tr1[j] - tr_base, tr2[j] - tr_base, tr3[j] - tr_base);
+#endif
     }
-    __syncwarp();
   } else {
     // ======================================================================== online softmax
     // Warpgroup g (warps 0-3: g = 0, warps 8-11: g = 1) owns query tile g; thread == query row == TMEM lane, with the
@@ -438,7 +505,9 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_flash_kernel(const __grid_
     float m = -FLT_MAX, l = 0.f;
     uint8_t* prow = Ps + (size_t)g * kPBytes + (size_t)rowi * 128;
     for (int j = 0; j < ntm; ++j) {
+      FA_TR(tr3, j);
       mbar_wait(&s_full[g], (uint32_t)(j & 1));
+      FA_TR(tr0, j);
       tc_fence_after();
       float v[128];
       tmem_ld64(ts, *reinterpret_cast<float(*)[64]>(&v[0]));
@@ -467,15 +536,13 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_flash_kernel(const __grid_
           if (q <= kmaxv) mx = fmaxf(mx, v[q]);
       }
       mx = (mx == -FLT_MAX) ? mx : mx * sc;  // sc > 0: max commutes with the scaling
-      if (j > 0) {  // P^g_{j-1} V_{j-1} has completed: the P tile is free and O^g is stable
-        mbar_wait(&o_full[g], (uint32_t)((j - 1) & 1));
-        tc_fence_after();
-      }
       const bool grow = mx > m + kTau || m == -FLT_MAX;
       if (__any_sync(0xffffffffu, grow)) {  // rare after the first tiles: move this warp's rows to their new maxima
         const float m_new = grow ? fmaxf(mx, m) : m;
         const float alpha = ex2_fast(m - m_new);  // 1 for the rows that stay; 0 for a row without any key so far
         if (j > 0) {
+          mbar_wait(&o_full[g], (uint32_t)((j - 1) & 1));  // P^g_{j-1} V_{j-1} has completed: O^g is stable
+          tc_fence_after();
 #pragma unroll 1
           for (int c0 = 0; c0 < d; c0 += 16) {
             float w[16];
@@ -488,12 +555,15 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_flash_kernel(const __grid_
         l *= alpha;
         m = m_new;
       }
+      // The exponentials go to registers first (the logits die as they are consumed: no extra pressure) and the P tile is
+      // only written afterwards: the wait for P^g_{j-1} V_{j-1}, which reads that tile, then comes a whole exponential
+      // phase after its MMA was issued instead of right after the maximum
       const uint64_t nm2 = pk2(-m, -m);
       uint64_t sum2[4] = {0ull, 0ull, 0ull, 0ull};
+      uint32_t pw[64];
       if (!edge) {
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {  // 8 keys = one 16-byte chunk of the P row; chunks 0-7 key block 0, 8-15 key block 1
-          uint32_t pw[4];
+        for (int c = 0; c < 16; ++c) {  // 8 keys = one 16-byte chunk of the P row
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             float e0, e1;
@@ -501,14 +571,12 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_flash_kernel(const __grid_
             e0 = ex2_fast(e0);
             e1 = ex2_fast(e1);
             sum2[q] = fadd2(sum2[q], pk2(e0, e1));  // (the bf16 rounding of P happens in pack2; the row sum keeps the unrounded terms)
-            pw[q] = pack2(e0, e1);
+            pw[c * 4 + q] = pack2(e0, e1);
           }
-          *reinterpret_cast<uint4*>(prow + (size_t)(c >> 3) * 128 * 128 + (((c & 7) ^ (rowi & 7)) * 16)) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
         }
       } else {
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
-          uint32_t pw[4];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int k0 = c * 8 + 2 * q;
@@ -516,11 +584,17 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_flash_kernel(const __grid_
             if (k0 > kmaxv) e0 = 0.0f;
             if (k0 + 1 > kmaxv) e1 = 0.0f;
             sum2[q] = fadd2(sum2[q], pk2(e0, e1));
-            pw[q] = pack2(e0, e1);
+            pw[c * 4 + q] = pack2(e0, e1);
           }
-          *reinterpret_cast<uint4*>(prow + (size_t)(c >> 3) * 128 * 128 + (((c & 7) ^ (rowi & 7)) * 16)) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
         }
       }
+      FA_TR(tr1, j);
+      if (j > 0) mbar_wait(&o_full[g], (uint32_t)((j - 1) & 1));  // P^g_{j-1} V_{j-1} has completed: the P tile is free
+      FA_TR(tr2, j);
+#pragma unroll
+      for (int c = 0; c < 16; ++c)  // chunks 0-7: key block 0, 8-15: key block 1
+        *reinterpret_cast<uint4*>(prow + (size_t)(c >> 3) * 128 * 128 + (((c & 7) ^ (rowi & 7)) * 16)) =
+            make_uint4(pw[c * 4], pw[c * 4 + 1], pw[c * 4 + 2], pw[c * 4 + 3]);
       fence_async_smem();
       tc_fence_before();
       mbar_arrive(&p_full[g]);
@@ -528,6 +602,11 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_flash_kernel(const __grid_
       upk2(fadd2(fadd2(sum2[0], sum2[1]), fadd2(sum2[2], sum2[3])), a0, a1);
       l += a0 + a1;
     }
+#if JEN1_FA_TRACE
+    if (trace_on && (tid == 0 || tid == 256))
+      for (int j = 0; j < min(ntm, 36); ++j)
+        printf("[fa-sm%d] j %2d  tile start %7lld  S seen %7lld  exps done %7lld  PV(j-1) seen %7lld\n", g, j, tr3[j] - tr_base, tr0[j] - tr_base, tr1[j] - tr_base, tr2[j] - tr_base);
+#endif
     if (ntm > 0) {  // normalise and store this thread's row
       mbar_wait(&o_full[g], (uint32_t)((ntm - 1) & 1));
       tc_fence_after();
@@ -569,7 +648,7 @@ bool attn_flash_supported(const AttnParams& p) {
 static size_t attn_flash_smem(int d) {
   // two Q tiles + K / V rings + two P tiles + 25 barriers + the TMEM slot; the dynamic shared-memory window is 1024-byte
   // aligned (no manual round-up in the kernel, hence no slack here: d = 128 uses 224.2 of 227 KB)
-  const int DB = (d + 63) / 64, NSK = d <= 64 ? 4 : 2, NSV = d <= 64 ? 2 : 1;
+  const int DB = (d + 63) / 64, NSK = d <= 64 ? 4 : 2, NSV = d <= 64 ? 2 : 1;  // (d = 128: three stages in all, see the kernel)
   return (size_t)(2 + NSK + NSV) * DB * 128 * 128 + 2 * (2 * 128 * 128) + 26 * 8;
 }
 
