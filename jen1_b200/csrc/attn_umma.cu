@@ -50,6 +50,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// one lane of a converged warp (elect.sync)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -230,34 +240,38 @@ __global__ void __launch_bounds__(kAtThreads, 1) attn_umma_kernel(const __grid_c
   fence_async_smem();
   mbar_arrive(&bars[0]);
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 4) {
     // ======================================================================== MMA issuer
+    // (warp-uniform control flow, one elected lane issues, descriptors built once: under a divergent `lane == 0` branch
+    //  every tcgen05 instruction is wrapped in an elect-and-branch loop -- ~85 clocks per MMA, see attn_flash.cu)
     // instruction descriptor: fp32 accumulate, bf16 A/B, M = 128; bit 16 = B operand is MN-major
     const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(g.KP >> 3) << 17) | ((128u >> 4) << 24);
     const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(d >> 3) << 17) | ((128u >> 4) << 24);
+    const uint64_t qd = make_desc_sw128(smem_u32(Qs), 16u, 1024u), kd = make_desc_sw128(smem_u32(Ks), 16u, 1024u);
+    const uint64_t pd = make_desc_sw128(smem_u32(Ps), 16u, 1024u), vd = make_desc_sw128(smem_u32(Vs), (uint32_t)g.KR * 128u, 1024u);
+    const uint32_t kblk16 = (uint32_t)g.KR * 8u;  // one 64-channel block of K rows in descriptor address units (16 bytes)
+    const int nk = d >> 4;
     mbar_wait(&bars[0], 0);
     tc_fence_after();
-    uint32_t acc = 0;
-    for (int db = 0; db < g.DB; ++db) {
-      const int kmax = min(4, (d - db * 64) / 16);
-      for (int kk = 0; kk < kmax; ++kk) {
-        const uint64_t ad = make_desc_sw128(smem_u32(Qs) + (uint32_t)db * 128u * 128u + (uint32_t)kk * 32u, 16u, 1024u);
-        const uint64_t bd = make_desc_sw128(smem_u32(Ks) + (uint32_t)db * (uint32_t)g.KR * 128u + (uint32_t)kk * 32u, 16u, 1024u);
-        umma_bf16(tmem_base, ad, bd, idesc_s, acc);
-        acc = 1;
-      }
+    if (elect_one()) {
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk)  // 64-channel block kk >> 2, 32 bytes per K step inside the swizzle atom
+        if (kk < nk)
+          umma_bf16(tmem_base, qd + (uint64_t)((kk >> 2) * 1024 + (kk & 3) * 2), kd + (uint64_t)((uint32_t)(kk >> 2) * kblk16 + (uint32_t)(kk & 3) * 2u),
+                    idesc_s, kk > 0 ? 1u : 0u);
+      umma_commit(&bars[1]);
     }
-    umma_commit(&bars[1]);
+    __syncwarp();
     mbar_wait(&bars[2], 0);
     tc_fence_after();
-    acc = 0;
-    for (int k16 = 0; k16 < g.KP / 16; ++k16) {
-      const uint64_t ad = make_desc_sw128(smem_u32(Ps) + (uint32_t)(k16 >> 2) * 128u * 128u + (uint32_t)(k16 & 3) * 32u, 16u, 1024u);
-      const uint64_t bd = make_desc_sw128(smem_u32(Vs) + (uint32_t)k16 * 2048u, (uint32_t)g.KR * 128u, 1024u);
-      umma_bf16(tmem_base, ad, bd, idesc_o, acc);
-      acc = 1;
+    if (elect_one()) {
+      const int n16 = g.KP >> 4;
+#pragma unroll 4
+      for (int k16 = 0; k16 < n16; ++k16)
+        umma_bf16(tmem_base, pd + (uint64_t)((k16 >> 2) * 1024 + (k16 & 3) * 2), vd + (uint64_t)(k16 * 128), idesc_o, k16 > 0 ? 1u : 0u);
+      umma_commit(&bars[3]);
     }
-    umma_commit(&bars[3]);
+    __syncwarp();
   } else if (warp < 4) {
     // ======================================================================== softmax + epilogue (thread == query row)
     const int i = i0 + tid;

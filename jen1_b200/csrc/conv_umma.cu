@@ -28,7 +28,7 @@
 //     while unit k is transformed.
 //
 // Warp roles (192 threads): warps 0-3 build panels, then run the epilogue (TMEM lane quarter = warp index);
-// warp 4 lane 0 streams weights; warp 5 allocates TMEM and its lane 0 issues tcgen05.mma.
+// warp 4 streams weights; warp 5 allocates TMEM and issues tcgen05.mma (one elected lane each, warp-uniform control flow).
 #include <stdlib.h>
 #include <string.h>
 
@@ -107,6 +107,16 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// one lane of a converged warp (elect.sync): the issue pattern the compiler treats as uniform
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -286,73 +296,78 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
   const float4 bias4 = (warp < 4 && p.bias) ? __ldg(reinterpret_cast<const float4*>(p.bias + mt * 128) + lane)
                                             : make_float4(0.f, 0.f, 0.f, 0.f);
 
+  // Warps 4 and 5 run their (warp-uniform) control flow with all lanes and ONE ELECTED lane issues the bulk copies / MMAs:
+  // under a divergent `lane == 0` branch the compiler wraps every UBLKCP / UTCHMMA / UTCBAR in an elect-and-branch loop and
+  // rebuilds its operands per instruction (measured in attn_flash.cu: ~85 clocks per MMA, slower than the tensor pipe).
   if (warp == 4) {
     // ======================================================================== weight streamer
-    if (lane == 0) {
-      int s = 0, k = 0;
-      for (int t = st0; t < st1; ++t) {
-        const bool s1 = t >= pl.steps0;
-        const int ntp = s1 ? 1 : ntaps0;
-        const bf16* src = s1 ? A.w1 + ((size_t)mt * pl.steps1 + (t - pl.steps0)) * (kABytes / 2)
-                             : A.w0 + (((size_t)(mt * p.nphase + z) * pl.steps0 + t) * ntaps0) * (kABytes / 2);
-        for (int j = 0; j < ntp; ++j) {
-          if (k > 0) mbar_wait(&a_empty[s], (uint32_t)((k - 1) & 1));
+    int s = 0, k = 0;
+    for (int t = st0; t < st1; ++t) {
+      const bool s1 = t >= pl.steps0;
+      const int ntp = s1 ? 1 : ntaps0;
+      const bf16* src = s1 ? A.w1 + ((size_t)mt * pl.steps1 + (t - pl.steps0)) * (kABytes / 2)
+                           : A.w0 + (((size_t)(mt * p.nphase + z) * pl.steps0 + t) * ntaps0) * (kABytes / 2);
+      for (int j = 0; j < ntp; ++j) {
+        if (k > 0) mbar_wait(&a_empty[s], (uint32_t)((k - 1) & 1));
+        if (elect_one()) {
           mbar_expect_tx(&a_full[s], kABytes);
           bulk_g2s(a_ring + (size_t)s * kABytes, src + (size_t)j * (kABytes / 2), kABytes, &a_full[s]);
-          if (++s == pl.stages) {
-            s = 0;
-            ++k;
-          }
+        }
+        __syncwarp();
+        if (++s == pl.stages) {
+          s = 0;
+          ++k;
         }
       }
     }
-    __syncwarp();
   } else if (warp == 5) {
     // ======================================================================== MMA issuer
-    if (lane == 0) {
-      // tap geometry: panel row offset of tap j (sub-panel of its residue + whole-row shift)
-      for (int j = 0; j < ntaps0; ++j) {
-        const int d = p.seg[0].shift0 + j * p.seg[0].shift_step;
-        int rho = d % f0;
-        if (rho < 0) rho += f0;
-        const int a = (d - rho) / f0;
-        tapg[j] = make_int2(rho * pl.PS + (a - pl.amin), 0);
-      }
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
-      int s = 0, k = 0;
-      uint32_t acc = 0;
-      for (int t = st0; t < st1; ++t) {
-        const int n = t - st0, pb = n & 1;
-        const bool s1 = t >= pl.steps0;
-        const int ntp = s1 ? 1 : ntaps0;
-        mbar_wait(&p_full[pb], (uint32_t)((n >> 1) & 1));
-        tc_fence_after();
-        const uint32_t pbase = smem_u32(panels + (size_t)pb * panel_bytes);
-        for (int j = 0; j < ntp; ++j) {
-          const uint32_t prow = s1 ? 0u : (uint32_t)tapg[j].x;
-          mbar_wait(&a_full[s], (uint32_t)(k & 1));
-          tc_fence_after();
-          if (t == st0 && j == 0) TL_MARK(9);
-          // K advances by 32 bytes inside the swizzle atom: +2 in the (address >> 4) field of the descriptor
-          const uint64_t ad = make_desc_sw128(smem_u32(a_ring + (size_t)s * kABytes));
-          const uint64_t bd = make_desc_sw128(pbase + prow * 128u);
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            umma_bf16(tmem_base, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc, acc);
-            acc = 1;
-          }
-          umma_commit(&a_empty[s]);
-          if (++s == pl.stages) {
-            s = 0;
-            ++k;
-          }
-        }
-        umma_commit(&p_empty[pb]);
-      }
-      umma_commit(acc_full);
-      TL_MARK(10);
+    // tap geometry: panel row offset of tap j (sub-panel of its residue + whole-row shift); one tap per lane
+    if (lane < ntaps0) {
+      const int d = p.seg[0].shift0 + lane * p.seg[0].shift_step;
+      int rho = d % f0;
+      if (rho < 0) rho += f0;
+      const int a = (d - rho) / f0;
+      tapg[lane] = make_int2(rho * pl.PS + (a - pl.amin), 0);
     }
     __syncwarp();
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
+    const uint64_t ad0 = make_desc_sw128(smem_u32(a_ring)), bd0 = make_desc_sw128(smem_u32(panels));
+    int s = 0, k = 0;
+    uint32_t acc = 0;
+    for (int t = st0; t < st1; ++t) {
+      const int n = t - st0, pb = n & 1;
+      const bool s1 = t >= pl.steps0;
+      const int ntp = s1 ? 1 : ntaps0;
+      mbar_wait(&p_full[pb], (uint32_t)((n >> 1) & 1));
+      tc_fence_after();
+      const uint32_t pbase16 = (uint32_t)pb * (panel_bytes >> 4);  // descriptor address units (16 bytes)
+      for (int j = 0; j < ntp; ++j) {
+        const uint32_t prow = s1 ? 0u : (uint32_t)tapg[j].x;
+        mbar_wait(&a_full[s], (uint32_t)(k & 1));
+        tc_fence_after();
+        if (t == st0 && j == 0 && lane == 0) TL_MARK(9);
+        // K advances by 32 bytes inside the swizzle atom: +2 in the (address >> 4) field of the descriptor
+        const uint64_t ad = ad0 + (uint64_t)((uint32_t)s * (kABytes >> 4));
+        const uint64_t bd = bd0 + (uint64_t)(pbase16 + prow * 8u);
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) umma_bf16(tmem_base, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc, (acc | (uint32_t)kk) ? 1u : 0u);
+          umma_commit(&a_empty[s]);
+        }
+        __syncwarp();
+        acc = 1;
+        if (++s == pl.stages) {
+          s = 0;
+          ++k;
+        }
+      }
+      if (elect_one()) umma_commit(&p_empty[pb]);
+      __syncwarp();
+    }
+    if (elect_one()) umma_commit(acc_full);
+    __syncwarp();
+    if (lane == 0) TL_MARK(10);
   } else {
     // ======================================================================== panel producers, then epilogue
     const ConvSeg& S0 = p.seg[0];

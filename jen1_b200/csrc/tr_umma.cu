@@ -90,6 +90,16 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// one lane of a converged warp (elect.sync)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
@@ -237,117 +247,120 @@ __global__ void __launch_bounds__(kThreads, 1) tr_umma_kernel(const __grid_const
 
   const int n_ops = P.n_ops;
 
+  // Warps 4 and 5 run their warp-uniform control flow with all lanes and one ELECTED lane issues (see conv_umma.cu: a
+  // divergent `lane == 0` issuer costs ~85 clocks per tcgen05.mma -- the "2.3 us accumulate phase" of the first version)
   if (warp == 4) {
     // ======================================================================== weight streamer (runs ahead of the ops)
-    if (lane == 0) {
-      int s = 0, k = 0;
-      for (int oi = 0; oi < n_ops; ++oi) {
-        const TrOp& op = P.ops[oi];
-        if (op.type != TR_GEMM) continue;
-        const int kb_n = op.K >> 6, mtiles = op.Cout >> 7;
-        for (int mt = crank; mt < mtiles; mt += CS) {
-          const bf16* src = op.w + (size_t)mt * kb_n * (kABytes / 2);
-          for (int kb = 0; kb < kb_n; ++kb) {
-            if (k > 0) mbar_wait(&a_empty[s], (uint32_t)((k - 1) & 1));
+    int s = 0, k = 0;
+    for (int oi = 0; oi < n_ops; ++oi) {
+      const TrOp& op = P.ops[oi];
+      if (op.type != TR_GEMM) continue;
+      const int kb_n = op.K >> 6, mtiles = op.Cout >> 7;
+      for (int mt = crank; mt < mtiles; mt += CS) {
+        const bf16* src = op.w + (size_t)mt * kb_n * (kABytes / 2);
+        for (int kb = 0; kb < kb_n; ++kb) {
+          if (k > 0) mbar_wait(&a_empty[s], (uint32_t)((k - 1) & 1));
+          if (elect_one()) {
             mbar_expect_tx(&a_full[s], kABytes);
             bulk_g2s(ring + (size_t)s * kABytes, src + (size_t)kb * (kABytes / 2), kABytes, &a_full[s]);
+          }
+          __syncwarp();
+          if (++s == kStages) {
+            s = 0;
+            ++k;
+          }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ======================================================================== MMA issuer
+    int s = 0, k = 0;
+    uint32_t n_panel = 0, n_acc_use = 0, n_p = 0;  // completed phases of panel_full / uses of the accumulator / p_full
+    auto commit = [&](uint64_t* bar) {
+      if (elect_one()) umma_commit(bar);
+      __syncwarp();
+    };
+    const uint64_t ring_d = make_desc_sw128(smem_u32(ring), 16u, 1024u), panel_d = make_desc_sw128(smem_u32(panel), 16u, 1024u);
+    for (int oi = 0; oi < n_ops; ++oi) {
+      const TrOp& op = P.ops[oi];
+      if (op.type == TR_GEMM) {
+        const int kb_n = op.K >> 6, mtiles = op.Cout >> 7;
+        if (crank >= mtiles) continue;
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
+        mbar_wait(panel_full, n_panel & 1);
+        ++n_panel;
+        tc_fence_after();
+        if (P.timeline && crank == 0 && row == 0 && lane == 0) P.timeline[oi * 8 + 6] = clock64();
+        for (int mt = crank; mt < mtiles; mt += CS) {
+          if (n_acc_use > 0) {  // the previous accumulator contents have been read out
+            mbar_wait(acc_empty, (n_acc_use - 1) & 1);
+            tc_fence_after();
+          }
+          for (int kb = 0; kb < kb_n; ++kb) {
+            mbar_wait(&a_full[s], (uint32_t)(k & 1));
+            tc_fence_after();
+            const uint64_t ad = ring_d + (uint64_t)((uint32_t)s * (kABytes >> 4));
+            const uint64_t bd = panel_d + (uint64_t)((uint32_t)kb * (uint32_t)NT * 8u);
+            if (elect_one()) {
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) umma_bf16(tmem_base, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc, (kb | kk) ? 1u : 0u);
+              umma_commit(&a_empty[s]);
+            }
+            __syncwarp();
             if (++s == kStages) {
               s = 0;
               ++k;
             }
           }
+          commit(acc_full);
+          ++n_acc_use;
+          if (P.timeline && crank == 0 && row == 0 && mt == crank && lane == 0) P.timeline[oi * 8 + 7] = clock64();
         }
-      }
-    }
-    __syncwarp();
-  } else if (warp == 5) {
-    // ======================================================================== MMA issuer
-    if (lane == 0) {
-      int s = 0, k = 0;
-      uint32_t n_panel = 0, n_acc_use = 0, n_p = 0;  // completed phases of panel_full / uses of the accumulator / p_full
-      for (int oi = 0; oi < n_ops; ++oi) {
-        const TrOp& op = P.ops[oi];
-        if (op.type == TR_GEMM) {
-          const int kb_n = op.K >> 6, mtiles = op.Cout >> 7;
-          if (crank >= mtiles) continue;
-          const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((128u >> 4) << 24);
+      } else {
+        // attention: heads crank, crank + CS, ...
+        const AttnTiles g = attn_tiles(op.M, P.d);
+        const int d = P.d;
+        const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(g.KP >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(d >> 3) << 17) | ((128u >> 4) << 24);
+        const int nk = d >> 4, n16 = g.KP >> 4;
+        for (int h = crank; h < P.H; h += CS) {
           mbar_wait(panel_full, n_panel & 1);
           ++n_panel;
           tc_fence_after();
-          if (P.timeline && crank == 0 && row == 0) P.timeline[oi * 8 + 6] = clock64();
-          const uint32_t pbase = smem_u32(panel);
-          for (int mt = crank; mt < mtiles; mt += CS) {
-            if (n_acc_use > 0) {  // the previous accumulator contents have been read out
-              mbar_wait(acc_empty, (n_acc_use - 1) & 1);
-              tc_fence_after();
-            }
-            uint32_t acc = 0;
-            for (int kb = 0; kb < kb_n; ++kb) {
-              mbar_wait(&a_full[s], (uint32_t)(k & 1));
-              tc_fence_after();
-              const uint64_t ad = make_desc_sw128(smem_u32(ring + (size_t)s * kABytes), 16u, 1024u);
-              const uint64_t bd = make_desc_sw128(pbase + (uint32_t)kb * (uint32_t)NT * 128u, 16u, 1024u);
+          if (n_acc_use > 0) {
+            mbar_wait(acc_empty, (n_acc_use - 1) & 1);
+            tc_fence_after();
+          }
+          const bool ext = prestage && op.cross && h == crank;
+          const uint32_t Qs = smem_u32(work), Ps = Qs + g.off_p;
+          const uint32_t Ks = ext ? smem_u32(kvx) : Qs + g.off_k, Vs = ext ? smem_u32(kvx) + kvx_half : Qs + g.off_v;
+          const uint64_t qd = make_desc_sw128(Qs, 16u, 1024u), kd = make_desc_sw128(Ks, 16u, 1024u);
+          const uint64_t pd = make_desc_sw128(Ps, 16u, 1024u), vd = make_desc_sw128(Vs, (uint32_t)g.KP * 128u, 1024u);
+          const uint32_t kblk16 = (uint32_t)g.KP * 8u;  // one 64-channel block of K rows in descriptor address units
+          if (elect_one()) {
 #pragma unroll
-              for (int kk = 0; kk < 4; ++kk) {
-                umma_bf16(tmem_base, ad + (uint64_t)(kk * 2), bd + (uint64_t)(kk * 2), idesc, acc);
-                acc = 1;
-              }
-              umma_commit(&a_empty[s]);
-              if (++s == kStages) {
-                s = 0;
-                ++k;
-              }
-            }
-            umma_commit(acc_full);
-            ++n_acc_use;
-            if (P.timeline && crank == 0 && row == 0 && mt == crank) P.timeline[oi * 8 + 7] = clock64();
-          }
-        } else {
-          // attention: heads crank, crank + CS, ...
-          const AttnTiles g = attn_tiles(op.M, P.d);
-          const int d = P.d;
-          const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(g.KP >> 3) << 17) | ((128u >> 4) << 24);
-          const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(d >> 3) << 17) | ((128u >> 4) << 24);
-          for (int h = crank; h < P.H; h += CS) {
-            mbar_wait(panel_full, n_panel & 1);
-            ++n_panel;
-            tc_fence_after();
-            if (n_acc_use > 0) {
-              mbar_wait(acc_empty, (n_acc_use - 1) & 1);
-              tc_fence_after();
-            }
-            const bool ext = prestage && op.cross && h == crank;
-            const uint32_t Qs = smem_u32(work), Ps = Qs + g.off_p;
-            const uint32_t Ks = ext ? smem_u32(kvx) : Qs + g.off_k, Vs = ext ? smem_u32(kvx) + kvx_half : Qs + g.off_v;
-            uint32_t acc = 0;
-            for (int db = 0; db < g.DB; ++db) {
-              const int kmax = min(4, (d - db * 64) / 16);
-              for (int kk = 0; kk < kmax; ++kk) {
-                const uint64_t ad = make_desc_sw128(Qs + (uint32_t)db * 128u * 128u + (uint32_t)kk * 32u, 16u, 1024u);
-                const uint64_t bd = make_desc_sw128(Ks + (uint32_t)db * (uint32_t)g.KP * 128u + (uint32_t)kk * 32u, 16u, 1024u);
-                umma_bf16(tmem_base, ad, bd, idesc_s, acc);
-                acc = 1;
-              }
-            }
+            for (int kk = 0; kk < 8; ++kk)
+              if (kk < nk)
+                umma_bf16(tmem_base, qd + (uint64_t)((kk >> 2) * 1024 + (kk & 3) * 2),
+                          kd + (uint64_t)((uint32_t)(kk >> 2) * kblk16 + (uint32_t)(kk & 3) * 2u), idesc_s, kk > 0 ? 1u : 0u);
             umma_commit(acc_full);  // S ready
-            ++n_acc_use;
-            mbar_wait(p_full, n_p & 1);  // P written (and S fully read)
-            ++n_p;
-            tc_fence_after();
-            acc = 0;
-            for (int k16 = 0; k16 < g.KP / 16; ++k16) {
-              const uint64_t ad = make_desc_sw128(Ps + (uint32_t)(k16 >> 2) * 128u * 128u + (uint32_t)(k16 & 3) * 32u, 16u, 1024u);
-              const uint64_t bd = make_desc_sw128(Vs + (uint32_t)k16 * 2048u, (uint32_t)g.KP * 128u, 1024u);
-              umma_bf16(tmem_base, ad, bd, idesc_o, acc);
-              acc = 1;
-            }
-            umma_commit(acc_full);  // O ready (second use of the accumulator by this head)
-            ++n_acc_use;
           }
+          __syncwarp();
+          ++n_acc_use;
+          mbar_wait(p_full, n_p & 1);  // P written (and S fully read)
+          ++n_p;
+          tc_fence_after();
+          if (elect_one()) {
+#pragma unroll 4
+            for (int k16 = 0; k16 < n16; ++k16)
+              umma_bf16(tmem_base, pd + (uint64_t)((k16 >> 2) * 1024 + (k16 & 3) * 2), vd + (uint64_t)(k16 * 128), idesc_o, k16 > 0 ? 1u : 0u);
+            umma_commit(acc_full);  // O ready (second use of the accumulator by this head)
+          }
+          __syncwarp();
+          ++n_acc_use;
         }
       }
     }
-    __syncwarp();
   } else {
     // ======================================================================== producers / softmax / epilogues
     uint32_t n_acc = 0;   // acc_full phases consumed
