@@ -195,14 +195,35 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
 }
+// packed fp32 pairs (sm_100: FFMA2 / FADD2 / FMUL2 -- one issue slot for two lanes of arithmetic; the producer warps are
+// bound by their own instruction latency, one warp per scheduler)
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
 // SiLU whose result is rounded to bf16 right away: x*sigmoid(x) = h + h*tanh(h), h = x/2, with the single-instruction
-// hardware tanh (MUFU.TANH, rel. error ~2^-11 -- below bf16's 2^-9 rounding step); 3 instructions instead of ~7 and one
-// MUFU op instead of two on the producers' critical path
-__device__ __forceinline__ float silu_fast(float x) {
-  const float h = 0.5f * x;
+// hardware tanh (MUFU.TANH, rel. error ~2^-11 -- below bf16's 2^-9 rounding step)
+__device__ __forceinline__ float tanh_fast(float h) {
   float t;
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
-  return fmaf(h, t, h);
+  return t;
 }
 
 inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
@@ -259,7 +280,9 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
   int4* rowmeta1 = reinterpret_cast<int4*>(tabs + pl.off_rowmeta1);        // [NT] same for the seg-1 K steps
   int4* colmeta = reinterpret_cast<int4*>(tabs + pl.off_colmeta);          // [NT]: (out offset | -1, residual offset, slot, batch row)
   float2* rowstat = reinterpret_cast<float2*>(tabs + pl.off_rowstat);      // [rows0] LayerNorm (mean, rstd) per slot
-  float2* coef = reinterpret_cast<float2*>(tabs + pl.off_coef);            // [slots][ch_cap] (a, s): y = a*x + s
+  // [slots][ch_cap / 2] (a_even, a_odd, s_even, s_odd): y = a*x + s per channel pair (operands of one FFMA2); with SiLU the
+  // halved coefficients, i.e. h = x/2 of silu(x) = h + h*tanh(h)
+  float* coef = reinterpret_cast<float*>(tabs + pl.off_coef);
   const int ch_cap = pl.ch_cap;
   // epilogue scratch aliases the weight ring (all MMAs have completed by then)
   // [0, kSredBytes): per-warp GroupNorm fine-group sums; then the fp32 staging tile [columns][128] (the whole partial
@@ -383,6 +406,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
     const bool need_coef = (has_gn || has_film) && my_ch > 0;
     const int cpg = has_gn ? Ct / p.G : 1;
     const int zoff = p.out_off0 + z * p.out_off_phase;
+    const float hs = (affine && p.act == ACT_SILU) ? 0.5f : 1.0f;  // SiLU works on x/2: folded into the coefficients
 
     // ---- tables that do not depend on earlier kernels (built while the previous layer is still running)
     // (the conditioning rows are written before the step's kernel chain starts)
@@ -453,9 +477,14 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
               P *= f1;
               Q = fmaf(Q, f1, __ldg(fp + Ct + ch));
             }
-            if (!has_gn) P *= (ch >= S0.s[0].C ? S0.s[1] : S0.s[0]).scale;  // final: no statistics to wait for
+            if (!has_gn) {  // final: no statistics to wait for
+              P *= (ch >= S0.s[0].C ? S0.s[1] : S0.s[0]).scale * hs;
+              Q *= hs;
+            }
           }
-          coef[(size_t)bl * ch_cap + c] = make_float2(P, Q);
+          float* cd = coef + ((size_t)bl * ch_cap + (c & ~1)) * 2 + (c & 1);
+          cd[0] = P;
+          cd[2] = Q;
         }
       }
     }
@@ -529,41 +558,50 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
         const int prow = mz >> 8;
         uint4 o = make_uint4(0u, 0u, 0u, 0u);
         if ((okm >> u) & 1u) {
-          float v[8];
-          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[u]);
+          const uint32_t w4[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
+          uint64_t x2[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            v[2 * e] = __low2float(h[e]);
-            v[2 * e + 1] = __high2float(h[e]);
-          }
+          for (int e = 0; e < 4; ++e) x2[e] = pk2(__uint_as_float(w4[e] << 16), __uint_as_float(w4[e] & 0xffff0000u));
           if (s1) {
+            const uint64_t sc2 = pk2(sscale, sscale);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] *= sscale;
+            for (int e = 0; e < 4; ++e) x2[e] = fmul2(x2[e], sc2);
           } else if (affine) {
             if (need_coef) {
-              const float4* cf = reinterpret_cast<const float4*>(coef + (size_t)((mz & 255) - b_first) * ch_cap + (c0 - ch_base));
-              const float4 k0 = cf[0], k1 = cf[1], k2 = cf[2], k3 = cf[3];
-              v[0] = fmaf(k0.x, v[0], k0.y); v[1] = fmaf(k0.z, v[1], k0.w);
-              v[2] = fmaf(k1.x, v[2], k1.y); v[3] = fmaf(k1.z, v[3], k1.w);
-              v[4] = fmaf(k2.x, v[4], k2.y); v[5] = fmaf(k2.z, v[5], k2.w);
-              v[6] = fmaf(k3.x, v[6], k3.y); v[7] = fmaf(k3.z, v[7], k3.w);
+              const float4* cf = reinterpret_cast<const float4*>(coef + ((size_t)((mz & 255) - b_first) * ch_cap + (c0 - ch_base)) * 2);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float4 kq = cf[e];
+                x2[e] = ffma2(pk2(kq.x, kq.y), x2[e], pk2(kq.z, kq.w));
+              }
             } else {
+              const uint64_t sc2 = pk2(sscale * hs, sscale * hs);
 #pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] *= sscale;
+              for (int e = 0; e < 4; ++e) x2[e] = fmul2(x2[e], sc2);
             }
-            if (p.act == ACT_SILU) {
+            if (p.act == ACT_SILU) {  // x2 holds h = x/2: silu(x) = h + h*tanh(h) (hardware tanh)
 #pragma unroll
-              for (int e = 0; e < 8; ++e) v[e] = silu_fast(v[e]);
+              for (int e = 0; e < 4; ++e) {
+                float h0, h1;
+                upk2(x2[e], h0, h1);
+                x2[e] = ffma2(x2[e], pk2(tanh_fast(h0), tanh_fast(h1)), x2[e]);
+              }
             }
           } else {
             const float2 ms = rowstat[idx];
+            const uint64_t nm2 = pk2(-ms.x, -ms.x), rs2 = pk2(ms.y, ms.y);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = (v[e] - ms.x) * ms.y;
+            for (int e = 0; e < 4; ++e) x2[e] = fmul2(fadd2(x2[e], nm2), rs2);
           }
-          o.x = pack2(v[0], v[1]);
-          o.y = pack2(v[2], v[3]);
-          o.z = pack2(v[4], v[5]);
-          o.w = pack2(v[6], v[7]);
+          float y0, y1;
+          upk2(x2[0], y0, y1);
+          o.x = pack2(y0, y1);
+          upk2(x2[1], y0, y1);
+          o.y = pack2(y0, y1);
+          upk2(x2[2], y0, y1);
+          o.z = pack2(y0, y1);
+          upk2(x2[3], y0, y1);
+          o.w = pack2(y0, y1);
         }
         *reinterpret_cast<uint4*>(pan + (size_t)prow * 128 + (size_t)((kc ^ (prow & 7)) * 16)) = o;
       }
@@ -679,10 +717,12 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
             for (int c = tid; c < my_ch; c += kProducers) {
               const int ch = ch_base + c;
               const int g = cpg_shift >= 0 ? ch >> cpg_shift : ch / cpg;
-              const float2 pq = coef[(size_t)bl * ch_cap + c];
-              const float rp = (ch < Ct) ? grstd[bl * 32 + g] * pq.x : 0.f;
+              float* cd = coef + ((size_t)bl * ch_cap + (c & ~1)) * 2 + (c & 1);
+              const float rp = (ch < Ct) ? grstd[bl * 32 + g] * cd[0] : 0.f;
               const float scale = (ch >= S0.s[0].C ? S0.s[1] : S0.s[0]).scale;
-              coef[(size_t)bl * ch_cap + c] = make_float2(rp * scale, (ch < Ct) ? fmaf(-gmean[bl * 32 + g], rp, pq.y) : 0.f);
+              const float sh = (ch < Ct) ? fmaf(-gmean[bl * 32 + g], rp, cd[2]) : 0.f;
+              cd[0] = rp * scale * hs;
+              cd[2] = sh * hs;
             }
           }
           bar_sync_producers();
