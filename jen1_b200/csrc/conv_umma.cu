@@ -1093,9 +1093,16 @@ UmmaPlan conv_umma_plan(const ConvParams& p, bool want_stats, int num_sms) {
     const double wkb = (double)steps * ntaps * 16.0;
     const double prefetch = c.stages * 16.0;
     const double cols = c.splitk > 1 ? (double)((c.NT + c.splitk - 1) / c.splitk) : (double)c.NT;
-    double t = steps * (0.6 + 0.15 * rows / 16.0);      // K loop: fixed round trip + panel rows
+    static double kstep_us = -1.0, xch_us = -1.0;  // planner experiments: JEN1_KSTEP_US (fixed cost of a K step), JEN1_XCH_US (per exchanged column)
+    if (kstep_us < 0.0) {
+      const char* e1 = getenv("JEN1_KSTEP_US");
+      const char* e2 = getenv("JEN1_XCH_US");
+      kstep_us = e1 ? atof(e1) : 0.45;  // (0.6 before the MMA issue became warp-uniform; A/B in one GPU call: -0.75 % per step)
+      xch_us = e2 ? atof(e2) : 0.16;
+    }
+    double t = steps * (kstep_us + 0.15 * rows / 16.0);      // K loop: fixed round trip + panel rows
     t += (wkb > prefetch ? (wkb - prefetch) / 60.0 : 0.0);  // weight bytes beyond the PDL prefetch at ~60 GB/s per SM
-    t += (c.splitk > 1 ? 0.12 * cols + 0.6 : 0.04 * cols);  // epilogue columns (DSMEM reduction vs TMEM), cluster exchange
+    t += (c.splitk > 1 ? xch_us * cols + 0.6 : 0.04 * cols);  // epilogue columns (DSMEM reduction vs TMEM), cluster exchange
     return t * waves * over_mul + over_add;
   };
   static const int cand[] = {16, 32, 48, 64, 96, 128, 192, 256};

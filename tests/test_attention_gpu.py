@@ -44,7 +44,7 @@ def rel_l2(a, b):
     (3, 129, 4, 16, False, "flash"), (2, 300, 4, 32, True, "flash"), (1, 1137, 8, 64, False, "tcgen05"),
     (1, 1137, 8, 64, True, "tcgen05"), (1, 4545, 8, 64, False, "tcgen05"), (1, 4545, 8, 64, True, "tcgen05"),
     (1, 4545, 8, 128, False, "tcgen05"), (2, 285, 8, 128, True, "flash"), (2, 256, 2, 64, False, "flash"),
-    (1, 257, 2, 64, True, "flash"),
+    (1, 257, 2, 64, True, "flash"), (2, 130, 4, 64, True, "flash"), (2, 385, 2, 128, False, "flash"), (1, 700, 2, 16, True, "flash"),
 ])
 def test_attention_kernels_match_torch_fp32(engine, B, N, H, d, causal, impl):
     g = torch.Generator().manual_seed(1000 + N + d)
@@ -67,3 +67,21 @@ def test_key_tiled_kernel_equals_single_tile_kernel_where_both_apply(engine):
     a = engine.attention(qkv, 8, causal=True, impl="tcgen05")
     b = engine.attention(qkv, 8, causal=True, impl="flash")
     assert rel_l2(a, b) < 5e-3
+
+
+@pytest.mark.parametrize("d,causal", [(64, False), (128, True), (32, False)])
+def test_key_tiled_kernel_rescales_when_the_row_maximum_keeps_growing(engine, d, causal):
+    """The key-tiled kernel keeps its output accumulator in TMEM and rescales it in place only when a row maximum moves
+    by more than 2^8: keys whose magnitude grows along the sequence make the maximum jump in (almost) every key tile, so
+    this drives the rescale path (tcgen05.ld / st of the accumulator) on late tiles, not only on the first one."""
+    B, N, H = 2, 900, 2
+    g = torch.Generator().manual_seed(77 + d)
+    qkv = torch.randn(B, N, 3 * H * d, generator=g)
+    ramp = torch.linspace(0.5, 6.0, N).view(1, N, 1)
+    qkv[:, :, H * d:2 * H * d] *= ramp  # keys
+    qkv = qkv.to(torch.bfloat16).to(DEV)
+    ref = torch_reference(qkv, H, causal)
+    out = engine.attention(qkv, H, causal=causal, impl="flash")
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all()
+    assert rel_l2(out, ref) < 1e-2
