@@ -1,24 +1,27 @@
 // Key-tiled tcgen05 / TMEM attention with online softmax for bf16 storage on sm_100a (reference jen1/model/blocks.py:355-380
 // AttentionBase.forward, causal mask :304-319) -- the general-length companion of attn_umma.cu (which holds a whole head's
-// keys in one TMEM accumulator, <= 256 keys, the model's own shapes).  One CTA = (batch row, head, 128-query tile); the
-// keys stream through in tiles of 128:
+// keys in one TMEM accumulator, <= 256 keys, the model's own shapes).  One CTA = (batch row, head, 256 queries = two query
+// tiles of 128); the keys stream through in tiles of 128:
 //
 //   loaders (warps 5-7)   K_j, V_j tiles -> shared-memory rings (TMA: one thread per ring, or cp.async; K-major 128-byte-
 //                         swizzled rows; V is consumed as an MN-major operand straight from its [key][channel] layout).
-//                         The K and the V ring have their OWN full / empty barriers: a K stage is free as soon as S_j has
-//                         been computed, a whole tile period before the V stage (free after P_j V_j), so the load of
-//                         K_{j+NS} is never on the critical path of S_{j+NS} even with a two-stage ring (d = 128)
-//   MMA issuer (warp 4)   S_j = Q K_j^T  -> TMEM buffer j & 1 (2 x 128 columns);  O_j = P_j V_j -> TMEM buffer 2 + (j & 1).
-//                         S_{j+1} is issued BEFORE P_j V_j, so the tensor core computes the next logits while the softmax
-//                         warps are busy with the current ones
-//   softmax (warps 0-3)   thread == query row (TMEM lane): running max m and sum l in base 2 (online softmax), P_j = 2^(s-m)
-//                         rounded to bf16 into a swizzled A tile (double-buffered: writing P_j does not wait for
-//                         P_{j-1} V_{j-1}); the partial product O_j comes back from TMEM and is folded
-//                         into register accumulators  o = o * 2^(m_old - m_new) + O_j  -- no read-modify-write of TMEM and no
-//                         separate correction pass
+//                         The K and the V ring have their OWN full / empty barriers: a K stage is free as soon as the S_j of
+//                         both query tiles have been computed, a whole tile period before the V stage (free after P_j V_j),
+//                         so the load of the next K tile is never on the critical path of the next S
+//   MMA issuer (warp 4)   S^g_j = Q^g K_j^T -> TMEM columns [g * 128, +128) for both query tiles g, issued one key tile AHEAD of
+//                         the softmax;  O^g += P^g_j V_j -> TMEM columns [256 + g * 128, +d), accumulated over ALL key tiles.
+//                         Warp-uniform control flow, one elect.sync lane issues (a divergent lane-0 issuer costs ~85 clocks
+//                         per MMA: the compiler wraps every tcgen05 instruction in an elect-and-branch loop)
+//   softmax (warps 0-3: query tile 0, warps 8-11: query tile 1)
+//                         thread == query row == TMEM lane with the row's 128 logits of a key tile in registers: maximum, sum
+//                         and scaling are private to the thread (no exchange).  P_j = 2^(s - m) rounded to bf16 into a
+//                         swizzled A tile.  The reference maximum m may lag the row's true maximum by up to 2^8; the output
+//                         accumulator stays in TMEM and is rescaled in place (tcgen05.ld / st) only when a maximum moves by
+//                         more than that -- no per-tile read-back, no register accumulator, no correction pass
 //
-// Six mbarrier pipelines connect them (k_full/k_empty, v_full/v_empty, s_full/s_empty, p_full, o_full/o_empty).  Causal tiles that lie
-// completely above the diagonal are skipped.  Keys beyond the key count are zero-filled and excluded from the softmax.
+// Mbarrier pipelines: k_full/k_empty, v_full/v_empty (rings), s_full/s_empty, p_full, o_full (one each per query tile).  Causal
+// tiles that lie completely above a query tile's diagonal are skipped for that tile.  Keys beyond the key count are zero-filled
+// and excluded from the softmax.
 #include <cuda.h>
 #include <float.h>
 #include <stdio.h>
@@ -209,7 +212,6 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
 }
-__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
 // tcgen05.st: 16 consecutive columns of this thread's TMEM lane
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {

@@ -87,7 +87,8 @@ cudaError_t attention_init();   // per-device function attributes (call after cu
 cudaError_t attn_umma_init();
 // tcgen05 / TMEM implementation for bf16 storage (attn_umma.cu): head dim in {16, 32, 64, 128}, up to 256 keys
 bool attn_umma_supported(const AttnParams& p);
-// key-tiled online-softmax tcgen05 attention for any self-attention length (attn_flash.cu)
+// key-tiled online-softmax tcgen05 attention for any self-attention length (attn_flash.cu): two query tiles per CTA,
+// TMA-staged K / V rings, output accumulator resident in TMEM
 bool attn_flash_supported(const AttnParams& p);
 cudaError_t attn_flash_init();
 cudaError_t launch_attention_flash(const AttnParams& p, bool pdl, cudaStream_t stream);
