@@ -83,6 +83,37 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
   } while (!done);
 }
+// JEN1_ISSUER_WAIT (A/B, profiles/r02_ab_issue_and_planner.txt): how the weight-stream / MMA warps wait.  0 = pure polling
+// (test_wait), 1 = suspending try_wait for the waits completed by thread arrivals (p_full) only, 2 = for all their waits.
+// The issuer warps share schedulers 0 and 1 with producer warps 0 and 1 of this CTA and of the co-resident one (whose issuer
+// warps already wait while this kernel runs): polling there takes issue slots from the warps on the critical path.
+// Measured: 2 is 1.1 % / 1.7 % faster per step than 0 (config 3 / 2), 1 is neutral.  (The late wake-up of try_wait noted at
+// mbar_wait was observed with the former single-lane issuers; the producer / epilogue warps keep polling.)
+#ifndef JEN1_ISSUER_WAIT
+#define JEN1_ISSUER_WAIT 2
+#endif
+__device__ __forceinline__ void mbar_wait_suspend(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void issuer_wait(uint64_t* bar, uint32_t parity, int kind) {  // kind 0: thread arrivals, 1: async completions
+#if JEN1_ISSUER_WAIT == 2
+  mbar_wait_suspend(bar, parity);
+#elif JEN1_ISSUER_WAIT == 1
+  if (kind == 0) mbar_wait_suspend(bar, parity); else mbar_wait(bar, parity);
+#else
+  mbar_wait(bar, parity);
+#endif
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -331,7 +362,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
       const bf16* src = s1 ? A.w1 + ((size_t)mt * pl.steps1 + (t - pl.steps0)) * (kABytes / 2)
                            : A.w0 + (((size_t)(mt * p.nphase + z) * pl.steps0 + t) * ntaps0) * (kABytes / 2);
       for (int j = 0; j < ntp; ++j) {
-        if (k > 0) mbar_wait(&a_empty[s], (uint32_t)((k - 1) & 1));
+        if (k > 0) issuer_wait(&a_empty[s], (uint32_t)((k - 1) & 1), 1);
         if (elect_one()) {
           mbar_expect_tx(&a_full[s], kABytes);
           bulk_g2s(a_ring + (size_t)s * kABytes, src + (size_t)j * (kABytes / 2), kABytes, &a_full[s]);
@@ -362,12 +393,12 @@ __global__ void __launch_bounds__(kThreads, 2) conv_umma_kernel(const __grid_con
       const int n = t - st0, pb = n & 1;
       const bool s1 = t >= pl.steps0;
       const int ntp = s1 ? 1 : ntaps0;
-      mbar_wait(&p_full[pb], (uint32_t)((n >> 1) & 1));
+      issuer_wait(&p_full[pb], (uint32_t)((n >> 1) & 1), 0);
       tc_fence_after();
       const uint32_t pbase16 = (uint32_t)pb * (panel_bytes >> 4);  // descriptor address units (16 bytes)
       for (int j = 0; j < ntp; ++j) {
         const uint32_t prow = s1 ? 0u : (uint32_t)tapg[j].x;
-        mbar_wait(&a_full[s], (uint32_t)(k & 1));
+        issuer_wait(&a_full[s], (uint32_t)(k & 1), 1);
         tc_fence_after();
         if (t == st0 && j == 0 && lane == 0) TL_MARK(9);
         // K advances by 32 bytes inside the swizzle atom: +2 in the (address >> 4) field of the descriptor
