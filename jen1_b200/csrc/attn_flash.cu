@@ -70,7 +70,7 @@ __device__ __forceinline__ void tma_load_tile(void* dst, const CUtensorMap* tm, 
 }
 // suspending wait (hardware time-limited sleep) for the warps whose waits are long: keeps them off the issue slots
 #ifndef JEN1_FA_POLL
-#define JEN1_FA_POLL 0  // A/B: 1 = the MMA issuer polls (test_wait) instead of the suspending try_wait
+#define JEN1_FA_POLL 0  // A/B: 1 = the MMA issuer polls (test_wait) instead of the suspending try_wait (measured: -9 %)
 #endif
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
   const uint32_t a = smem_u32(bar);
@@ -88,24 +88,9 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-#ifndef JEN1_FA_HINT
-#define JEN1_FA_HINT 0  // A/B: > 0 = suspend-time hint (ns) of the MMA issuer's try_wait
-#endif
 __device__ __forceinline__ void mma_wait(uint64_t* bar, uint32_t parity) {
 #if JEN1_FA_POLL
   mbar_wait(bar, parity);
-#elif JEN1_FA_HINT > 0
-  const uint32_t a = smem_u32(bar);
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(a), "r"(parity), "r"((uint32_t)JEN1_FA_HINT)
-        : "memory");
-  } while (!done);
 #else
   mbar_wait_sleep(bar, parity);
 #endif
@@ -256,10 +241,7 @@ __global__ void __launch_bounds__(kFaThreads, 1) attn_flash_kernel(const __grid_
   // K / V ring depths (what fits next to two Q and two P tiles).  S_{j+1} is issued a whole tile period ahead of its use,
   // so K_{j+1} (loaded once S_j has completed) has that period to arrive even with ONE stage; V_j is needed at the END of
   // tile j, one stage would put its load (started after P_{j-1} V_{j-1}) on the critical path: d = 128 gives V the two stages
-#ifndef JEN1_FA_NSK128
-#define JEN1_FA_NSK128 1
-#endif
-  const int NSK = d <= 64 ? 4 : JEN1_FA_NSK128, NSV = d <= 64 ? 2 : 3 - JEN1_FA_NSK128;
+  const int NSK = d <= 64 ? 4 : 1, NSV = 2;  // (K2 / V1 at d = 128 measured the same)
   uint8_t* Qs = smem;                                 // [2 query tiles]
   uint8_t* Ks = Qs + 2 * tile_bytes;                  // [NSK stages]
   uint8_t* Vs = Ks + NSK * tile_bytes;                // [NSV stages]
