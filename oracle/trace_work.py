@@ -109,6 +109,48 @@ def trace(model, T: int, emb_len: int, emb_feat: int, in_ch: int, ctx_ch: int):
     return rec
 
 
+def trace_codec(T: int):
+    """The same for the Encodec-48k decoder, on the Hugging Face port of the SEANet decoder (the pip package
+    the reference imports is absent offline): 2*MAC of every Conv1d / ConvTranspose1d / LSTM call for one sample of T frames."""
+    from transformers import EncodecConfig
+    from transformers.models.encodec.modeling_encodec import EncodecDecoder
+    from jen1_b200.codec_config import CodecDesc
+    desc = CodecDesc()
+    cfg = EncodecConfig(sampling_rate=48000, audio_channels=desc.channels, normalize=True, chunk_length_s=1.0, overlap=0.01,
+                        hidden_size=desc.dimension, num_filters=desc.n_filters, num_residual_layers=1,
+                        upsampling_ratios=list(desc.ratios), norm_type="time_group_norm", kernel_size=desc.kernel_size,
+                        last_kernel_size=desc.last_kernel_size, residual_kernel_size=desc.residual_kernel_size,
+                        dilation_growth_rate=2, use_causal_conv=False, pad_mode="reflect", compress=desc.compress,
+                        num_lstm_layers=desc.lstm_layers, trim_right_ratio=1.0, use_conv_shortcut=True)
+    dec = EncodecDecoder(cfg).eval()
+    rec = {"flops": 0, "conv_out_elems": 0, "samples": 0}
+
+    def conv_hook(mod, inp, out):
+        x = inp[0]
+        k = mod.kernel_size[0]
+        if isinstance(mod, torch.nn.ConvTranspose1d):
+            rec["flops"] += 2 * x.shape[1] * x.shape[-1] * mod.out_channels * k
+        else:
+            rec["flops"] += 2 * mod.out_channels * out.shape[-1] * mod.in_channels * k
+        rec["conv_out_elems"] += out.numel()
+
+    def lstm_hook(mod, inp, out):
+        L = inp[0].shape[0] if not mod.batch_first else inp[0].shape[1]
+        for layer in range(mod.num_layers):
+            cin = mod.input_size if layer == 0 else mod.hidden_size
+            rec["flops"] += 2 * L * 4 * mod.hidden_size * (cin + mod.hidden_size)
+
+    for m in dec.modules():
+        if isinstance(m, (torch.nn.Conv1d, torch.nn.ConvTranspose1d)):
+            m.register_forward_hook(conv_hook)
+        elif isinstance(m, torch.nn.LSTM):
+            m.register_forward_hook(lstm_hook)
+    with torch.no_grad():
+        y = dec(torch.randn(1, desc.dimension, T, generator=torch.Generator().manual_seed(T)))
+    rec["samples"] = y.shape[-1]
+    return rec
+
+
 def main():
     torch.manual_seed(0)
     model = ref_import.build_reference_unet().eval()
@@ -119,6 +161,10 @@ def main():
         out["per_T"][str(T)] = trace(model, T, kw["context_embedding_max_length"], kw["context_embedding_features"],
                                      kw["in_channels"], kw["context_channels"][0])
         print(T, out["per_T"][str(T)])
+    out["codec_decoder_per_T"] = {}
+    for T in (150, 600):
+        out["codec_decoder_per_T"][str(T)] = trace_codec(T)
+        print("codec", T, out["codec_decoder_per_T"][str(T)])
     with open(GOLD, "w") as f:
         json.dump(out, f, indent=1)
     print("wrote", GOLD)

@@ -53,3 +53,16 @@ def test_step_bytes_of_the_benchmarked_configurations():
     assert c2["rows"] == 2 and c3["rows"] == 8
     assert abs(c2["total_bytes"] / 1e6 - 548.9) < 1.0   # 498.3 MB of weights + 2 rows x 25.3 MB
     assert abs(c3["total_bytes"] / 1e6 - 1032.6) < 1.5  # 498.3 MB of weights + 8 rows x 66.8 MB
+
+
+@pytest.mark.parametrize("T", [150, 600])
+def test_codec_work_model_matches_the_decoder_trace(T):
+    """Encodec-48k decoder: `codec_config.decode_work` against the forward-hook trace of the Hugging Face
+    port of the SEANet decoder -- 2*MAC of every Conv1d / ConvTranspose1d / LSTM call, exactly (181 GFLOP per 30 s sample)."""
+    from jen1_b200.codec_config import CodecDesc, decode_work
+    with open(os.path.join(HERE, "golden", "work_trace.json")) as f:
+        r = json.load(f)["codec_decoder_per_T"][str(T)]
+    w = decode_work(CodecDesc(), T)
+    assert int(w["flops"]) == r["flops"]
+    assert int(w["samples"]) == r["samples"] == 320 * T
+    assert abs(decode_work(CodecDesc(), 4545)["flops"] / 1e9 - 181.2) < 0.5
